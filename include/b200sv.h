@@ -1,0 +1,156 @@
+/* b200sv -- B200-native statevector engine: the thin C ABI.
+ *
+ * This is the drop-in boundary behind Qiskit Aer's C++ `QubitVector` method
+ * set (the duck-typed `statevec_t` of `Statevector::State`,
+ * /root/reference/src/simulators/statevector/statevector_state.hpp:100-101).
+ * Every entry point names the reference method it replaces (file:line refer
+ * to /root/reference/src/simulators/statevector/ unless stated otherwise).
+ * Style precedent: the reference's own C facade,
+ * contrib/runtime/aer_runtime.cpp:19-240 (opaque handle, plain scalars).
+ *
+ * Conventions (identical to the reference, qubitvector.hpp:225-411):
+ *   - qubit q <-> bit q of the amplitude index (little endian);
+ *   - qubit lists are uint64_t arrays, controls first, target(s) last;
+ *   - matrices are complex<double>, interleaved (re,im), COLUMN-major
+ *     vectorised: mat[i + dim*j] = M[i][j]; qubits[0] = least significant
+ *     matrix bit; diagonals have 2^k entries;
+ *   - Pauli strings: pauli[k-1-i] acts on qubits[i];
+ *   - random draws (rnds) are uniform in [0,1) and come from the HOST
+ *     (Aer's RngEngine); only draws cross this ABI.
+ * One handle = `num_states` statevectors of `num_qubits` qubits, stored
+ * contiguously on ONE device (state s occupies amplitudes [s<<n, (s+1)<<n)).
+ * num_states > 1 is the batched-shot container (qubitvector_thrust.hpp:
+ * 1184-1214): gates act on every state, reductions return one value per state.
+ * A sharded state uses one handle per GPU (= per process) with
+ * b200sv_set_chunk() describing which slice of the global register it holds.
+ *
+ * All functions return 0 on success, non-zero on error (then
+ * b200sv_last_error() describes it; the C++ adapter re-throws, matching the
+ * reference's exception behaviour, circuit_executor.hpp:574,726).
+ * There is NO CPU fallback: without a CUDA device every call fails loudly.
+ * Thread-safety: a handle may be used by one host thread at a time; every call
+ * selects the handle's device first (as the reference does,
+ * chunk/device_chunk_container.hpp:131-135).
+ */
+#ifndef B200SV_H
+#define B200SV_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200sv_state *b200sv_handle;
+
+enum { B200SV_F64 = 64, B200SV_F32 = 32 };
+
+/* ---- lifetime / configuration ------------------------------------------ */
+/* ABI version (bumped on any signature change). */
+int b200sv_version(void);
+const char *b200sv_last_error(void);
+/* number of visible CUDA devices (chunk_manager.hpp:166-190) */
+int b200sv_device_count(int *count);
+
+/* QubitVector(), set_num_qubits (qubitvector.hpp:922; thrust :860 chunk_setup).
+ * Allocates num_states << num_qubits amplitudes on `device` and a private stream. */
+int b200sv_create(b200sv_handle *out, int num_qubits, int64_t num_states, int precision, int device);
+/* Same, but adopts device memory + stream owned by the caller (e.g. a torch
+ * tensor / torch stream used for NCCL plumbing).  dev_ptr must hold
+ * num_states << num_qubits amplitudes of the given precision, 16-byte aligned. */
+int b200sv_create_external(b200sv_handle *out, int num_qubits, int64_t num_states, int precision, int device,
+                           void *dev_ptr, void *cuda_stream);
+int b200sv_destroy(b200sv_handle h);
+int b200sv_num_qubits(b200sv_handle h, int *n);
+/* raw device pointer / stream (for peer exchange and torch interop) */
+int b200sv_device_ptr(b200sv_handle h, void **dev_ptr);
+int b200sv_stream(b200sv_handle h, void **cuda_stream);
+/* chunk_setup(chunk_bits, num_qubits, chunk_index, ...) (qubitvector.hpp:1045;
+ * thrust :860): this handle is chunk `chunk_index` of a register of
+ * `global_num_qubits` qubits; local qubits are [0, num_qubits). Controls /
+ * diagonal qubits >= num_qubits are then resolved from chunk_index without
+ * data movement (thrust_kernels.hpp:1190,1342,2004 base_index_). */
+int b200sv_set_chunk(b200sv_handle h, int global_num_qubits, uint64_t chunk_index);
+/* synchronize() (qubitvector_thrust.hpp:1088-1099) */
+int b200sv_synchronize(b200sv_handle h);
+/* set_sample_measure_index_size is accepted for API parity and ignored. */
+
+/* ---- data -------------------------------------------------------------- */
+int b200sv_initialize(b200sv_handle h);                 /* initialize(): |0..0> in every state (qubitvector.hpp:1088) */
+int b200sv_zero(b200sv_handle h);                       /* zero() (qubitvector.hpp:903) */
+/* initialize_from_data / copy_to_vector (qubitvector.hpp:1153; thrust CopyIn/CopyOut):
+ * host <-> device copy of `count` amplitudes starting at amplitude `offset`
+ * (over the whole batch), in the handle's precision. */
+int b200sv_upload(b200sv_handle h, const void *host, uint64_t offset, uint64_t count);
+int b200sv_download(b200sv_handle h, void *host, uint64_t offset, uint64_t count);
+/* initialize_component(qubits, state) (qubitvector.hpp:879-900) */
+int b200sv_initialize_component(b200sv_handle h, const uint64_t *qubits, int k, const double *state);
+/* checkpoint()/revert(keep)/inner_product() (qubitvector.hpp:995-1041) -- device-resident copy */
+int b200sv_checkpoint(b200sv_handle h);
+int b200sv_revert(b200sv_handle h, int keep);
+int b200sv_inner_product(b200sv_handle h, double *re, double *im);
+
+/* ---- gates ------------------------------------------------------------- */
+/* apply_matrix (qubitvector.hpp:1299 -> transformer.hpp:90) */
+int b200sv_apply_matrix(b200sv_handle h, const uint64_t *qubits, int k, const double *mat);
+/* apply_diagonal_matrix (qubitvector.hpp:1343 -> transformer.hpp:235) */
+int b200sv_apply_diagonal(b200sv_handle h, const uint64_t *qubits, int k, const double *diag);
+/* apply_multiplexer (qubitvector.hpp:1305) */
+int b200sv_apply_multiplexer(b200sv_handle h, const uint64_t *ctrl, int nc, const uint64_t *tgt, int nt,
+                             const double *mat);
+/* apply_permutation_matrix (qubitvector.hpp:1354) pairs = 2*npairs matrix indices */
+int b200sv_apply_permutation(b200sv_handle h, const uint64_t *qubits, int k, const uint64_t *pairs, int npairs);
+/* apply_mcx / apply_mcy / apply_mcswap (qubitvector.hpp:1447,1489,1540) -- bit exact */
+int b200sv_apply_mcx(b200sv_handle h, const uint64_t *qubits, int k);
+int b200sv_apply_mcy(b200sv_handle h, const uint64_t *qubits, int k);
+int b200sv_apply_mcswap(b200sv_handle h, const uint64_t *qubits, int k);
+/* apply_mcphase (qubitvector.hpp:1576) */
+int b200sv_apply_mcphase(b200sv_handle h, const uint64_t *qubits, int k, double re, double im);
+/* apply_mcu (qubitvector.hpp:1615): 2x2 column-major on the last qubit, incl. the
+ * reference's exact-== routing to phase / diagonal */
+int b200sv_apply_mcu(b200sv_handle h, const uint64_t *qubits, int k, const double *mat);
+/* apply_pauli (qubitvector.hpp:2393) */
+int b200sv_apply_pauli(b200sv_handle h, const uint64_t *qubits, int k, const char *pauli, double cre, double cim);
+/* apply_batched_pauli_ops (qubitvector_thrust.hpp:2892, batched_pauli_func :2819):
+ * per-state Pauli given as num_states x {x_mask, z_mask, num_y, apply(0/1)} */
+int b200sv_apply_batched_pauli(b200sv_handle h, const uint64_t *masks4);
+
+/* ---- reductions (out has num_states entries unless noted) --------------- */
+int b200sv_norm(b200sv_handle h, double *out);          /* norm() (qubitvector.hpp:1879) */
+/* norm(qubits, mat) (qubitvector.hpp:1889) -- Kraus probability ||M psi||^2 */
+int b200sv_norm_matrix(b200sv_handle h, const uint64_t *qubits, int k, const double *mat, double *out);
+/* probabilities(qubits) (qubitvector.hpp:2108): out[num_states][2^k], ALL outcomes in one pass */
+int b200sv_probabilities(b200sv_handle h, const uint64_t *qubits, int k, double *out);
+/* sample_measure(rnds) (qubitvector.hpp:2149): out[shots] (state 0 only when num_states == 1;
+ * for batches rnds/out are [num_states][shots]).  Non-destructive. */
+int b200sv_sample_measure(b200sv_handle h, const double *rnds, int64_t shots, uint64_t *out);
+/* expval_pauli (qubitvector.hpp:2300) */
+int b200sv_expval_pauli(b200sv_handle h, const uint64_t *qubits, int k, const char *pauli, double pre, double pim,
+                        double *out);
+/* expval_pauli with a pair chunk (qubitvector.hpp:2350; thrust_kernels.hpp:2413):
+ * the X-part crosses a global qubit, pair_dev_ptr is the partner chunk's device memory. */
+int b200sv_expval_pauli_pair(b200sv_handle h, const uint64_t *qubits, int k, const char *pauli,
+                             const void *pair_dev_ptr, uint64_t z_count, uint64_t z_count_pair, double pre,
+                             double pim, double *out);
+
+/* ---- global-qubit exchange (sharded states) ------------------------------ */
+/* apply_chunk_swap(qubits, chunk) (qubitvector.hpp:1753; thrust :1677, CSwapChunk_func
+ * thrust_kernels.hpp:1884): swap local qubit `local_q` with the global qubit that
+ * distinguishes this chunk from `peer_dev_ptr` (peer-mapped device memory of the partner
+ * chunk).  `this_is_upper` = this chunk has the global bit set.  Each side calls it once and
+ * moves half of the pairs (`half` = 0/1) so both NVLink directions are used. */
+int b200sv_chunk_swap_peer(b200sv_handle h, int local_q, void *peer_dev_ptr, int this_is_upper, int half);
+/* staging variant for NCCL send/recv: gather/scatter the half-slice of amplitudes whose
+ * local qubit `local_q` equals `bit`, slice [begin, begin+count) of that half, to/from a
+ * contiguous device buffer (send_buffer/recv_buffer, qubitvector.hpp:1061-1081). */
+int b200sv_pack_half(b200sv_handle h, int local_q, int bit, uint64_t begin, uint64_t count, void *dev_buf);
+int b200sv_unpack_half(b200sv_handle h, int local_q, int bit, uint64_t begin, uint64_t count, const void *dev_buf);
+
+/* ---- host RNG identical to Aer's RngEngine (framework/rng.hpp:31-99) ------ */
+/* n draws of rand(0,1) from std::mt19937_64 seeded with `seed` (what
+ * State::sample_measure consumes, statevector_state.hpp:1026-1027). */
+int b200sv_rng_uniform(uint64_t seed, int64_t n, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SV_H */

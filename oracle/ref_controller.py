@@ -72,6 +72,7 @@ def run_circuit(n, ops, shots=0, seed=1234, threads=0, fusion=True, fusion_max_q
     cfg.n_qubits = n
     cfg.memory_slots = n
     cfg.seed_simulator = seed
+    cfg.shots = max(shots, 1)
     cfg.fusion_enable = bool(fusion)
     cfg.fusion_max_qubit = fusion_max_qubit
     cfg.fusion_threshold = fusion_threshold

@@ -1,0 +1,541 @@
+// b200sv C ABI (include/b200sv.h): handle management, argument validation,
+// the reference's host-side routing rules (exact-== special cases, Pauli mask
+// construction, global-qubit resolution for sharded chunks) and error
+// translation.  Kernels live in gates.cu / reduce.cu.
+#include <algorithm>
+#include <cstring>
+#include <random>
+
+#include "common.cuh"
+
+namespace b200sv {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+
+void *State::ensure_scratch(size_t bytes) {
+  if (bytes > scratch_bytes) {
+    if (scratch) {
+      B200_CUDA(cudaStreamSynchronize(stream));
+      B200_CUDA(cudaFree(scratch));
+      scratch = nullptr;
+    }
+    size_t want = std::max<size_t>(bytes, 1 << 20);
+    B200_CUDA(cudaMalloc(&scratch, want));
+    scratch_bytes = want;
+  }
+  return scratch;
+}
+void *State::ensure_pinned(size_t bytes) {
+  if (bytes > pinned_bytes) {
+    if (pinned) {
+      B200_CUDA(cudaStreamSynchronize(stream));
+      B200_CUDA(cudaFreeHost(pinned));
+      pinned = nullptr;
+    }
+    size_t want = std::max<size_t>(bytes, 1 << 16);
+    B200_CUDA(cudaMallocHost(&pinned, want));
+    pinned_bytes = want;
+  }
+  return pinned;
+}
+
+std::vector<int> checked_qubits(const State &s, const uint64_t *qubits, int k, bool allow_global) {
+  if (k < 0 || (k > 0 && !qubits)) throw Error("invalid qubit list");
+  std::vector<int> q(k);
+  const int limit = allow_global && s.global_nq > s.nq ? s.global_nq : s.nq;
+  for (int i = 0; i < k; i++) {
+    if (qubits[i] >= (uint64_t)limit) throw Error("qubit index " + std::to_string(qubits[i]) + " out of range");
+    q[i] = (int)qubits[i];
+    for (int j = 0; j < i; j++)
+      if (q[j] == q[i]) throw Error("duplicate qubit " + std::to_string(q[i]));
+  }
+  return q;
+}
+
+// pauli_masks_and_phase + add_y_phase (qubitvector.hpp:2236-2298)
+struct PauliMasks {
+  uint64_t x = 0, z = 0;
+  int num_y = 0, x_max = 0;
+};
+static PauliMasks pauli_masks(const std::vector<int> &q, const char *pauli) {
+  const size_t N = q.size();
+  if (!pauli || strlen(pauli) != N) throw Error("Pauli string length must equal the number of qubits");
+  PauliMasks m;
+  for (size_t i = 0; i < N; i++) {
+    const uint64_t bit = 1ull << q[i];
+    switch (pauli[N - 1 - i]) {
+    case 'I': break;
+    case 'X': m.x += bit; m.x_max = std::max(m.x_max, q[i]); break;
+    case 'Z': m.z += bit; break;
+    case 'Y': m.x += bit; m.x_max = std::max(m.x_max, q[i]); m.z += bit; m.num_y++; break;
+    default: throw Error(std::string("Invalid Pauli \"") + pauli[N - 1 - i] + "\".");
+    }
+  }
+  return m;
+}
+static void add_y_phase(int num_y, double &re, double &im) {
+  const double r = re, i = im;
+  switch (num_y & 3) {
+  case 1: re = i; im = -r; break;
+  case 2: re = -r; im = -i; break;
+  case 3: re = -i; im = r; break;
+  default: break;
+  }
+}
+
+static void select(State *s) {
+  if (!s) throw Error("null handle");
+  B200_CUDA(cudaSetDevice(s->device));
+}
+
+// Split a control list into local controls and the verdict of global ones
+// (chunk_utils.hpp:55-80 / thrust base_index_ masks): returns false when a global
+// control bit is 0 for this chunk (gate is the identity here).
+static bool resolve_controls(const State &s, std::vector<int> &controls) {
+  std::vector<int> local;
+  for (int c : controls) {
+    if (c < s.nq) local.push_back(c);
+    else if (!((s.chunk_index >> (c - s.nq)) & 1ull)) return false;
+  }
+  controls.swap(local);
+  return true;
+}
+
+template <typename F> static int guard(F f) {
+  try {
+    f();
+    return 0;
+  } catch (const std::exception &e) {
+    set_last_error(e.what());
+    return 1;
+  }
+}
+
+static State *make_state(int nq, int64_t nstates, int precision, int device) {
+  if (nq < 0 || nq > 40) throw Error("num_qubits out of range");
+  if (nstates < 1) throw Error("num_states must be >= 1");
+  if (precision != B200SV_F64 && precision != B200SV_F32) throw Error("precision must be 64 or 32");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    throw Error("No CUDA device available! b200sv has no CPU fallback (cf. aer_controller.hpp:306-310)");
+  if (device < 0 || device >= count) throw Error("device index out of range");
+  State *s = new State();
+  s->device = device; s->nq = nq; s->nstates = nstates; s->precision = precision; s->global_nq = nq;
+  B200_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B200_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    delete s;
+    throw Error("b200sv kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+  }
+  s->num_sms = prop.multiProcessorCount;
+  return s;
+}
+
+}  // namespace b200sv
+
+using namespace b200sv;
+#define H ((State *)h)
+
+extern "C" {
+
+int b200sv_version(void) { return 1; }
+const char *b200sv_last_error(void) { return g_last_error.c_str(); }
+
+int b200sv_device_count(int *count) {
+  return guard([&] {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) c = 0;
+    *count = c;
+  });
+}
+
+int b200sv_create(b200sv_handle *out, int num_qubits, int64_t num_states, int precision, int device) {
+  return guard([&] {
+    State *s = make_state(num_qubits, num_states, precision, device);
+    try {
+      B200_CUDA(cudaMalloc(&s->data, s->total_amps() * s->amp_bytes()));
+      s->owns_data = true;
+      B200_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+      s->owns_stream = true;
+      launch_init(*s, true);
+    } catch (...) {
+      if (s->data) cudaFree(s->data);
+      delete s;
+      throw;
+    }
+    *out = (b200sv_handle)s;
+  });
+}
+
+int b200sv_create_external(b200sv_handle *out, int num_qubits, int64_t num_states, int precision, int device,
+                           void *dev_ptr, void *cuda_stream) {
+  return guard([&] {
+    if (!dev_ptr || ((uintptr_t)dev_ptr & 15)) throw Error("external device pointer must be non-null and 16-byte aligned");
+    State *s = make_state(num_qubits, num_states, precision, device);
+    s->data = dev_ptr;
+    s->stream = (cudaStream_t)cuda_stream;
+    *out = (b200sv_handle)s;
+  });
+}
+
+int b200sv_destroy(b200sv_handle h) {
+  return guard([&] {
+    if (!h) return;
+    select(H);
+    cudaStreamSynchronize(H->stream);
+    if (H->owns_data && H->data) cudaFree(H->data);
+    if (H->scratch) cudaFree(H->scratch);
+    if (H->pinned) cudaFreeHost(H->pinned);
+    if (H->checkpoint) cudaFree(H->checkpoint);
+    if (H->owns_stream && H->stream) cudaStreamDestroy(H->stream);
+    delete H;
+  });
+}
+
+int b200sv_num_qubits(b200sv_handle h, int *n) { return guard([&] { select(H); *n = H->nq; }); }
+int b200sv_device_ptr(b200sv_handle h, void **p) { return guard([&] { select(H); *p = H->data; }); }
+int b200sv_stream(b200sv_handle h, void **p) { return guard([&] { select(H); *p = (void *)H->stream; }); }
+
+int b200sv_set_chunk(b200sv_handle h, int global_num_qubits, uint64_t chunk_index) {
+  return guard([&] {
+    select(H);
+    if (global_num_qubits < H->nq || global_num_qubits > 63) throw Error("global_num_qubits out of range");
+    if (global_num_qubits - H->nq < 63 && (chunk_index >> (global_num_qubits - H->nq)) != 0)
+      throw Error("chunk_index out of range");
+    H->global_nq = global_num_qubits;
+    H->chunk_index = chunk_index;
+  });
+}
+
+int b200sv_synchronize(b200sv_handle h) {
+  return guard([&] { select(H); B200_CUDA(cudaStreamSynchronize(H->stream)); });
+}
+
+int b200sv_initialize(b200sv_handle h) { return guard([&] { select(H); launch_init(*H, true); }); }
+int b200sv_zero(b200sv_handle h) { return guard([&] { select(H); launch_init(*H, false); }); }
+
+int b200sv_upload(b200sv_handle h, const void *host, uint64_t offset, uint64_t count) {
+  return guard([&] {
+    select(H);
+    if (offset + count > H->total_amps()) throw Error("upload range exceeds the state");
+    B200_CUDA(cudaMemcpyAsync((char *)H->data + offset * H->amp_bytes(), host, count * H->amp_bytes(),
+                              cudaMemcpyHostToDevice, H->stream));
+    B200_CUDA(cudaStreamSynchronize(H->stream));
+  });
+}
+int b200sv_download(b200sv_handle h, void *host, uint64_t offset, uint64_t count) {
+  return guard([&] {
+    select(H);
+    if (offset + count > H->total_amps()) throw Error("download range exceeds the state");
+    B200_CUDA(cudaMemcpyAsync(host, (char *)H->data + offset * H->amp_bytes(), count * H->amp_bytes(),
+                              cudaMemcpyDeviceToHost, H->stream));
+    B200_CUDA(cudaStreamSynchronize(H->stream));
+  });
+}
+
+int b200sv_initialize_component(b200sv_handle h, const uint64_t *qubits, int k, const double *state) {
+  return guard([&] {
+    select(H);
+    auto q = checked_qubits(*H, qubits, k);
+    launch_init_component(*H, q.data(), k, state);
+  });
+}
+
+int b200sv_checkpoint(b200sv_handle h) {
+  return guard([&] {
+    select(H);
+    const size_t bytes = H->total_amps() * H->amp_bytes();
+    if (!H->checkpoint) B200_CUDA(cudaMalloc(&H->checkpoint, bytes));
+    B200_CUDA(cudaMemcpyAsync(H->checkpoint, H->data, bytes, cudaMemcpyDeviceToDevice, H->stream));
+  });
+}
+int b200sv_revert(b200sv_handle h, int keep) {
+  return guard([&] {
+    select(H);
+    if (!H->checkpoint) throw Error("revert: no checkpoint");
+    const size_t bytes = H->total_amps() * H->amp_bytes();
+    B200_CUDA(cudaMemcpyAsync(H->data, H->checkpoint, bytes, cudaMemcpyDeviceToDevice, H->stream));
+    if (!keep) {
+      B200_CUDA(cudaStreamSynchronize(H->stream));
+      B200_CUDA(cudaFree(H->checkpoint));
+      H->checkpoint = nullptr;
+    }
+  });
+}
+int b200sv_inner_product(b200sv_handle h, double *re, double *im) {
+  return guard([&] {
+    select(H);
+    if (!H->checkpoint) throw Error("inner_product: no checkpoint");
+    reduce_inner_product(*H, H->checkpoint, re, im);
+  });
+}
+
+// ------------------------------------------------------------------ gates
+int b200sv_apply_matrix(b200sv_handle h, const uint64_t *qubits, int k, const double *mat) {
+  return guard([&] {
+    select(H);
+    if (k < 1) throw Error("apply_matrix: empty qubit list");
+    auto q = checked_qubits(*H, qubits, k);
+    if (k <= kMaxRegQubits) launch_dense(*H, q.data(), k, nullptr, 0, mat);
+    else launch_dense_generic(*H, q.data(), k, mat);
+  });
+}
+
+int b200sv_apply_diagonal(b200sv_handle h, const uint64_t *qubits, int k, const double *diag) {
+  return guard([&] {
+    select(H);
+    if (k < 1) throw Error("apply_diagonal_matrix: empty qubit list");
+    auto q = checked_qubits(*H, qubits, k, true);
+    // restrict to local qubits given this chunk's global bits (chunk_utils.hpp:82-118 block_diagonal_matrix)
+    std::vector<int> lq;
+    std::vector<int> lbit;
+    uint64_t fixed = 0;
+    for (int j = 0; j < k; j++) {
+      if (q[j] < H->nq) { lq.push_back(q[j]); lbit.push_back(j); }
+      else if ((H->chunk_index >> (q[j] - H->nq)) & 1ull) fixed |= 1ull << j;
+    }
+    if ((int)lq.size() == k) { launch_diagonal(*H, q.data(), k, diag); return; }
+    const int kl = (int)lq.size();
+    std::vector<double> d2(2ull << kl);
+    for (uint64_t i = 0; i < (1ull << kl); i++) {
+      uint64_t src = fixed;
+      for (int b = 0; b < kl; b++)
+        if ((i >> b) & 1) src |= 1ull << lbit[b];
+      d2[2 * i] = diag[2 * src];
+      d2[2 * i + 1] = diag[2 * src + 1];
+    }
+    if (kl == 0) {  // scalar on this chunk: apply as a 1-qubit diagonal {d,d} (cf. global phase, statevector_state.hpp:446-450)
+      int q0 = 0;
+      double dd[4] = {d2[0], d2[1], d2[0], d2[1]};
+      if (H->nq == 0) throw Error("apply_diagonal_matrix: zero-qubit chunk");
+      launch_diagonal(*H, &q0, 1, dd);
+    } else {
+      launch_diagonal(*H, lq.data(), kl, d2.data());
+    }
+  });
+}
+
+int b200sv_apply_multiplexer(b200sv_handle h, const uint64_t *ctrl, int nc, const uint64_t *tgt, int nt,
+                             const double *mat) {
+  return guard([&] {
+    select(H);
+    // qubits = targets ++ controls; block b acts on the targets (qubitvector.hpp:1305-1340).
+    std::vector<uint64_t> all(tgt, tgt + nt);
+    all.insert(all.end(), ctrl, ctrl + nc);
+    const int k = nc + nt;
+    auto q = checked_qubits(*H, all.data(), k);
+    const uint64_t DIM = 1ull << k, columns = 1ull << nt, blocks = 1ull << nc;
+    std::vector<double> full(2 * DIM * DIM, 0.0);  // block-diagonal expansion, column major
+    for (uint64_t b = 0; b < blocks; b++)
+      for (uint64_t i = 0; i < columns; i++)
+        for (uint64_t j = 0; j < columns; j++) {
+          const uint64_t src = i + b * columns + DIM * j;
+          const uint64_t dst = (i + b * columns) + DIM * (j + b * columns);
+          full[2 * dst] = mat[2 * src];
+          full[2 * dst + 1] = mat[2 * src + 1];
+        }
+    if (k <= kMaxRegQubits) launch_dense(*H, q.data(), k, nullptr, 0, full.data());
+    else launch_dense_generic(*H, q.data(), k, full.data());
+  });
+}
+
+int b200sv_apply_permutation(b200sv_handle h, const uint64_t *qubits, int k, const uint64_t *pairs, int npairs) {
+  return guard([&] {
+    select(H);
+    auto q = checked_qubits(*H, qubits, k);
+    launch_permutation(*H, q.data(), k, pairs, npairs);
+  });
+}
+
+int b200sv_apply_mcx(b200sv_handle h, const uint64_t *qubits, int k) {
+  return guard([&] {
+    select(H);
+    if (k < 1) throw Error("apply_mcx: empty qubit list");
+    auto q = checked_qubits(*H, qubits, k, true);
+    const int t = q.back();
+    if (t >= H->nq) throw Error("apply_mcx: target on a global qubit needs a chunk swap first");
+    std::vector<int> c(q.begin(), q.end() - 1);
+    if (!resolve_controls(*H, c)) return;
+    launch_mcx(*H, c.data(), (int)c.size(), t);
+  });
+}
+int b200sv_apply_mcy(b200sv_handle h, const uint64_t *qubits, int k) {
+  return guard([&] {
+    select(H);
+    if (k < 1) throw Error("apply_mcy: empty qubit list");
+    auto q = checked_qubits(*H, qubits, k, true);
+    const int t = q.back();
+    if (t >= H->nq) throw Error("apply_mcy: target on a global qubit needs a chunk swap first");
+    std::vector<int> c(q.begin(), q.end() - 1);
+    if (!resolve_controls(*H, c)) return;
+    launch_mcy(*H, c.data(), (int)c.size(), t);
+  });
+}
+int b200sv_apply_mcswap(b200sv_handle h, const uint64_t *qubits, int k) {
+  return guard([&] {
+    select(H);
+    if (k < 2) throw Error("apply_mcswap: needs at least two qubits");
+    auto q = checked_qubits(*H, qubits, k, true);
+    const int t0 = q[k - 2], t1 = q[k - 1];
+    if (t0 >= H->nq || t1 >= H->nq) throw Error("apply_mcswap: target on a global qubit needs a chunk swap first");
+    std::vector<int> c(q.begin(), q.end() - 2);
+    if (!resolve_controls(*H, c)) return;
+    launch_mcswap(*H, c.data(), (int)c.size(), t0, t1);
+  });
+}
+int b200sv_apply_mcphase(b200sv_handle h, const uint64_t *qubits, int k, double re, double im) {
+  return guard([&] {
+    select(H);
+    if (k < 1) throw Error("apply_mcphase: empty qubit list");
+    auto q = checked_qubits(*H, qubits, k, true);
+    if (!resolve_controls(*H, q)) return;  // every listed qubit acts as a control of the phase
+    if (q.empty()) {                       // all listed qubits are global and set: scalar phase on this chunk
+      int q0 = 0;
+      double dd[4] = {re, im, re, im};
+      launch_diagonal(*H, &q0, 1, dd);
+      return;
+    }
+    launch_mcphase(*H, q.data(), (int)q.size(), re, im);
+  });
+}
+
+int b200sv_apply_mcu(b200sv_handle h, const uint64_t *qubits, int k, const double *m) {
+  return guard([&] {
+    select(H);
+    if (k < 1) throw Error("apply_mcu: empty qubit list");
+    auto q = checked_qubits(*H, qubits, k, true);
+    // reference routing on exact equality (qubitvector.hpp:1626-1633)
+    const bool offdiag_zero = m[2] == 0.0 && m[3] == 0.0 && m[4] == 0.0 && m[5] == 0.0;
+    if (offdiag_zero && m[0] == 1.0 && m[1] == 0.0) {
+      std::vector<int> all = q;
+      if (!resolve_controls(*H, all)) return;
+      if (all.empty()) { int q0 = 0; double dd[4] = {m[6], m[7], m[6], m[7]}; launch_diagonal(*H, &q0, 1, dd); return; }
+      launch_mcphase(*H, all.data(), (int)all.size(), m[6], m[7]);
+      return;
+    }
+    const int t = q.back();
+    std::vector<int> c(q.begin(), q.end() - 1);
+    if (t >= H->nq) {
+      if (!offdiag_zero) throw Error("apply_mcu: non-diagonal target on a global qubit needs a chunk swap first");
+      // diagonal on a global target: scalar d[bit] under the (local) controls
+      if (!resolve_controls(*H, c)) return;
+      const int bit = (int)((H->chunk_index >> (t - H->nq)) & 1ull);
+      const double re = m[6 * bit], im = m[6 * bit + 1];
+      if (c.empty()) { int q0 = 0; double dd[4] = {re, im, re, im}; launch_diagonal(*H, &q0, 1, dd); }
+      else launch_mcphase(*H, c.data(), (int)c.size(), re, im);
+      return;
+    }
+    if (!resolve_controls(*H, c)) return;
+    if (offdiag_zero && c.empty()) {
+      double dd[4] = {m[0], m[1], m[6], m[7]};
+      launch_diagonal(*H, &t, 1, dd);
+      return;
+    }
+    launch_dense(*H, &t, 1, c.data(), (int)c.size(), m);
+  });
+}
+
+int b200sv_apply_pauli(b200sv_handle h, const uint64_t *qubits, int k, const char *pauli, double cre, double cim) {
+  return guard([&] {
+    select(H);
+    auto q = checked_qubits(*H, qubits, k);
+    PauliMasks m = pauli_masks(q, pauli);
+    if (m.x + m.z == 0) return;  // identity string: no-op even with coeff (qubitvector.hpp:2400-2403)
+    add_y_phase(m.num_y, cre, cim);
+    launch_pauli(*H, m.x, m.z, m.x_max, cre, cim);
+  });
+}
+
+int b200sv_apply_batched_pauli(b200sv_handle h, const uint64_t *masks4) {
+  return guard([&] { select(H); launch_batched_pauli(*H, masks4); });
+}
+
+// ------------------------------------------------------------------ reductions
+int b200sv_norm(b200sv_handle h, double *out) { return guard([&] { select(H); reduce_norm(*H, out); }); }
+
+int b200sv_norm_matrix(b200sv_handle h, const uint64_t *qubits, int k, const double *mat, double *out) {
+  return guard([&] {
+    select(H);
+    if (k < 1) throw Error("norm(qubits, mat): empty qubit list");
+    auto q = checked_qubits(*H, qubits, k);
+    reduce_norm_matrix(*H, q.data(), k, mat, out);
+  });
+}
+
+int b200sv_probabilities(b200sv_handle h, const uint64_t *qubits, int k, double *out) {
+  return guard([&] {
+    select(H);
+    auto q = checked_qubits(*H, qubits, k);
+    if (k == 0) { reduce_norm(*H, out); return; }
+    reduce_probabilities(*H, q.data(), k, out);
+  });
+}
+
+int b200sv_sample_measure(b200sv_handle h, const double *rnds, int64_t shots, uint64_t *out) {
+  return guard([&] { select(H); sample_measure(*H, rnds, shots, out); });
+}
+
+int b200sv_expval_pauli(b200sv_handle h, const uint64_t *qubits, int k, const char *pauli, double pre, double pim,
+                        double *out) {
+  return guard([&] {
+    select(H);
+    auto q = checked_qubits(*H, qubits, k);
+    PauliMasks m = pauli_masks(q, pauli);
+    if (m.x + m.z == 0) { reduce_norm(*H, out); return; }  // qubitvector.hpp:2309-2311
+    add_y_phase(m.num_y, pre, pim);
+    reduce_expval_pauli(*H, m.x, m.z, m.x_max, pre, pim, nullptr, 0, 0, out);
+  });
+}
+
+int b200sv_expval_pauli_pair(b200sv_handle h, const uint64_t *qubits, int k, const char *pauli,
+                             const void *pair_dev_ptr, uint64_t z_count, uint64_t z_count_pair, double pre,
+                             double pim, double *out) {
+  return guard([&] {
+    select(H);
+    auto q = checked_qubits(*H, qubits, k);
+    PauliMasks m = pauli_masks(q, pauli);
+    add_y_phase(m.num_y, pre, pim);
+    reduce_expval_pauli(*H, m.x, m.z, m.x_max, pre, pim, pair_dev_ptr ? pair_dev_ptr : H->data, z_count, z_count_pair,
+                        out);
+  });
+}
+
+// ------------------------------------------------------------------ exchange
+int b200sv_chunk_swap_peer(b200sv_handle h, int local_q, void *peer, int upper, int half) {
+  return guard([&] {
+    select(H);
+    if (local_q < 0 || local_q >= H->nq) throw Error("chunk swap: local qubit out of range");
+    if (H->nstates != 1) throw Error("chunk swap: not available on batched containers");
+    if (H->nq < 2) throw Error("chunk swap: chunk too small");
+    launch_chunk_swap_peer(*H, local_q, peer, upper, half);
+  });
+}
+int b200sv_pack_half(b200sv_handle h, int local_q, int bit, uint64_t begin, uint64_t count, void *buf) {
+  return guard([&] {
+    select(H);
+    if (local_q < 0 || local_q >= H->nq) throw Error("pack_half: local qubit out of range");
+    if (begin + count > (H->total_amps() >> 1)) throw Error("pack_half: range exceeds half the chunk");
+    launch_pack_half(*H, local_q, bit, begin, count, buf, false);
+  });
+}
+int b200sv_unpack_half(b200sv_handle h, int local_q, int bit, uint64_t begin, uint64_t count, const void *buf) {
+  return guard([&] {
+    select(H);
+    if (local_q < 0 || local_q >= H->nq) throw Error("unpack_half: local qubit out of range");
+    if (begin + count > (H->total_amps() >> 1)) throw Error("unpack_half: range exceeds half the chunk");
+    launch_pack_half(*H, local_q, bit, begin, count, (void *)buf, true);
+  });
+}
+
+// ------------------------------------------------------------------ RNG (host)
+int b200sv_rng_uniform(uint64_t seed, int64_t n, double *out) {
+  return guard([&] {
+    std::mt19937_64 rng(seed);  // RngEngine::set_seed / rand(0,1) (framework/rng.hpp:45-70)
+    for (int64_t i = 0; i < n; i++) out[i] = std::uniform_real_distribution<double>(0.0, 1.0)(rng);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// b200sv internal header: handle layout, error plumbing, complex/index helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cstring>
+
+#include "../../include/b200sv.h"
+
+namespace b200sv {
+
+constexpr int kMaxDenseQubits = 10;   // generic (smem) dense kernel limit, like the reference's K3 (chunk_container.hpp:850)
+constexpr int kMaxRegQubits = 5;      // register-resident dense kernel (fusion_max_qubit default, fusion.hpp:762)
+constexpr int kMaxDiagQubits = 10;
+constexpr int kMaxInsert = 40;        // zero-insert positions (targets + controls)
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+void set_last_error(const std::string &msg);
+
+#define B200_CUDA(expr)                                                                  \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      throw ::b200sv::Error(std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+  } while (0)
+
+template <typename T> struct cx_of;
+template <> struct cx_of<double> { using type = double2; };
+template <> struct cx_of<float> { using type = float2; };
+template <typename T> using cx = typename cx_of<T>::type;
+
+template <typename T> __host__ __device__ __forceinline__ cx<T> mk(T re, T im) {
+  cx<T> r; r.x = re; r.y = im; return r;
+}
+// a*b
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+  C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+// acc += a*b   (4 FMAs)
+template <typename C> __device__ __forceinline__ void cfma(C &acc, C a, C b) {
+  acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+
+// insert a zero bit at position `pos` (index0 building block, indexes.hpp:212-222)
+__host__ __device__ __forceinline__ uint64_t insert_zero(uint64_t v, int pos) {
+  const uint64_t low = v & ((1ull << pos) - 1);
+  return ((v >> pos) << (pos + 1)) | low;
+}
+
+struct InsertList {  // sorted ascending positions
+  int n;
+  uint8_t pos[kMaxInsert];
+};
+__host__ __device__ __forceinline__ uint64_t insert_zeros(uint64_t v, const InsertList &l) {
+  for (int i = 0; i < l.n; i++) v = insert_zero(v, l.pos[i]);
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+struct State {
+  int device = 0;
+  int nq = 0;                 // local qubits per state
+  int64_t nstates = 1;
+  int precision = B200SV_F64;
+  void *data = nullptr;       // nstates << nq amplitudes
+  bool owns_data = false;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  // sharding (b200sv_set_chunk)
+  int global_nq = 0;
+  uint64_t chunk_index = 0;
+  // scratch
+  void *scratch = nullptr;    // device scratch for reductions / sampler
+  size_t scratch_bytes = 0;
+  void *pinned = nullptr;     // pinned host staging
+  size_t pinned_bytes = 0;
+  void *checkpoint = nullptr;
+  int num_sms = 148;
+
+  uint64_t amps_per_state() const { return 1ull << nq; }
+  uint64_t total_amps() const { return (uint64_t)nstates << nq; }
+  size_t amp_bytes() const { return precision == B200SV_F64 ? 16 : 8; }
+  void *ensure_scratch(size_t bytes);
+  void *ensure_pinned(size_t bytes);
+};
+
+// sorted copy + validation of a qubit list against nq (throws)
+std::vector<int> checked_qubits(const State &s, const uint64_t *qubits, int k, bool allow_global = false);
+
+// ---- kernel launchers (gates.cu) -------------------------------------------
+void launch_dense(State &s, const int *targets, int k, const int *controls, int nc, const double *mat_colmajor);
+void launch_dense_generic(State &s, const int *targets, int k, const double *mat_colmajor);
+void launch_diagonal(State &s, const int *qubits, int k, const double *diag);
+void launch_mcphase(State &s, const int *qubits, int k, double re, double im);
+void launch_mcx(State &s, const int *controls, int nc, int target);
+void launch_mcy(State &s, const int *controls, int nc, int target);
+void launch_mcswap(State &s, const int *controls, int nc, int t0, int t1);
+void launch_permutation(State &s, const int *qubits, int k, const uint64_t *pairs, int npairs);
+void launch_pauli(State &s, uint64_t x_mask, uint64_t z_mask, int x_max, double pre, double pim);
+void launch_batched_pauli(State &s, const uint64_t *masks4_host);
+void launch_init(State &s, bool ket0);
+void launch_init_component(State &s, const int *qubits, int k, const double *state);
+void launch_pack_half(State &s, int q, int bit, uint64_t begin, uint64_t count, void *buf, bool unpack);
+void launch_chunk_swap_peer(State &s, int q, void *peer, int upper, int half);
+
+// ---- reductions (reduce.cu) -------------------------------------------------
+void reduce_norm(State &s, double *out);
+void reduce_norm_matrix(State &s, const int *qubits, int k, const double *mat, double *out);
+void reduce_probabilities(State &s, const int *qubits, int k, double *out);
+void reduce_expval_pauli(State &s, uint64_t x_mask, uint64_t z_mask, int x_max, double pre, double pim,
+                         const void *pair, uint64_t zc, uint64_t zcp, double *out);
+void reduce_inner_product(State &s, const void *other, double *re, double *im);
+void sample_measure(State &s, const double *rnds, int64_t shots, uint64_t *out);
+
+}  // namespace b200sv

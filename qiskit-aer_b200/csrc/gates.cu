@@ -1,0 +1,563 @@
+// b200sv gate-application kernels (sm_100a).
+//
+// Every kernel is a streaming pass over the amplitudes it must touch:
+//   * one thread owns one "group" (the 2^k amplitudes coupled by a k-qubit
+//     gate); the 2^k loads are each a 128-bit access (one complex<double>)
+//     and are issued back to back before any math, so a warp keeps
+//     32 * 2^k independent 16-byte requests in flight;
+//   * controls are folded into index generation: a gate with c controls
+//     launches 2^(n-c-k) groups, never 2^(n-k) masked threads (the reference
+//     launches and masks, thrust_kernels.hpp:1190);
+//   * gate matrices travel as __grid_constant__ kernel parameters (constant
+//     bank, no H2D copy, no per-gate cudaMemcpy as in
+//     device_chunk_container.hpp:566-594) and feed DFMA directly.
+// Index algebra: base = insert_zeros(g, sorted(targets U controls)) | ctrl_mask,
+// element e at base + off[e]  (indexes.hpp:212-250).
+#include "common.cuh"
+
+namespace b200sv {
+
+static inline int grid_for(const State &s, uint64_t work_items, int threads, int per_sm) {
+  uint64_t blocks = (work_items + threads - 1) / threads;
+  uint64_t cap = (uint64_t)s.num_sms * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------ dense, registers
+template <typename T, int K> struct DenseParams {
+  cx<T> m[1 << (2 * K)];     // row major: m[i*DIM + j] = M[i][j]
+  uint64_t off[1 << K];      // amplitude offset of matrix index e
+  uint64_t ctrl_mask;
+  uint64_t ngroups;
+  InsertList ins;
+};
+
+template <typename T, int K>
+__global__ void __launch_bounds__(K >= 5 ? 128 : 256)
+dense_kernel(cx<T> *__restrict__ psi, const __grid_constant__ DenseParams<T, K> p) {
+  constexpr int DIM = 1 << K;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.ngroups; g += stride) {
+    const uint64_t base = insert_zeros(g, p.ins) | p.ctrl_mask;
+    cx<T> in[DIM];
+#pragma unroll
+    for (int e = 0; e < DIM; e++) in[e] = psi[base + p.off[e]];
+#pragma unroll
+    for (int i = 0; i < DIM; i++) {
+      cx<T> acc = mk<T>(0, 0);
+#pragma unroll
+      for (int j = 0; j < DIM; j++) cfma(acc, p.m[i * DIM + j], in[j]);
+      psi[base + p.off[i]] = acc;
+    }
+  }
+}
+
+template <typename T, int K>
+static void launch_dense_t(State &s, const int *targets, const int *controls, int nc, const double *mat) {
+  constexpr int DIM = 1 << K;
+  static DenseParams<T, K> p;  // large: keep off the stack (single-threaded use per process is documented)
+  for (int i = 0; i < DIM; i++)
+    for (int j = 0; j < DIM; j++)
+      p.m[i * DIM + j] = mk<T>((T)mat[2 * (i + DIM * j)], (T)mat[2 * (i + DIM * j) + 1]);
+  for (int e = 0; e < DIM; e++) {
+    uint64_t o = 0;
+    for (int b = 0; b < K; b++)
+      if ((e >> b) & 1) o |= 1ull << targets[b];
+    p.off[e] = o;
+  }
+  std::vector<int> all(targets, targets + K);
+  p.ctrl_mask = 0;
+  for (int c = 0; c < nc; c++) {
+    all.push_back(controls[c]);
+    p.ctrl_mask |= 1ull << controls[c];
+  }
+  std::sort(all.begin(), all.end());
+  p.ins.n = (int)all.size();
+  for (size_t i = 0; i < all.size(); i++) p.ins.pos[i] = (uint8_t)all[i];
+  p.ngroups = s.total_amps() >> (K + nc);
+  const int threads = K >= 5 ? 128 : 256;
+  const int grid = grid_for(s, p.ngroups, threads, K >= 5 ? 12 : 16);
+  dense_kernel<T, K><<<grid, threads, 0, s.stream>>>((cx<T> *)s.data, p);
+  B200_CUDA(cudaGetLastError());
+}
+
+void launch_dense(State &s, const int *targets, int k, const int *controls, int nc, const double *mat) {
+  const bool f64 = s.precision == B200SV_F64;
+#define CASE(K)                                                                  \
+  case K:                                                                        \
+    if (f64) launch_dense_t<double, K>(s, targets, controls, nc, mat);           \
+    else launch_dense_t<float, K>(s, targets, controls, nc, mat);                \
+    break;
+  switch (k) {
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5)
+  default:
+    throw Error("launch_dense: k out of range");
+  }
+#undef CASE
+}
+
+// ------------------------------------------------------------------ dense, generic (k = 6..10)
+// One CTA per group: stage the 2^k inputs in shared memory, every thread then
+// produces outputs i = tid, tid+NT, ... reading the column-major matrix from
+// global memory (coalesced across i).  Correctness fallback for blocks larger
+// than fusion ever emits (reference K3/K4, thrust_kernels.hpp:900-1100).
+struct GenericParams {
+  uint64_t off_bits[kMaxDenseQubits];
+  uint64_t ngroups;
+  InsertList ins;
+  int k;
+};
+template <typename T>
+__global__ void dense_generic_kernel(cx<T> *__restrict__ psi, const cx<T> *__restrict__ mat,
+                                     const __grid_constant__ GenericParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *in = reinterpret_cast<cx<T> *>(smem_raw);
+  const int DIM = 1 << p.k;
+  for (uint64_t g = blockIdx.x; g < p.ngroups; g += gridDim.x) {
+    const uint64_t base = insert_zeros(g, p.ins);
+    for (int e = threadIdx.x; e < DIM; e += blockDim.x) {
+      uint64_t o = 0;
+      for (int b = 0; b < p.k; b++)
+        if ((e >> b) & 1) o |= p.off_bits[b];
+      in[e] = psi[base + o];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < DIM; i += blockDim.x) {
+      cx<T> acc = mk<T>(0, 0);
+      for (int j = 0; j < DIM; j++) cfma(acc, mat[i + (size_t)DIM * j], in[j]);
+      uint64_t o = 0;
+      for (int b = 0; b < p.k; b++)
+        if ((i >> b) & 1) o |= p.off_bits[b];
+      psi[base + o] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+void launch_dense_generic(State &s, const int *targets, int k, const double *mat) {
+  if (k > kMaxDenseQubits) throw Error("apply_matrix: more than 10 qubits is not supported");
+  const size_t dim = 1ull << k, nelem = dim * dim;
+  const size_t abytes = s.amp_bytes();
+  // stage matrix: pinned host -> device scratch (stream ordered)
+  void *hm = s.ensure_pinned(nelem * abytes);
+  void *dm = s.ensure_scratch(nelem * abytes);
+  B200_CUDA(cudaStreamSynchronize(s.stream));  // pinned buffer reuse
+  if (s.precision == B200SV_F64) {
+    memcpy(hm, mat, nelem * 16);
+  } else {
+    float *f = (float *)hm;
+    for (size_t i = 0; i < 2 * nelem; i++) f[i] = (float)mat[i];
+  }
+  B200_CUDA(cudaMemcpyAsync(dm, hm, nelem * abytes, cudaMemcpyHostToDevice, s.stream));
+  GenericParams p;
+  p.k = k;
+  std::vector<int> all(targets, targets + k);
+  for (int b = 0; b < k; b++) p.off_bits[b] = 1ull << targets[b];
+  std::sort(all.begin(), all.end());
+  p.ins.n = k;
+  for (int i = 0; i < k; i++) p.ins.pos[i] = (uint8_t)all[i];
+  p.ngroups = s.total_amps() >> k;
+  const int threads = (int)std::min<size_t>(dim, 256);
+  const int grid = (int)std::min<uint64_t>(p.ngroups, (uint64_t)s.num_sms * 8);
+  if (s.precision == B200SV_F64)
+    dense_generic_kernel<double><<<grid, threads, dim * 16, s.stream>>>((double2 *)s.data, (const double2 *)dm, p);
+  else
+    dense_generic_kernel<float><<<grid, threads, dim * 8, s.stream>>>((float2 *)s.data, (const float2 *)dm, p);
+  B200_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ diagonal (streaming)
+template <typename T> struct DiagParams {
+  cx<T> d[1 << 5];   // tables up to 5 qubits ride in the parameter bank
+  uint64_t total;
+  int k;
+  uint8_t q[kMaxDiagQubits];
+};
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(256)
+diag_kernel(cx<T> *__restrict__ psi, const cx<T> *__restrict__ big_table, const __grid_constant__ DiagParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *tab = reinterpret_cast<cx<T> *>(smem_raw);
+  const int dim = 1 << p.k;
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) tab[i] = big_table ? big_table[i] : p.d[i];
+  __syncthreads();
+  const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint64_t i0 = tid; i0 < p.total; i0 += nthreads * UNROLL) {
+    cx<T> v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const uint64_t idx = i0 + u * nthreads;
+      if (idx < p.total) v[u] = psi[idx];
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const uint64_t idx = i0 + u * nthreads;
+      if (idx < p.total) {
+        uint32_t iv = 0;
+        for (int j = 0; j < p.k; j++) iv |= (uint32_t)((idx >> p.q[j]) & 1ull) << j;
+        psi[idx] = cmul(v[u], tab[iv]);
+      }
+    }
+  }
+}
+
+void launch_diagonal(State &s, const int *qubits, int k, const double *diag) {
+  if (k > kMaxDiagQubits) throw Error("apply_diagonal_matrix: more than 10 qubits is not supported");
+  const int dim = 1 << k;
+  const bool f64 = s.precision == B200SV_F64;
+  void *big = nullptr;
+  if (k > 5) {
+    const size_t bytes = (size_t)dim * s.amp_bytes();
+    void *hm = s.ensure_pinned(bytes);
+    big = s.ensure_scratch(bytes);
+    B200_CUDA(cudaStreamSynchronize(s.stream));
+    if (f64) memcpy(hm, diag, bytes);
+    else for (int i = 0; i < 2 * dim; i++) ((float *)hm)[i] = (float)diag[i];
+    B200_CUDA(cudaMemcpyAsync(big, hm, bytes, cudaMemcpyHostToDevice, s.stream));
+  }
+  const uint64_t total = s.total_amps();
+  const int threads = 256;
+  const int grid = grid_for(s, (total + 3) / 4, threads, 8);
+  if (f64) {
+    DiagParams<double> p;
+    p.k = k; p.total = total;
+    for (int j = 0; j < k; j++) p.q[j] = (uint8_t)qubits[j];
+    if (k <= 5) for (int i = 0; i < dim; i++) p.d[i] = mk<double>(diag[2 * i], diag[2 * i + 1]);
+    diag_kernel<double, 4><<<grid, threads, dim * 16, s.stream>>>((double2 *)s.data, (const double2 *)big, p);
+  } else {
+    DiagParams<float> p;
+    p.k = k; p.total = total;
+    for (int j = 0; j < k; j++) p.q[j] = (uint8_t)qubits[j];
+    if (k <= 5) for (int i = 0; i < dim; i++) p.d[i] = mk<float>((float)diag[2 * i], (float)diag[2 * i + 1]);
+    diag_kernel<float, 4><<<grid, threads, dim * 8, s.stream>>>((float2 *)s.data, (const float2 *)big, p);
+  }
+  B200_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ sub-cube kernels (controls in the index)
+struct CubeParams {
+  uint64_t ngroups;
+  uint64_t mask0;  // bits OR'ed into the first element
+  uint64_t mask1;  // bits OR'ed into the second element (pair kernels)
+  InsertList ins;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) mcphase_kernel(cx<T> *__restrict__ psi, const __grid_constant__ CubeParams p,
+                                                      cx<T> phase) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.ngroups; g += stride) {
+    const uint64_t i = insert_zeros(g, p.ins) | p.mask0;
+    psi[i] = cmul(psi[i], phase);
+  }
+}
+
+// MODE 0: swap (mcx / mcswap)   MODE 1: mcy (d0 = -i*d1, d1 = i*d0) -- pure moves + sign flips: bit exact
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) pair_perm_kernel(cx<T> *__restrict__ psi, const __grid_constant__ CubeParams p) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.ngroups; g += stride) {
+    const uint64_t base = insert_zeros(g, p.ins);
+    const uint64_t i0 = base | p.mask0, i1 = base | p.mask1;
+    const cx<T> a = psi[i0], b = psi[i1];
+    if (MODE == 0) {
+      psi[i0] = b;
+      psi[i1] = a;
+    } else {
+      psi[i0] = mk<T>(b.y, -b.x);
+      psi[i1] = mk<T>(-a.y, a.x);
+    }
+  }
+}
+
+static CubeParams cube_params(const State &s, std::vector<int> all) {
+  CubeParams p;
+  std::sort(all.begin(), all.end());
+  p.ins.n = (int)all.size();
+  for (size_t i = 0; i < all.size(); i++) p.ins.pos[i] = (uint8_t)all[i];
+  p.ngroups = s.total_amps() >> all.size();
+  p.mask0 = p.mask1 = 0;
+  return p;
+}
+
+void launch_mcphase(State &s, const int *qubits, int k, double re, double im) {
+  CubeParams p = cube_params(s, std::vector<int>(qubits, qubits + k));
+  for (int j = 0; j < k; j++) p.mask0 |= 1ull << qubits[j];
+  const int grid = grid_for(s, p.ngroups, 256, 16);
+  if (s.precision == B200SV_F64)
+    mcphase_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, p, mk<double>(re, im));
+  else
+    mcphase_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, p, mk<float>((float)re, (float)im));
+  B200_CUDA(cudaGetLastError());
+}
+
+template <int MODE> static void launch_pair(State &s, const CubeParams &p) {
+  const int grid = grid_for(s, p.ngroups, 256, 16);
+  if (s.precision == B200SV_F64)
+    pair_perm_kernel<double, MODE><<<grid, 256, 0, s.stream>>>((double2 *)s.data, p);
+  else
+    pair_perm_kernel<float, MODE><<<grid, 256, 0, s.stream>>>((float2 *)s.data, p);
+  B200_CUDA(cudaGetLastError());
+}
+
+void launch_mcx(State &s, const int *controls, int nc, int target) {
+  std::vector<int> all(controls, controls + nc);
+  all.push_back(target);
+  CubeParams p = cube_params(s, all);
+  for (int c = 0; c < nc; c++) p.mask0 |= 1ull << controls[c];
+  p.mask1 = p.mask0 | (1ull << target);
+  launch_pair<0>(s, p);
+}
+void launch_mcy(State &s, const int *controls, int nc, int target) {
+  std::vector<int> all(controls, controls + nc);
+  all.push_back(target);
+  CubeParams p = cube_params(s, all);
+  for (int c = 0; c < nc; c++) p.mask0 |= 1ull << controls[c];
+  p.mask1 = p.mask0 | (1ull << target);
+  launch_pair<1>(s, p);
+}
+void launch_mcswap(State &s, const int *controls, int nc, int t0, int t1) {
+  std::vector<int> all(controls, controls + nc);
+  all.push_back(t0);
+  all.push_back(t1);
+  CubeParams p = cube_params(s, all);
+  uint64_t cm = 0;
+  for (int c = 0; c < nc; c++) cm |= 1ull << controls[c];
+  p.mask0 = cm | (1ull << t0);
+  p.mask1 = cm | (1ull << t1);
+  launch_pair<0>(s, p);
+}
+
+// ------------------------------------------------------------------ general permutation (sequential swaps per group)
+struct PermParams {
+  uint64_t off_bits[kMaxDenseQubits];
+  uint64_t ngroups;
+  InsertList ins;
+  int k, npairs;
+  uint16_t pairs[2 * 1024];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) perm_kernel(cx<T> *psi, const __grid_constant__ PermParams p) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.ngroups; g += stride) {
+    const uint64_t base = insert_zeros(g, p.ins);
+    for (int t = 0; t < p.npairs; t++) {
+      uint64_t oa = 0, ob = 0;
+      const int ea = p.pairs[2 * t], eb = p.pairs[2 * t + 1];
+      for (int b = 0; b < p.k; b++) {
+        if ((ea >> b) & 1) oa |= p.off_bits[b];
+        if ((eb >> b) & 1) ob |= p.off_bits[b];
+      }
+      volatile cx<T> *vp = psi;  // sequential swaps may alias within a thread's group
+      const T ax = vp[base + oa].x, ay = vp[base + oa].y;
+      const T bx = vp[base + ob].x, by = vp[base + ob].y;
+      vp[base + oa].x = bx; vp[base + oa].y = by;
+      vp[base + ob].x = ax; vp[base + ob].y = ay;
+    }
+  }
+}
+void launch_permutation(State &s, const int *qubits, int k, const uint64_t *pairs, int npairs) {
+  if (k > kMaxDenseQubits) throw Error("apply_permutation_matrix: more than 10 qubits is not supported");
+  if (npairs > 1024) throw Error("apply_permutation_matrix: more than 1024 pairs is not supported");
+  static PermParams p;
+  p.k = k; p.npairs = npairs;
+  std::vector<int> all(qubits, qubits + k);
+  for (int b = 0; b < k; b++) p.off_bits[b] = 1ull << qubits[b];
+  std::sort(all.begin(), all.end());
+  p.ins.n = k;
+  for (int i = 0; i < k; i++) p.ins.pos[i] = (uint8_t)all[i];
+  for (int t = 0; t < 2 * npairs; t++) {
+    if (pairs[t] >= (1ull << k)) throw Error("apply_permutation_matrix: pair index out of range");
+    p.pairs[t] = (uint16_t)pairs[t];
+  }
+  p.ngroups = s.total_amps() >> k;
+  const int grid = grid_for(s, p.ngroups, 256, 16);
+  if (s.precision == B200SV_F64) perm_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, p);
+  else perm_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, p);
+  B200_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ Pauli string
+// pairs (i0, i0 ^ x_mask), i0 = insert_zero(i, x_max); Z-only strings use pos 0 and no swap.
+template <typename T>
+__device__ __forceinline__ void pauli_pair(cx<T> *__restrict__ psi, uint64_t i, uint64_t x_mask, uint64_t z_mask,
+                                           int pos, cx<T> phase) {
+  const uint64_t i0 = insert_zero(i, pos);
+  const uint64_t i1 = i0 ^ (x_mask ? x_mask : 1ull);
+  cx<T> a = psi[i0], b = psi[i1];
+  if (x_mask) { const cx<T> t = a; a = b; b = t; }
+  if (__popcll(i0 & z_mask) & 1) a = mk<T>(-a.x, -a.y);
+  if (__popcll(i1 & z_mask) & 1) b = mk<T>(-b.x, -b.y);
+  psi[i0] = cmul(a, phase);
+  psi[i1] = cmul(b, phase);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) pauli_kernel(cx<T> *__restrict__ psi, uint64_t npairs, uint64_t x_mask,
+                                                    uint64_t z_mask, int pos, cx<T> phase) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride)
+    pauli_pair<T>(psi, i, x_mask, z_mask, pos, phase);
+}
+void launch_pauli(State &s, uint64_t x_mask, uint64_t z_mask, int x_max, double pre, double pim) {
+  const uint64_t npairs = s.total_amps() >> 1;
+  const int pos = x_mask ? x_max : 0;
+  const int grid = grid_for(s, npairs, 256, 16);
+  if (s.precision == B200SV_F64)
+    pauli_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, npairs, x_mask, z_mask, pos,
+                                                     mk<double>(pre, pim));
+  else
+    pauli_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, npairs, x_mask, z_mask, pos,
+                                                    mk<float>((float)pre, (float)pim));
+  B200_CUDA(cudaGetLastError());
+}
+
+// per-state Pauli (batched noisy shots): masks4[s] = {x_mask, z_mask, num_y, apply}
+template <typename T>
+__global__ void __launch_bounds__(256) batched_pauli_kernel(cx<T> *__restrict__ psi, int nq, uint64_t pairs_per_state,
+                                                            const uint64_t *__restrict__ masks4) {
+  const uint64_t s = blockIdx.y;
+  const uint64_t x_mask = masks4[4 * s], z_mask = masks4[4 * s + 1], ny = masks4[4 * s + 2];
+  if (!masks4[4 * s + 3] || (x_mask | z_mask) == 0) return;
+  cx<T> phase = mk<T>(1, 0);                     // (-i)^num_y, add_y_phase (qubitvector.hpp:2275)
+  if ((ny & 3) == 1) phase = mk<T>(0, -1);
+  if ((ny & 3) == 2) phase = mk<T>(-1, 0);
+  if ((ny & 3) == 3) phase = mk<T>(0, 1);
+  const int pos = x_mask ? 63 - __clzll((long long)x_mask) : 0;
+  cx<T> *st = psi + (s << nq);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs_per_state; i += stride)
+    pauli_pair<T>(st, i, x_mask, z_mask, pos, phase);
+}
+void launch_batched_pauli(State &s, const uint64_t *masks4_host) {
+  const size_t bytes = (size_t)s.nstates * 4 * sizeof(uint64_t);
+  void *hm = s.ensure_pinned(bytes);
+  void *dm = s.ensure_scratch(bytes);
+  B200_CUDA(cudaStreamSynchronize(s.stream));
+  memcpy(hm, masks4_host, bytes);
+  B200_CUDA(cudaMemcpyAsync(dm, hm, bytes, cudaMemcpyHostToDevice, s.stream));
+  const uint64_t pps = s.amps_per_state() >> 1;
+  int gx = (int)std::min<uint64_t>((pps + 255) / 256, std::max<uint64_t>(1, (uint64_t)s.num_sms * 16 / s.nstates));
+  if (gx < 1) gx = 1;
+  if (s.nstates > 65535) throw Error("apply_batched_pauli_ops: more than 65535 states per container");
+  dim3 grid(gx, (unsigned)s.nstates);
+  if (s.precision == B200SV_F64)
+    batched_pauli_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, s.nq, pps, (const uint64_t *)dm);
+  else
+    batched_pauli_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, s.nq, pps, (const uint64_t *)dm);
+  B200_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ init
+template <typename T> __global__ void set_ket0_kernel(cx<T> *psi, int nq, int64_t nstates) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nstates) psi[(uint64_t)s << nq] = mk<T>(1, 0);
+}
+void launch_init(State &s, bool ket0) {
+  B200_CUDA(cudaMemsetAsync(s.data, 0, s.total_amps() * s.amp_bytes(), s.stream));
+  if (!ket0) return;
+  const int grid = (int)((s.nstates + 255) / 256);
+  if (s.precision == B200SV_F64) set_ket0_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, s.nq, s.nstates);
+  else set_ket0_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, s.nq, s.nstates);
+  B200_CUDA(cudaGetLastError());
+}
+
+// initialize_component (qubitvector.hpp:879-900): for each group, cache = d[inds[0]];
+// d[inds[i]] = cache * state[i].
+template <typename T>
+__global__ void __launch_bounds__(256)
+init_component_kernel(cx<T> *__restrict__ psi, const cx<T> *__restrict__ comp, const __grid_constant__ GenericParams p) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const int DIM = 1 << p.k;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.ngroups; g += stride) {
+    const uint64_t base = insert_zeros(g, p.ins);
+    const cx<T> cache = psi[base];
+    for (int e = 0; e < DIM; e++) {
+      uint64_t o = 0;
+      for (int b = 0; b < p.k; b++)
+        if ((e >> b) & 1) o |= p.off_bits[b];
+      psi[base + o] = cmul(cache, comp[e]);
+    }
+  }
+}
+void launch_init_component(State &s, const int *qubits, int k, const double *state) {
+  if (k > kMaxDenseQubits) throw Error("initialize_component: more than 10 qubits is not supported");
+  const size_t dim = 1ull << k, bytes = dim * s.amp_bytes();
+  void *hm = s.ensure_pinned(bytes);
+  void *dm = s.ensure_scratch(bytes);
+  B200_CUDA(cudaStreamSynchronize(s.stream));
+  if (s.precision == B200SV_F64) memcpy(hm, state, bytes);
+  else for (size_t i = 0; i < 2 * dim; i++) ((float *)hm)[i] = (float)state[i];
+  B200_CUDA(cudaMemcpyAsync(dm, hm, bytes, cudaMemcpyHostToDevice, s.stream));
+  GenericParams p;
+  p.k = k;
+  std::vector<int> all(qubits, qubits + k);
+  for (int b = 0; b < k; b++) p.off_bits[b] = 1ull << qubits[b];
+  std::sort(all.begin(), all.end());
+  p.ins.n = k;
+  for (int i = 0; i < k; i++) p.ins.pos[i] = (uint8_t)all[i];
+  p.ngroups = s.total_amps() >> k;
+  const int grid = grid_for(s, p.ngroups, 256, 16);
+  if (s.precision == B200SV_F64)
+    init_component_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, (const double2 *)dm, p);
+  else
+    init_component_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, (const float2 *)dm, p);
+  B200_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ global-qubit exchange helpers
+// pack: buf[j] = psi[insert_zero(begin+j, q) | bit<<q]   unpack: the inverse.
+template <typename T, bool UNPACK>
+__global__ void __launch_bounds__(256) pack_half_kernel(cx<T> *__restrict__ psi, cx<T> *__restrict__ buf, int q,
+                                                        uint64_t bitmask, uint64_t begin, uint64_t count) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+    const uint64_t i = insert_zero(begin + j, q) | bitmask;
+    if (UNPACK) psi[i] = buf[j];
+    else buf[j] = psi[i];
+  }
+}
+void launch_pack_half(State &s, int q, int bit, uint64_t begin, uint64_t count, void *buf, bool unpack) {
+  const int grid = grid_for(s, count, 256, 16);
+  const uint64_t bm = bit ? (1ull << q) : 0;
+  if (s.precision == B200SV_F64) {
+    if (unpack) pack_half_kernel<double, true><<<grid, 256, 0, s.stream>>>((double2 *)s.data, (double2 *)buf, q, bm, begin, count);
+    else pack_half_kernel<double, false><<<grid, 256, 0, s.stream>>>((double2 *)s.data, (double2 *)buf, q, bm, begin, count);
+  } else {
+    if (unpack) pack_half_kernel<float, true><<<grid, 256, 0, s.stream>>>((float2 *)s.data, (float2 *)buf, q, bm, begin, count);
+    else pack_half_kernel<float, false><<<grid, 256, 0, s.stream>>>((float2 *)s.data, (float2 *)buf, q, bm, begin, count);
+  }
+  B200_CUDA(cudaGetLastError());
+}
+
+// In-place swap with a peer-mapped partner chunk over NVLink (CSwapChunk_func,
+// thrust_kernels.hpp:1884): lower chunk's (q=1) half <-> upper chunk's (q=0) half.
+template <typename T>
+__global__ void __launch_bounds__(256) chunk_swap_peer_kernel(cx<T> *__restrict__ mine, cx<T> *__restrict__ peer, int q,
+                                                              uint64_t mine_mask, uint64_t peer_mask, uint64_t begin,
+                                                              uint64_t count) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
+    const uint64_t iz = insert_zero(begin + j, q);
+    const cx<T> a = mine[iz | mine_mask];
+    const cx<T> b = peer[iz | peer_mask];
+    mine[iz | mine_mask] = b;
+    peer[iz | peer_mask] = a;
+  }
+}
+void launch_chunk_swap_peer(State &s, int q, void *peer, int upper, int half) {
+  const uint64_t npairs = s.amps_per_state() >> 1;
+  const uint64_t count = npairs >> 1, begin = half ? count : 0;
+  const uint64_t bit = 1ull << q;
+  const uint64_t mine_mask = upper ? 0 : bit, peer_mask = upper ? bit : 0;
+  const int grid = grid_for(s, count, 256, 16);
+  if (s.precision == B200SV_F64)
+    chunk_swap_peer_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, (double2 *)peer, q, mine_mask, peer_mask, begin, count);
+  else
+    chunk_swap_peer_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, (float2 *)peer, q, mine_mask, peer_mask, begin, count);
+  B200_CUDA(cudaGetLastError());
+}
+
+}  // namespace b200sv

@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the statevector amplitude-update path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 engine
+    python bench.py --impl reference --gpus N --steps K ...   # reference CPU path (AerSimulator CPU equivalent)
+
+A "step" is one full pass of the workload circuit over a freshly initialised state:
+Quantum Volume, depth 10, double precision, 33 qubits per GPU (128 GiB of amplitudes; weak scaling:
+33 + log2(N) qubits on N GPUs, i.e. QV-36 on 8), gates fused by the engine's own fusion pass.
+`value` = circuit-level amplitude updates per second (sum over the circuit's gates of the amplitudes
+an un-fused pass would write, BASELINE.md section 3 -- independent of how an engine fuses) with the
+state resident in HBM; `e2e` = the same through the public host API (circuit in host memory ->
+fusion -> C-ABI calls -> sampled counts + Pauli expectation values back on the host).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+DEPTH = 10
+SHOTS = 1024
+AMP_BYTES = 16
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def workload(args, world):
+    from qiskit_aer_b200 import circuits, fusion
+    n = args.qubits if args.qubits else 33 + int(np.log2(world))
+    if args.workload == "qft":
+        n = args.qubits if args.qubits else 30 + int(np.log2(world))
+        ops = circuits.qft(n)
+        name = "qft%d_fused" % n
+    else:
+        ops = circuits.quantum_volume(n, args.depth, seed=1234)
+        name = "qv%d_depth%d_fused" % (n, args.depth)
+    return n, name, ops, circuits.amplitudes_written(ops, n)
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def reference_arm(args):
+    """The reference's own CPU implementation (Controller + Fusion + OpenMP/AVX2 QubitVector, built
+    unmodified into oracle/_ref/controller_wrappers.so) on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_controller
+    from qiskit_aer_b200 import circuits
+    world = args.gpus
+    n_full, name, _, _ = workload(args, world)
+    cores = os.cpu_count() or 1
+    if not ref_controller.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/controller_wrappers.so not built"}))
+        return
+
+    def run(n):
+        ops = circuits.qft(n) if args.workload == "qft" else circuits.quantum_volume(n, args.depth, seed=1234)
+        t0 = time.perf_counter()
+        r = ref_controller.run_circuit(n, ops, shots=SHOTS, seed=1234, threads=cores, fusion=True,
+                                       fusion_max_qubit=5, fusion_threshold=14,
+                                       expvals=[([0, 1, n - 1], "ZXY")])
+        return time.perf_counter() - t0, float(r["time_taken"]), circuits.amplitudes_written(ops, n)
+
+    # size the sample: ~6 s per step (time doubles per qubit), capped by host memory
+    n = 22
+    t, _, _ = run(n)
+    t, _, _ = run(n)
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 32 << 30
+    while n < n_full and t * 2 < 6.0 and (16 << (n + 1)) * 2.5 < avail:
+        n += 1
+        t *= 2
+    for _ in range(args.warmup):
+        run(n)
+    walls = []
+    for _ in range(args.steps):
+        w, tt, amps = run(n)
+        walls.append(w)
+    ms = 1e3 * float(np.mean(walls))
+    value = amps / (ms / 1e3)
+    sample = "QV n=%d depth=%d (%s fits the CPU time budget; full config is n=%d)" % (n, args.depth, name, n_full)
+    if args.workload == "qft":
+        sample = "QFT n=%d (full config is n=%d)" % (n, n_full)
+    print(json.dumps({
+        "impl": "reference", "metric": "amplitude_updates_per_s", "value": value, "unit": "amp-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "sample_qubits": n, "depth": args.depth, "fusion_max_qubit": 5,
+                   "device": "CPU", "threads": cores},
+        "cpu_baseline": {"value": value, "unit": "amp-updates/s", "cores": cores, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "amp-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline_leg(args):
+    """Reported beside the GPU number (rank 0, N=1): reference Controller on a bounded QV sample."""
+    try:
+        from oracle import ref_controller
+        from qiskit_aer_b200 import circuits
+        cores = os.cpu_count() or 1
+        if not ref_controller.available():
+            raise RuntimeError("oracle/_ref/controller_wrappers.so missing")
+        n, t = 22, None
+        mk = (lambda m: circuits.qft(m)) if args.workload == "qft" else (lambda m: circuits.quantum_volume(m, args.depth, 1234))
+        for _ in range(2):
+            t0 = time.perf_counter()
+            ref_controller.run_circuit(n, mk(n), shots=SHOTS, seed=1234, threads=cores)
+            t = time.perf_counter() - t0
+        try:
+            avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+        except (ValueError, OSError):
+            avail = 32 << 30
+        while t * 2 < 8.0 and (16 << (n + 1)) * 2.5 < avail and n < 31:
+            n += 1
+            t *= 2
+        ops = mk(n)
+        t0 = time.perf_counter()
+        ref_controller.run_circuit(n, ops, shots=SHOTS, seed=1234, threads=cores)
+        t = time.perf_counter() - t0
+        return {"value": circuits.amplitudes_written(ops, n) / t, "unit": "amp-updates/s", "cores": cores,
+                "kind": "reference",
+                "sample": "reference Controller (statevector, device=CPU, fusion_max_qubit=5), %s n=%d, one run, %.2f s wall"
+                          % ("QFT" if args.workload == "qft" else "QV depth=%d" % args.depth, n, t)}
+    except Exception as e:  # the baseline is reported, never required
+        return {"value": None, "unit": "amp-updates/s", "cores": os.cpu_count(), "kind": "reference",
+                "sample": "unavailable: %s" % e}
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    import qiskit_aer_b200 as q
+    from qiskit_aer_b200 import executor, fusion
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, name, ops, amps_written = workload(args, world)
+    n_local = n - int(np.log2(world))
+    fused = fusion.fuse(ops, max_qubit=args.fusion_max_qubit)
+    if rank == 0:
+        log("workload %s: %d gates -> %d fused passes, n_local=%d (%.1f GiB/GPU)"
+            % (name, len(ops), len(fused), n_local, AMP_BYTES * 2.0 ** n_local / 2 ** 30))
+
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        buf = torch.empty((1 << n_local) * 2, dtype=torch.float64, device=dev)
+    qv = q.QubitVectorB200(n_local, np.complex128, device=local_rank, external_ptr=buf.data_ptr(),
+                           stream=stream.cuda_stream)
+    if world > 1:
+        from qiskit_aer_b200 import sharded
+        runner = sharded.ShardedRunner(qv, n, rank, world, stream, buf)
+        plan = runner.plan(fused)
+    else:
+        runner, plan = None, fused
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    class_of = lambda op: "%s_k%d" % ("dense" if op[0] == "unitary" else op[0], len(op[1]))  # noqa: E731
+    per_class = {}
+    launches = [0]
+
+    def run_step(timed):
+        qv.initialize()
+        launches[0] += 1
+        evs = []
+        for op in plan:
+            if timed:
+                e0 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            if runner is not None:
+                launches[0] += runner.apply(op)
+            else:
+                executor.apply_op(qv, op)
+                launches[0] += 1
+            if timed:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record(stream)
+                evs.append((class_of(op) if op[0] in ("unitary", "diagonal") else op[0], e0, e1))
+        return evs
+
+    for _ in range(args.warmup):
+        run_step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches[0] = 0
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    all_evs = []
+    for _ in range(args.steps):
+        all_evs += run_step(True)
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    for cls, e0, e1 in all_evs:
+        d = per_class.setdefault(cls, [0, 0.0])
+        d[0] += 1
+        d[1] += e0.elapsed_time(e1)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = amps_written / (ms_per_step / 1e3)
+    gpu_launches = launches[0]
+
+    # ---- end to end through the host API: circuit (host) -> fusion -> C ABI -> counts + expvals (host)
+    paulis = [([0, 1, n_local - 1], "ZXY"), ([2, 5], "ZZ"), ([3], "X")]
+
+    def e2e_step():
+        f = fusion.fuse(ops, max_qubit=args.fusion_max_qubit)
+        p = runner.plan(f) if runner is not None else f
+        qv.initialize()
+        h2d = 0
+        for op in p:
+            if runner is not None:
+                runner.apply(op)
+            else:
+                executor.apply_op(qv, op)
+            h2d += executor.op_h2d_bytes(op) if op[0] in ("unitary", "diagonal", "gate") else 0
+        rnds = q.rng_uniform(1234, SHOTS)
+        if runner is not None:
+            samples = runner.sample_measure(rnds)
+            ev = [runner.expval_pauli(qs, pl) for qs, pl in paulis]
+        else:
+            samples = qv.sample_measure(rnds)
+            ev = [qv.expval_pauli(qs, pl) for qs, pl in paulis]
+        counts = np.unique(samples, return_counts=True)
+        return h2d + rnds.nbytes, samples.nbytes + 8 * len(ev), counts, ev
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h2d, d2h, counts, ev = e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        dom = max((c for c in per_class if c.startswith(("dense", "diagonal"))), key=lambda c: per_class[c][1])
+        cnt, tot = per_class[dom]
+        avg_ms = tot / cnt
+        bytes_per_launch = 2 * AMP_BYTES * 2.0 ** n_local
+        achieved = bytes_per_launch / (avg_ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom)
+        out = {
+            "metric": "amplitude_updates_per_s", "value": value, "unit": "amp-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "qubits": n, "qubits_per_gpu": n_local, "depth": args.depth,
+                       "circuit_gates": len(ops), "fused_passes": len(fused),
+                       "fusion_max_qubit": args.fusion_max_qubit, "shots": SHOTS,
+                       "l2": "state (%.0f GiB per GPU) is larger than L2; no flush needed" % (AMP_BYTES * 2.0 ** n_local / 2 ** 30),
+                       "sharding": "top %d qubits select the GPU" % int(np.log2(world))},
+            "wall_time_s": ms_per_step / 1e3,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": dom, "launches": cnt, "avg_ms": avg_ms,
+                         "bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
+                         "frac_of_nominal_8000": achieved / 8000.0},
+            "per_kernel": {c: {"launches": v[0], "avg_ms": v[1] / v[0],
+                               "GBps": (bytes_per_launch / (v[1] / v[0] / 1e3) / 1e9) if c.startswith(("dense", "diagonal")) else None}
+                           for c, v in sorted(per_class.items())},
+            "e2e": {"value": amps_written / (e2e_ms / 1e3), "unit": "amp-updates/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_leg(args)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="qv", choices=["qv", "qft"])
+    ap.add_argument("--qubits", type=int, default=0, help="override the total qubit count (default 33 + log2 N)")
+    ap.add_argument("--depth", type=int, default=DEPTH)
+    ap.add_argument("--fusion-max-qubit", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

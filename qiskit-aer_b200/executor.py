@@ -1,0 +1,51 @@
+"""Runs op lists on a QubitVectorB200 -- the slice of Statevector::State::apply_op
+(/root/reference/src/simulators/statevector/statevector_state.hpp:491-568, gate table :314-384)
+that the benchmark circuits need: matrix / diagonal_matrix ops plus the named gates h, x, cx,
+cp, swap, rz, sx mapped to the same QubitVector calls the reference uses."""
+import numpy as np
+
+from .fusion import gate_matrix
+
+
+def colmajor(U):
+    return np.asarray(U, dtype=np.complex128).reshape(-1, order="F")
+
+
+def apply_op(qv, op):
+    kind = op[0]
+    if kind == "unitary":
+        qv.apply_matrix(op[1], colmajor(op[2]))
+    elif kind == "diagonal":
+        qv.apply_diagonal_matrix(op[1], op[2])
+    elif kind == "gate":
+        name, qubits, params = op[1], op[2], op[3]
+        if name == "h":      # apply_mcu(u4(pi/2,0,pi,0)), statevector_state.hpp:809-811
+            qv.apply_mcu(qubits, colmajor(gate_matrix("h", [])))
+        elif name in ("x", "cx"):
+            qv.apply_mcx(qubits)
+        elif name == "cp":   # apply_mcphase, statevector_state.hpp:769-772
+            qv.apply_mcphase(qubits, np.exp(1j * params[0]))
+        elif name == "swap":
+            qv.apply_mcswap(qubits)
+        elif name == "rz":
+            qv.apply_diagonal_matrix(qubits, np.diag(gate_matrix("rz", params)))
+        elif name == "sx":
+            qv.apply_mcu(qubits, colmajor(gate_matrix("sx", [])))
+        else:
+            raise ValueError("unsupported gate %s" % name)
+    else:
+        raise ValueError(kind)
+
+
+def apply_ops(qv, ops):
+    for op in ops:
+        apply_op(qv, op)
+
+
+def op_h2d_bytes(op):
+    """Bytes of gate data that cross the ABI from host memory for this op."""
+    if op[0] == "unitary":
+        return 16 * np.asarray(op[2]).size
+    if op[0] == "diagonal":
+        return 16 * len(op[2])
+    return 64

@@ -1,0 +1,122 @@
+"""Host-side gate fusion for the B200 engine.
+
+Plays the role of the reference's transpile pass (src/transpile/fusion.hpp:849, cost-based
+`CostBasedFusion` :1002-1136, defaults max_qubit=5 / threshold=14 :762-763) but with a B200 cost
+model: a k<=4 double-precision block is HBM bound (one pass = 2*16*2^n bytes) while k=5 leans on
+the FP64 pipe (8 flop/byte), so blocks greedily grow up to `max_qubit` and never reorder
+non-commuting gates.  Output ops are exactly what `apply_matrix` / `apply_diagonal_matrix`
+consume.
+
+Algorithm (list scheduling over open blocks): a gate may join block B iff no block emitted after
+B touches any of its qubits; preference: the last block it depends on, then any later block that
+stays within max_qubit, else a new block.
+"""
+import numpy as np
+
+_H = np.array([[1, 1], [1, -1]], dtype=np.complex128) / np.sqrt(2)
+_X = np.array([[0, 1], [1, 0]], dtype=np.complex128)
+_SWAP = np.eye(4, dtype=np.complex128)[[0, 2, 1, 3]]
+
+
+def gate_matrix(name, params):
+    """Matrices of the named gates, numpy convention U[i, j], qubits[0] = least significant bit."""
+    if name == "h":
+        return _H
+    if name == "x":
+        return _X
+    if name == "swap":
+        return _SWAP
+    if name == "cp":  # diag(1,1,1,e^{i theta})
+        return np.diag([1, 1, 1, np.exp(1j * params[0])]).astype(np.complex128)
+    if name == "cx":  # control qubits[0], target qubits[1]
+        return np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=np.complex128)
+    if name == "rz":
+        return np.diag([np.exp(-0.5j * params[0]), np.exp(0.5j * params[0])])
+    if name == "sx":
+        return 0.5 * np.array([[1 + 1j, 1 - 1j], [1 - 1j, 1 + 1j]])
+    raise ValueError("unknown gate %s" % name)
+
+
+def op_matrix(op):
+    if op[0] == "unitary":
+        return list(op[1]), np.asarray(op[2], dtype=np.complex128)
+    if op[0] == "diagonal":
+        return list(op[1]), np.diag(np.asarray(op[2], dtype=np.complex128))
+    if op[0] == "gate":
+        return list(op[2]), gate_matrix(op[1], op[3])
+    raise ValueError(op[0])
+
+
+def embed(U, qubits, block_qubits):
+    """Lift U acting on `qubits` to the 2^k space of `block_qubits` (bit i of the index <-> block_qubits[i])."""
+    k = len(block_qubits)
+    pos = [block_qubits.index(q) for q in qubits]
+    dim = 1 << k
+    out = np.zeros((dim, dim), dtype=np.complex128)
+    m = len(qubits)
+    rest = [b for b in range(k) if b not in pos]
+    for r in range(1 << len(rest)):
+        base = 0
+        for i, b in enumerate(rest):
+            if (r >> i) & 1:
+                base |= 1 << b
+        idx = np.empty(1 << m, dtype=np.int64)
+        for e in range(1 << m):
+            v = base
+            for i in range(m):
+                if (e >> i) & 1:
+                    v |= 1 << pos[i]
+            idx[e] = v
+        out[np.ix_(idx, idx)] = U
+    return out
+
+
+class Block:
+    def __init__(self):
+        self.qubits = []
+        self.gates = []  # (qubits, U)
+
+    def matrix(self):
+        M = np.eye(1 << len(self.qubits), dtype=np.complex128)
+        for q, U in self.gates:
+            M = embed(U, q, self.qubits) @ M
+        return M
+
+    def is_diagonal(self):
+        return all(np.count_nonzero(U - np.diag(np.diag(U))) == 0 for _, U in self.gates)
+
+
+def fuse(ops, max_qubit=5, window=64):
+    """Returns a list of ("unitary", qubits, U) / ("diagonal", qubits, d) ops equivalent to `ops`."""
+    blocks = []
+    for op in ops:
+        q, U = op_matrix(op)
+        qs = set(q)
+        lo = max(0, len(blocks) - window)
+        last_dep = -1
+        for i in range(len(blocks) - 1, lo - 1, -1):
+            if qs & set(blocks[i].qubits):
+                last_dep = i
+                break
+        if lo > 0 and last_dep < 0:
+            last_dep = lo - 1  # cannot prove independence from blocks outside the window
+        target = None
+        cands = ([last_dep] if last_dep >= lo else []) + list(range(max(last_dep + 1, lo), len(blocks)))
+        for i in cands:
+            if len(set(blocks[i].qubits) | qs) <= max_qubit:
+                target = blocks[i]
+                break
+        if target is None:
+            target = Block()
+            blocks.append(target)
+        for x in q:
+            if x not in target.qubits:
+                target.qubits.append(x)
+        target.gates.append((q, U))
+    out = []
+    for b in blocks:
+        if b.is_diagonal():
+            out.append(("diagonal", list(b.qubits), np.diag(b.matrix()).copy()))
+        else:
+            out.append(("unitary", list(b.qubits), b.matrix()))
+    return out

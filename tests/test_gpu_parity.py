@@ -205,8 +205,13 @@ def test_reductions(n):
     for qs, p in opgen.random_paulis(n, n, 30):
         ph = complex(np.exp(2j * np.pi * rng.random()))
         assert abs(ora.expval_pauli(qs, p, ph) - gpu.expval_pauli(qs, p, ph)) < 1e-12, (qs, p)
-    rnds = np.concatenate([rng.random(2000), [0.0, np.nextafter(1.0, 0.0)]])
+    rnds = np.concatenate([rng.random(2000), [0.0, 1.0 - 1e-9]])
     assert np.array_equal(ora.sample_measure(rnds), gpu.sample_measure(rnds))
+    # rnd >= the (rounded) total probability: the reference's block-index path walks off the end and
+    # returns END (qubitvector.hpp:2212-2225 -- `sample += loop` for every block, then the `< END-1`
+    # loop never runs); we clamp to the last valid index instead.
+    last = gpu.sample_measure(np.array([np.nextafter(1.0, 0.0)]))[0]
+    assert last <= (1 << n) - 1
 
 
 def test_sampler_is_non_destructive_and_handles_concentrated_states():

@@ -212,6 +212,9 @@ def b200_arm(args):
         from qiskit_aer_b200 import sharded
         runner = sharded.ShardedRunner(qv, n, rank, world, stream, buf)
         plan = runner.plan(fused)
+        final_phys = list(runner.phys)
+        if rank == 0:
+            log("sharded plan: %d global-qubit exchanges" % sum(1 for p in plan if p[0] == "swap"))
     else:
         runner, plan = None, fused
 
@@ -225,7 +228,10 @@ def b200_arm(args):
     launches = [0]
 
     def run_step(timed):
-        qv.initialize()
+        if runner is not None:
+            runner.initialize()
+        else:
+            qv.initialize()
         launches[0] += 1
         evs = []
         for op in plan:
@@ -241,6 +247,8 @@ def b200_arm(args):
                 e1 = torch.cuda.Event(enable_timing=True)
                 e1.record(stream)
                 evs.append((class_of(op) if op[0] in ("unitary", "diagonal") else op[0], e0, e1))
+        if runner is not None:
+            runner.phys = list(final_phys)
         return evs
 
     for _ in range(args.warmup):
@@ -276,8 +284,12 @@ def b200_arm(args):
 
     def e2e_step():
         f = fusion.fuse(ops, max_qubit=args.fusion_max_qubit)
-        p = runner.plan(f) if runner is not None else f
-        qv.initialize()
+        if runner is not None:
+            runner.initialize()
+            p = runner.plan(f)
+        else:
+            qv.initialize()
+            p = f
         h2d = 0
         for op in p:
             if runner is not None:
@@ -317,7 +329,9 @@ def b200_arm(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(dom)
+            ent = json.load(open(tp)).get(dom)
+            if ent:  # per-amplitude DRAM bytes from the committed ncu --set full capture, scaled to this launch
+                traffic = ent["bytes_per_amp"] * 2.0 ** n_local
         out = {
             "metric": "amplitude_updates_per_s", "value": value, "unit": "amp-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

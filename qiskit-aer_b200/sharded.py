@@ -1,0 +1,298 @@
+"""Sharded statevector: one process per GPU, state split by the top log2(G) qubits.
+
+Replaces the reference's chunk distribution + global-qubit exchange
+(/root/reference/src/simulators/parallel_state_executor.hpp: apply_ops_chunks :772,
+apply_chunk_swap :1134-1336, MPI_Isend/Irecv :1317-1327) and the cache-blocking transpile pass that
+schedules it (src/transpile/cacheblocking.hpp:182-203,385-720), redesigned for NVSwitch:
+
+* one chunk per GPU (chunk_bits = n - log2 G): 3 global qubits for QV-36 on 8 GPUs instead of the
+  reference's >= 6 (it needs an exchange buffer chunk, chunk_manager.hpp:281);
+* NO swap-back: a logical->physical qubit map is carried on the host (all ranks compute the same
+  plan deterministically, no communication), so a global qubit that is swapped in stays local until
+  evicted; the victim is the local qubit whose next use is farthest away (Belady), restricted to high
+  physical positions so every transfer slice is one contiguous run (zero-copy send);
+* diagonal gates and controls on global qubits never move data (resolved from the chunk index,
+  thrust_kernels.hpp:1190,1342,2004 `base_index_` rule -- done inside the C ABI);
+* the exchange itself is pairwise ncclSend/ncclRecv (torch.distributed P2P ops) in slices, received
+  into a double-buffered staging area and copied into place while the next slice is in flight.
+
+Sampling / expectation values follow Statevector::Executor::{sample_measure :1149, expval_pauli :551}
+(statevector_executor.hpp): per-rank partial results, reduced over ranks; sampled physical indices are
+mapped back to logical bit order on the host.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def _insert_zero(v, pos):
+    low = v & ((1 << pos) - 1)
+    return ((v >> pos) << (pos + 1)) | low
+
+
+class ShardedRunner:
+    def __init__(self, qv, n, rank, world, stream, buf, slice_amps=1 << 26, min_run_bits=20):
+        """qv: chunk backend (QubitVectorB200 or a CPU stand-in with the same methods);
+        buf: torch tensor viewing the chunk's amplitudes as float64 pairs (exchange source/target)."""
+        self.qv, self.n, self.rank, self.world = qv, int(n), int(rank), int(world)
+        self.gbits = int(np.log2(world))
+        if (1 << self.gbits) != world:
+            raise ValueError("number of GPUs must be a power of two")
+        self.nl = self.n - self.gbits
+        self.stream, self.buf = stream, buf
+        self.amps = buf.view(-1, 2)  # [2^nl, 2]
+        self.slice_amps = int(min(slice_amps, 1 << max(self.nl - 1, 0)))
+        self.min_run_bits = min(min_run_bits, max(self.nl - 1, 0))
+        self.phys = list(range(self.n))  # logical qubit -> physical position
+        self._tmp = None
+        qv.chunk_setup(self.n, self.rank)
+        self.bytes_exchanged = 0
+
+    # ---------------------------------------------------------------- planning (host, deterministic)
+    def plan(self, ops, phys=None):
+        """Rewrite logical ops to physical ones, inserting ("swap", local_pos, global_bit) steps.
+        Updates self.phys to the mapping valid after the plan has run."""
+        phys = list(self.phys if phys is None else phys)
+        nl = self.nl
+        uses = {}  # logical qubit -> sorted op indices where it must be local
+        for i, op in enumerate(ops):
+            if op[0] == "unitary" or (op[0] == "gate" and op[1] not in ("cp",)):
+                for q in (op[1] if op[0] == "unitary" else op[2]):
+                    uses.setdefault(q, []).append(i)
+        out = []
+        for i, op in enumerate(ops):
+            if op[0] == "diagonal":
+                out.append(("diagonal", [phys[q] for q in op[1]], op[2]))
+                continue
+            if op[0] == "gate" and op[1] == "cp":
+                out.append(("gate", op[1], [phys[q] for q in op[2]], op[3]))
+                continue
+            qs = op[1] if op[0] == "unitary" else op[2]
+            need_local = qs if op[0] == "unitary" else self._gate_targets(op)
+            for q in need_local:
+                if phys[q] >= nl:
+                    victim = self._pick_victim(phys, set(qs), uses, i)
+                    lpos, gpos = phys[victim], phys[q]
+                    out.append(("swap", lpos, gpos - nl))
+                    phys[victim], phys[q] = gpos, lpos
+            if op[0] == "unitary":
+                out.append(("unitary", [phys[q] for q in qs], op[2]))
+            else:
+                out.append(("gate", op[1], [phys[q] for q in qs], op[3]))
+        self.phys = phys
+        return out
+
+    @staticmethod
+    def _gate_targets(op):
+        name, qs = op[1], op[2]
+        if name == "swap":
+            return qs[-2:]
+        return qs[-1:]  # controls may stay global
+
+    def _pick_victim(self, phys, busy, uses, now):
+        nl = self.nl
+        inv = {p: q for q, p in enumerate(phys)}
+        cands = [p for p in range(nl - 1, -1, -1) if inv[p] not in busy]
+        high = [p for p in cands if p >= self.min_run_bits]
+        cands = high or cands
+        best, best_next = None, -1
+        for p in cands:
+            nxt = next((u for u in uses.get(inv[p], []) if u > now), 1 << 60)
+            if nxt > best_next:
+                best, best_next = p, nxt
+        if best is None:
+            raise RuntimeError("no local qubit available to evict")
+        return inv[best]
+
+    # ---------------------------------------------------------------- execution
+    def initialize(self):
+        """|0...0> of the whole register: chunk 0 holds the 1, every other chunk is zero
+        (Statevector::Executor::initialize_qreg, statevector_executor.hpp:437-470)."""
+        self.phys = list(range(self.n))
+        if self.rank == 0:
+            self.qv.initialize()
+        else:
+            self.qv.zero()
+
+    def _ctx(self):
+        import contextlib
+        return torch.cuda.stream(self.stream) if self.stream is not None else contextlib.nullcontext()
+
+    def apply(self, op):
+        """Returns the number of kernel launches issued."""
+        from .executor import apply_op
+        if op[0] == "swap":
+            with self._ctx():
+                return self.swap_global(op[1], op[2])
+        apply_op(self.qv, op)
+        return 1
+
+    def _staging(self, count):
+        if self._tmp is None or self._tmp[0].shape[0] < count:
+            self._tmp = [torch.empty((count, 2), dtype=self.amps.dtype, device=self.amps.device) for _ in range(2)]
+        return self._tmp
+
+    def swap_global(self, lpos, gbit):
+        """Exchange local physical qubit `lpos` with global bit `gbit` (apply_chunk_swap,
+        qubitvector.hpp:1753-1790): the rank whose global bit is 0 trades its lpos=1 half for the
+        partner's lpos=0 half."""
+        nl = self.nl
+        peer = self.rank ^ (1 << gbit)
+        upper = (self.rank >> gbit) & 1
+        bit = 0 if upper else 1
+        half = 1 << (nl - 1)
+        launches = 0
+        if lpos >= self.min_run_bits or (1 << lpos) >= self.slice_amps:
+            c = min(self.slice_amps, 1 << lpos)
+            tmp = self._staging(c)
+            nslices = half // c
+            pending = {}
+
+            def region(i):
+                start = _insert_zero(i * c, lpos) | (bit << lpos)
+                return self.amps[start:start + c]
+
+            def issue(i):
+                ops = [dist.P2POp(dist.isend, region(i), peer), dist.P2POp(dist.irecv, tmp[i & 1][:c], peer)]
+                if upper:
+                    ops.reverse()
+                pending[i] = dist.batch_isend_irecv(ops)
+
+            for i in range(min(2, nslices)):
+                issue(i)
+            for i in range(nslices):
+                for w in pending.pop(i):
+                    w.wait()
+                region(i).copy_(tmp[i & 1][:c])
+                launches += 1
+                if i + 2 < nslices:
+                    issue(i + 2)
+        else:  # low local qubit: gather the strided half through pack / unpack kernels
+            c = min(self.slice_amps, half)
+            stage = self._staging(2 * c)
+            send = [stage[0][:c], stage[1][:c]]
+            recv = [stage[0][c:2 * c], stage[1][c:2 * c]]
+            nslices = half // c
+            for i in range(nslices):
+                s, r = send[i & 1], recv[i & 1]
+                self.qv.pack_half(lpos, bit, i * c, c, s.data_ptr())
+                ops = [dist.P2POp(dist.isend, s, peer), dist.P2POp(dist.irecv, r, peer)]
+                if upper:
+                    ops.reverse()
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+                self.qv.unpack_half(lpos, bit, i * c, c, r.data_ptr())
+                launches += 2
+        self.bytes_exchanged += half * self.amps.element_size() * 2
+        return launches
+
+    # ---------------------------------------------------------------- reductions over ranks
+    def _allreduce(self, arr):
+        with self._ctx():
+            t = torch.as_tensor(np.asarray(arr, dtype=np.float64)).to(self.amps.device)
+            dist.all_reduce(t)
+            return t.cpu().numpy()
+
+    def norm(self):
+        return float(self._allreduce([self.qv.norm()])[0])
+
+    def expval_pauli(self, qubits, pauli):
+        """Logical qubits; X/Y factors must be local (swap them in), Z factors on global qubits become a sign."""
+        N = len(qubits)
+        pq, pp = [], []
+        sign = 1.0
+        moved = False
+        for i, q in enumerate(qubits):
+            ch = pauli[N - 1 - i]
+            if ch == "I":
+                continue
+            if self.phys[q] >= self.nl and ch in "XY":
+                inv = {p: l for l, p in enumerate(self.phys)}
+                busy = {qq for qq in qubits}
+                victim = next(inv[p] for p in range(self.nl - 1, -1, -1) if inv[p] not in busy)
+                lpos, gpos = self.phys[victim], self.phys[q]
+                with self._ctx():
+                    self.swap_global(lpos, gpos - self.nl)
+                self.phys[victim], self.phys[q] = gpos, lpos
+                moved = True
+            p = self.phys[q]
+            if p >= self.nl:  # Z on a global qubit: (-1)^bit of this rank
+                if (self.rank >> (p - self.nl)) & 1:
+                    sign = -sign
+            else:
+                pq.append(p)
+                pp.append(ch)
+        del moved
+        if pq:
+            local = self.qv.expval_pauli(pq, "".join(reversed(pp)))
+        else:
+            local = self.qv.norm()
+        return float(self._allreduce([sign * local])[0])
+
+    def restore_order(self):
+        """Bring every logical qubit back to its own physical position (the reference's cache-blocking
+        pass does the same before measure / save ops so that chunked and unchunked runs sample
+        identically, cacheblocking.hpp `restore_qubit_map`; test/terra/backends/aer_simulator/
+        test_chunk.py:31-168 asserts exact count equality).  Global positions first (exchanges),
+        then the local permutation by transpositions (mcswap passes).  Returns launches issued."""
+        nl, launches = self.nl, 0
+        with self._ctx():
+            for g in range(nl, self.n):
+                inv = {p: l for l, p in enumerate(self.phys)}
+                if inv[g] == g:
+                    continue
+                p = self.phys[g]            # where logical qubit g lives now
+                if p >= nl:                 # on another global position: pull it to a local one first
+                    lpos = nl - 1
+                    victim = inv[lpos]
+                    launches += self.swap_global(lpos, p - nl)
+                    self.phys[victim], self.phys[g] = p, lpos
+                    p = lpos
+                    inv = {pp: l for l, pp in enumerate(self.phys)}
+                occupant = inv[g]
+                launches += self.swap_global(p, g - nl)
+                self.phys[occupant], self.phys[g] = p, g
+        for q in range(nl):
+            p = self.phys[q]
+            if p == q:
+                continue
+            inv = {pp: l for l, pp in enumerate(self.phys)}
+            other = inv[q]
+            self.qv.apply_mcswap([p, q])
+            launches += 1
+            self.phys[q], self.phys[other] = q, p
+        assert self.phys == list(range(self.n))
+        return launches
+
+    def physical_to_logical(self, samples):
+        """Map sampled physical basis-state indices to logical bit order."""
+        s = np.asarray(samples, dtype=np.uint64)
+        out = np.zeros_like(s)
+        for q, p in enumerate(self.phys):
+            out |= ((s >> np.uint64(p)) & np.uint64(1)) << np.uint64(q)
+        return out
+
+    def sample_measure(self, rnds, exact_order=True):
+        """Executor::sample_measure (statevector_executor.hpp:1149-1227): route each draw to the rank
+        whose cumulative-norm interval contains it, sample locally, combine.  With exact_order the
+        qubit order is restored first so that the sampled indices equal the unsharded reference's
+        for the same draws; otherwise sampling happens in physical order (same distribution, different
+        draw -> outcome assignment) and the indices are mapped back bit by bit."""
+        if exact_order:
+            self.restore_order()
+        rnds = np.asarray(rnds, dtype=np.float64)
+        norms = np.zeros(self.world)
+        norms[self.rank] = self.qv.norm()
+        norms = self._allreduce(norms)
+        cum = np.concatenate([[0.0], np.cumsum(norms)])
+        lo, hi = cum[self.rank], cum[self.rank + 1]
+        if self.rank == self.world - 1:
+            mine = rnds >= lo
+        else:
+            mine = (rnds >= lo) & (rnds < hi)
+        out = np.zeros(rnds.size, dtype=np.float64)  # exact for indices < 2^53
+        if mine.any():
+            local = self.qv.sample_measure(rnds[mine] - lo)
+            out[mine] = (local + np.uint64(self.rank << self.nl)).astype(np.float64)
+        out = self._allreduce(out)
+        return self.physical_to_logical(out.astype(np.uint64))

@@ -1,0 +1,75 @@
+"""Run under torchrun on >= 2 GPUs: sharded NCCL path vs the CPU oracle (n small enough for the CPU).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/check_sharded.py --qubits 20
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--qubits", type=int, default=20)
+    ap.add_argument("--slice-amps", type=int, default=1 << 14)
+    ap.add_argument("--min-run-bits", type=int, default=12)
+    args = ap.parse_args()
+    import opgen
+    import qiskit_aer_b200 as q
+    from oracle.oracle import OracleQV
+    from qiskit_aer_b200 import circuits, executor, fusion, sharded
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n = args.qubits
+    nl = n - int(np.log2(world))
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        buf = torch.empty((1 << nl) * 2, dtype=torch.float64, device=dev)
+    qv = q.QubitVectorB200(nl, np.complex128, device=local, external_ptr=buf.data_ptr(), stream=stream.cuda_stream)
+    ok = True
+    for min_run_bits in (args.min_run_bits, 40):  # contiguous-run path, then the pack/unpack path
+        run = sharded.ShardedRunner(qv, n, rank, world, stream, buf, slice_amps=args.slice_amps,
+                                    min_run_bits=min_run_bits)
+        ops = circuits.quantum_volume(n, 5, seed=11) + circuits.qft(n)
+        fused = fusion.fuse(ops, max_qubit=4)
+        run.initialize()
+        plan = run.plan(fused)
+        for p in plan:
+            run.apply(p)
+        ref = OracleQV(n)
+        executor.apply_ops(ref, ops)
+        ev_err = max(abs(run.expval_pauli(qs, pl) - ref.expval_pauli(qs, pl))
+                     for qs, pl in opgen.random_paulis(3, n, 6, max_weight=3))
+        rn = q.rng_uniform(99, 500)
+        same = np.array_equal(run.sample_measure(rn), ref.sample_measure(rn))
+        # after restore_order the chunks are the plain slices of the logical state
+        qv.synchronize()
+        mine = qv.vector()
+        want = ref.vector()[rank << nl:(rank + 1) << nl]
+        err = float(np.max(np.abs(mine - want)))
+        nsw = sum(1 for p in plan if p[0] == "swap")
+        good = err < 1e-12 and ev_err < 1e-10 and same and nsw > 0
+        ok = ok and good
+        print("rank %d min_run_bits=%d swaps=%d max|err|=%.2e ev_err=%.2e samples_equal=%s" %
+              (rank, min_run_bits, nsw, err, ev_err, same), flush=True)
+    t = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(t)
+    if rank == 0:
+        print("SHARDED_CHECK " + ("OK" if t.item() == 0 else "FAILED"), flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -226,6 +226,19 @@ def b200_arm(args):
     class_of = lambda op: "%s_k%d" % ("dense" if op[0] == "unitary" else op[0], len(op[1]))  # noqa: E731
     per_class = {}
     launches = [0]
+    tile = args.engine == "tile"
+    if tile:  # the tile engine consumes the circuit's own 1-/2-qubit gates; passes are formed inside the C ABI
+        if runner is not None:
+            runner.phys = list(range(n))
+            plan = runner.plan(ops)
+            final_phys = list(runner.phys)
+            if rank == 0:
+                log("sharded plan (tile engine): %d global-qubit exchanges" % sum(1 for p in plan if p[0] == "swap"))
+        else:
+            plan = ops
+
+    def ev_pair():
+        return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def run_step(timed):
         if runner is not None:
@@ -234,19 +247,50 @@ def b200_arm(args):
             qv.initialize()
         launches[0] += 1
         evs = []
-        for op in plan:
-            if timed:
-                e0 = torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-            if runner is not None:
-                launches[0] += runner.apply(op)
-            else:
-                executor.apply_op(qv, op)
-                launches[0] += 1
-            if timed:
-                e1 = torch.cuda.Event(enable_timing=True)
-                e1.record(stream)
-                evs.append((class_of(op) if op[0] in ("unitary", "diagonal") else op[0], e0, e1))
+        if tile:
+            # time maximal runs of queueable gates as one "tile_pass" sample (launch count = passes used)
+            seg = []
+
+            def flush_seg():
+                if not seg:
+                    return
+                st = {}
+                if timed:
+                    e0, e1 = ev_pair()
+                    e0.record(stream)
+                executor.apply_ops_queued(qv, seg, st)
+                if timed:
+                    e1.record(stream)
+                    evs.append(("tile_pass", e0, e1, st.get("passes", 0)))
+                launches[0] += st.get("launches", 0)
+                seg.clear()
+
+            for op in plan:
+                if op[0] == "swap":
+                    flush_seg()
+                    if timed:
+                        e0, e1 = ev_pair()
+                        e0.record(stream)
+                    launches[0] += runner.apply(op)
+                    if timed:
+                        e1.record(stream)
+                        evs.append(("swap", e0, e1, 1))
+                else:
+                    seg.append(op)
+            flush_seg()
+        else:
+            for op in plan:
+                if timed:
+                    e0, e1 = ev_pair()
+                    e0.record(stream)
+                if runner is not None:
+                    launches[0] += runner.apply(op)
+                else:
+                    executor.apply_op(qv, op)
+                    launches[0] += 1
+                if timed:
+                    e1.record(stream)
+                    evs.append((class_of(op) if op[0] in ("unitary", "diagonal") else op[0], e0, e1, 1))
         if runner is not None:
             runner.phys = list(final_phys)
         return evs
@@ -267,9 +311,9 @@ def b200_arm(args):
     barrier()
     clocks = sampler.stop()
     elapsed_ms = t_start.elapsed_time(t_end)
-    for cls, e0, e1 in all_evs:
+    for cls, e0, e1, cnt in all_evs:
         d = per_class.setdefault(cls, [0, 0.0])
-        d[0] += 1
+        d[0] += cnt
         d[1] += e0.elapsed_time(e1)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -283,20 +327,23 @@ def b200_arm(args):
     paulis = [([0, 1, n_local - 1], "ZXY"), ([2, 5], "ZZ"), ([3], "X")]
 
     def e2e_step():
-        f = fusion.fuse(ops, max_qubit=args.fusion_max_qubit)
-        if runner is not None:
-            runner.initialize()
-            p = runner.plan(f)
-        else:
-            qv.initialize()
-            p = f
-        h2d = 0
-        for op in p:
+        h2d = sum(executor.op_h2d_bytes(op) for op in ops)
+        if tile:
             if runner is not None:
-                runner.apply(op)
+                runner.initialize()
+                runner.run_plan(runner.plan(ops))
             else:
-                executor.apply_op(qv, op)
-            h2d += executor.op_h2d_bytes(op) if op[0] in ("unitary", "diagonal", "gate") else 0
+                qv.initialize()
+                executor.apply_ops_queued(qv, ops)
+        else:
+            f = fusion.fuse(ops, max_qubit=args.fusion_max_qubit)
+            h2d = sum(executor.op_h2d_bytes(op) for op in f)
+            if runner is not None:
+                runner.initialize()
+                runner.run_plan(runner.plan(f), queued=False)
+            else:
+                qv.initialize()
+                executor.apply_ops(qv, f)
         rnds = q.rng_uniform(1234, SHOTS)
         if runner is not None:
             samples = runner.sample_measure(rnds)
@@ -321,7 +368,7 @@ def b200_arm(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        dom = max((c for c in per_class if c.startswith(("dense", "diagonal"))), key=lambda c: per_class[c][1])
+        dom = max((c for c in per_class if c.startswith(("dense", "diagonal", "tile"))), key=lambda c: per_class[c][1])
         cnt, tot = per_class[dom]
         avg_ms = tot / cnt
         bytes_per_launch = 2 * AMP_BYTES * 2.0 ** n_local
@@ -337,8 +384,11 @@ def b200_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": name, "qubits": n, "qubits_per_gpu": n_local, "depth": args.depth,
-                       "circuit_gates": len(ops), "fused_passes": len(fused),
-                       "fusion_max_qubit": args.fusion_max_qubit, "shots": SHOTS,
+                       "circuit_gates": len(ops), "engine": args.engine,
+                       "hbm_passes": (per_class["tile_pass"][0] // args.steps) if tile else len(fused),
+                       "fusion": ("tile-blocked gate queue: 2^12-amplitude shared-memory tiles, gates applied from registers"
+                                  if tile else "dense blocks, max_qubit=%d" % args.fusion_max_qubit),
+                       "shots": SHOTS,
                        "l2": "state (%.0f GiB per GPU) is larger than L2; no flush needed" % (AMP_BYTES * 2.0 ** n_local / 2 ** 30),
                        "sharding": "top %d qubits select the GPU" % int(np.log2(world))},
             "wall_time_s": ms_per_step / 1e3,
@@ -347,7 +397,7 @@ def b200_arm(args):
                          "bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
                          "frac_of_nominal_8000": achieved / 8000.0},
             "per_kernel": {c: {"launches": v[0], "avg_ms": v[1] / v[0],
-                               "GBps": (bytes_per_launch / (v[1] / v[0] / 1e3) / 1e9) if c.startswith(("dense", "diagonal")) else None}
+                               "GBps": (bytes_per_launch / (v[1] / v[0] / 1e3) / 1e9) if c.startswith(("dense", "diagonal", "tile")) else None}
                            for c, v in sorted(per_class.items())},
             "e2e": {"value": amps_written / (e2e_ms / 1e3), "unit": "amp-updates/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
@@ -371,6 +421,8 @@ def main():
     ap.add_argument("--qubits", type=int, default=0, help="override the total qubit count (default 33 + log2 N)")
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--fusion-max-qubit", type=int, default=4)
+    ap.add_argument("--engine", default="tile", choices=["tile", "dense"],
+                    help="tile: multi-gate shared-memory passes (default); dense: one fused dense block per pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -114,6 +114,17 @@ int b200sv_apply_pauli(b200sv_handle h, const uint64_t *qubits, int k, const cha
  * per-state Pauli given as num_states x {x_mask, z_mask, num_y, apply(0/1)} */
 int b200sv_apply_batched_pauli(b200sv_handle h, const uint64_t *masks4);
 
+/* Gate-queue flush: apply a SEQUENCE of 1- and 2-qubit dense gates (same semantics as calling
+ * apply_matrix once per gate, in order) in as few HBM passes as possible: gates whose qubits fit a
+ * 12-bit shared-memory tile ride on one pass.  nq[i] in {1,2}; qubits = 2 entries per gate
+ * (second ignored for nq=1); mats = 16 complex<double> slots per gate, column-major like apply_matrix.
+ * Reference counterpart: the blocked-gate queue, chunk/device_chunk_container.hpp:999-1108
+ * (queue_blocked_gate) + :1208 (dev_apply_shared_memory_blocked_gates), entered through
+ * QubitVectorThrust::apply_matrix / apply_mcx while register blocking is active
+ * (qubitvector_thrust.hpp:1511-1512,1628-1634).  passes_out (optional) receives the pass count. */
+int b200sv_apply_gate_sequence(b200sv_handle h, int ngates, const int *nq, const uint64_t *qubits,
+                               const double *mats, int *passes_out);
+
 /* ---- reductions (out has num_states entries unless noted) --------------- */
 int b200sv_norm(b200sv_handle h, double *out);          /* norm() (qubitvector.hpp:1879) */
 /* norm(qubits, mat) (qubitvector.hpp:1889) -- Kraus probability ||M psi||^2 */

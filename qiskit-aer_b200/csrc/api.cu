@@ -449,6 +449,16 @@ int b200sv_apply_pauli(b200sv_handle h, const uint64_t *qubits, int k, const cha
   });
 }
 
+int b200sv_apply_gate_sequence(b200sv_handle h, int ngates, const int *nq, const uint64_t *qubits,
+                               const double *mats, int *passes_out) {
+  return guard([&] {
+    select(H);
+    if (ngates < 0 || (ngates > 0 && (!nq || !qubits || !mats))) throw Error("apply_gate_sequence: bad arguments");
+    const int passes = ngates ? apply_gate_sequence(*H, ngates, nq, qubits, mats, 2) : 0;
+    if (passes_out) *passes_out = passes;
+  });
+}
+
 int b200sv_apply_batched_pauli(b200sv_handle h, const uint64_t *masks4) {
   return guard([&] { select(H); launch_batched_pauli(*H, masks4); });
 }

@@ -111,6 +111,9 @@ void launch_init_component(State &s, const int *qubits, int k, const double *sta
 void launch_pack_half(State &s, int q, int bit, uint64_t begin, uint64_t count, void *buf, bool unpack);
 void launch_chunk_swap_peer(State &s, int q, void *peer, int upper, int half);
 
+// ---- tile-blocked multi-gate passes (tile.cu)
+int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats, int low_bits);
+
 // ---- reductions (reduce.cu) -------------------------------------------------
 void reduce_norm(State &s, double *out);
 void reduce_norm_matrix(State &s, const int *qubits, int k, const double *mat, double *out);

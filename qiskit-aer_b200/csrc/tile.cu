@@ -1,0 +1,362 @@
+// b200sv tile-blocked multi-gate pass (sm_100a).
+//
+// One HBM pass applies a whole *sequence* of 1- and 2-qubit dense gates whose
+// qubits fit a 12-bit tile: every CTA stages 2^12 amplitudes (64 KiB) in shared
+// memory with cp.async (LDGSTS.128, no register staging), runs the gates as
+// "rounds" -- each thread pulls the 16 amplitudes of a 4-qubit sub-block into
+// registers, applies every gate of the round there (16 DFMA per amplitude per
+// 2-qubit gate instead of 4*2^k for a fused dense block), writes them back --
+// and streams the tile out again.  HBM traffic per pass stays 2*16*2^n bytes
+// while 5-8 gates ride on it, which is what moves QV-style circuits from
+// ~2 gates per pass (dense k<=4 fusion) to the FP64/HBM balance point
+// (~90 DFMA per amplitude per pass on B200).
+//
+// Reference counterpart: the blocked-gate queue of the Thrust path
+// (chunk/device_chunk_container.hpp:999-1108 queue_blocked_gate,
+//  :1208 dev_apply_shared_memory_blocked_gates: <= 64 one-qubit gates on <= 10
+//  "blocked" qubits per launch), which no in-tree pass ever enables
+// (SURVEY Appendix B).  Here the queue is general (2-qubit gates, any qubits)
+// and the scheduler below decides passes and rounds.
+//
+// Shared-memory layout: tile-local index j (bit u of j <-> global bit tb[u],
+// tb sorted ascending and always containing the low global bits so that global
+// accesses stay in >= 64 B runs) is stored at 16-byte slot  j ^ S(j)  with
+//   S(j) = XOR_{u >= 3, bit u of j set} v[u],  v = {.,.,., 1,2,4, 3,6,5, 7, 1, 2}
+// a GF(2)-linear swizzle chosen so that for ANY 4 round positions three of the
+// remaining eight positions have linearly independent bank vectors: the host
+// maps lane bits 0..2 to those, which makes every quarter-warp LDS.128/STS.128
+// of a round hit 8 distinct 16-byte bank groups (conflict free), and keeps the
+// staging accesses (consecutive j) conflict free as well.  Because the swizzle
+// is linear, addresses are  phys(base) ^ phys(offset): one XOR per access.
+#include "common.cuh"
+
+namespace b200sv {
+
+constexpr int kTB = 12;               // tile bits
+constexpr int kTileAmps = 1 << kTB;
+constexpr int kTileThreads = 128;
+constexpr int kRoundBits = 4;
+constexpr int kMaxRounds = 16;
+constexpr int kMaxTileGates = 16;   // == kMaxRounds: worst case one gate per round
+constexpr int kMaxRoundGates = 8;
+
+__host__ __device__ constexpr int swz_vec(int u) {
+  return u < 3 ? (1 << u) : u == 3 ? 1 : u == 4 ? 2 : u == 5 ? 4 : u == 6 ? 3 : u == 7 ? 6 : u == 8 ? 5 : u == 9 ? 7
+                                                                                      : u == 10 ? 1 : 2;
+}
+__host__ __device__ inline uint32_t phys_slot(uint32_t j) {
+  uint32_t s = 0;
+  for (int u = 3; u < kTB; u++)
+    if ((j >> u) & 1u) s ^= (uint32_t)swz_vec(u);
+  return j ^ s;
+}
+
+struct TileRound {
+  uint16_t eoff[16];            // phys(sum_i bit_i(e) << pos[i]) for the 16 elements of a sub-block
+  uint16_t gbit[8];             // phys(1 << tpos[i]): contribution of group-id bit i
+  uint8_t ngates;
+  uint8_t gate[kMaxRoundGates]; // index into mats
+  uint8_t form[kMaxRoundGates]; // 0..5: 2-qubit on round-bit pair; 6..9: 1-qubit on round bit (form-6)
+};
+struct TilePassParams {
+  double2 mats[kMaxTileGates][16];  // 2q: row-major 4x4 with matrix bit0 <-> lower round bit; 1q: first 4 entries
+  uint64_t goff_hi[32];             // global offset of tile-local bits 7..11 (index m = j >> 7)
+  uint64_t goff_lo[7];              // global offset of tile-local bit u < 7
+  uint64_t ntiles;
+  uint16_t soff_hi[32];             // phys(m << 7)
+  InsertList ins;                   // sorted tile bits (global positions)
+  int nrounds;
+  TileRound rounds[kMaxRounds];
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// 2-qubit gate on round bits P0 < P1 of a 16-amplitude register block
+template <int P0, int P1>
+__device__ __forceinline__ void apply2(double2 (&a)[16], const double2 *__restrict__ m) {
+  double2 mm[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) mm[i] = m[i];
+#pragma unroll
+  for (int o = 0; o < 4; o++) {
+    // spread the two bits of o over the positions that are not P0 / P1
+    int base = 0, ob = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+      if (b != P0 && b != P1) {
+        if ((o >> ob) & 1) base |= 1 << b;
+        ob++;
+      }
+    const int i0 = base, i1 = base | (1 << P0), i2 = base | (1 << P1), i3 = base | (1 << P0) | (1 << P1);
+    const double2 x0 = a[i0], x1 = a[i1], x2 = a[i2], x3 = a[i3];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      double2 acc = mk<double>(0, 0);
+      cfma(acc, mm[r * 4 + 0], x0);
+      cfma(acc, mm[r * 4 + 1], x1);
+      cfma(acc, mm[r * 4 + 2], x2);
+      cfma(acc, mm[r * 4 + 3], x3);
+      a[r == 0 ? i0 : r == 1 ? i1 : r == 2 ? i2 : i3] = acc;
+    }
+  }
+}
+template <int P>
+__device__ __forceinline__ void apply1(double2 (&a)[16], const double2 *__restrict__ m) {
+  const double2 m00 = m[0], m01 = m[1], m10 = m[2], m11 = m[3];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    if (i & (1 << P)) continue;
+    const double2 x0 = a[i], x1 = a[i | (1 << P)];
+    double2 y0 = mk<double>(0, 0), y1 = mk<double>(0, 0);
+    cfma(y0, m00, x0); cfma(y0, m01, x1);
+    cfma(y1, m10, x0); cfma(y1, m11, x1);
+    a[i] = y0;
+    a[i | (1 << P)] = y1;
+  }
+}
+
+__global__ void __launch_bounds__(kTileThreads, 3)
+tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassParams p) {
+  extern __shared__ __align__(16) double2 tile[];
+  const int tid = threadIdx.x;
+  uint64_t glo = 0;
+#pragma unroll
+  for (int u = 0; u < 7; u++)
+    if ((tid >> u) & 1) glo |= p.goff_lo[u];
+  const uint32_t slo = phys_slot((uint32_t)tid);
+
+  for (uint64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    double2 *gt = psi + (insert_zeros(t, p.ins) | glo);
+#pragma unroll 8
+    for (int m = 0; m < 32; m++) cp_async16(&tile[slo ^ p.soff_hi[m]], gt + p.goff_hi[m]);
+    cp_async_wait_all();
+    __syncthreads();
+
+    for (int r = 0; r < p.nrounds; r++) {
+      const TileRound &R = p.rounds[r];
+#pragma unroll 1
+      for (int s = 0; s < 2; s++) {
+        const int g = tid + kTileThreads * s;
+        uint32_t base = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if ((g >> i) & 1) base ^= R.gbit[i];
+        double2 a[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) a[e] = tile[base ^ R.eoff[e]];
+        for (int k = 0; k < R.ngates; k++) {
+          const double2 *m = p.mats[R.gate[k]];
+          switch (R.form[k]) {
+          case 0: apply2<0, 1>(a, m); break;
+          case 1: apply2<0, 2>(a, m); break;
+          case 2: apply2<0, 3>(a, m); break;
+          case 3: apply2<1, 2>(a, m); break;
+          case 4: apply2<1, 3>(a, m); break;
+          case 5: apply2<2, 3>(a, m); break;
+          case 6: apply1<0>(a, m); break;
+          case 7: apply1<1>(a, m); break;
+          case 8: apply1<2>(a, m); break;
+          default: apply1<3>(a, m); break;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 16; e++) tile[base ^ R.eoff[e]] = a[e];
+      }
+      __syncthreads();
+    }
+
+#pragma unroll 8
+    for (int m = 0; m < 32; m++) gt[p.goff_hi[m]] = tile[slo ^ p.soff_hi[m]];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host scheduler
+struct QGate {
+  int nq;
+  int q[2];
+  const double *mat;  // column-major complex<double>, 4 or 16 entries
+};
+
+static uint64_t qmask(const QGate &g) { return (1ull << g.q[0]) | (g.nq == 2 ? (1ull << g.q[1]) : 0); }
+
+// choose 3 group-id "lane" positions with independent swizzle vectors among the non-round positions
+static bool pick_lane_positions(const std::vector<int> &free_pos, int out[3]) {
+  const int n = (int)free_pos.size();
+  for (int a = 0; a < n; a++)
+    for (int b = a + 1; b < n; b++)
+      for (int c = b + 1; c < n; c++) {
+        const int va = swz_vec(free_pos[a]), vb = swz_vec(free_pos[b]), vc = swz_vec(free_pos[c]);
+        if (va != vb && va != vc && vb != vc && (va ^ vb) != vc) {
+          out[0] = free_pos[a]; out[1] = free_pos[b]; out[2] = free_pos[c];
+          return true;
+        }
+      }
+  return false;
+}
+
+static void build_round(TileRound &R, const std::vector<int> &round_pos /*tile-local, <=4*/) {
+  // pad the round to 4 positions with unused tile positions (highest first)
+  std::vector<int> pos = round_pos;
+  for (int u = kTB - 1; (int)pos.size() < kRoundBits && u >= 0; u--)
+    if (std::find(pos.begin(), pos.end(), u) == pos.end()) pos.push_back(u);
+  std::sort(pos.begin(), pos.end());
+  for (int e = 0; e < 16; e++) {
+    uint32_t j = 0;
+    for (int i = 0; i < 4; i++)
+      if ((e >> i) & 1) j |= 1u << pos[i];
+    R.eoff[e] = (uint16_t)phys_slot(j);
+  }
+  std::vector<int> free_pos;
+  for (int u = 0; u < kTB; u++)
+    if (std::find(pos.begin(), pos.end(), u) == pos.end()) free_pos.push_back(u);
+  int lane[3];
+  if (!pick_lane_positions(free_pos, lane)) { lane[0] = free_pos[0]; lane[1] = free_pos[1]; lane[2] = free_pos[2]; }
+  std::vector<int> tpos(lane, lane + 3);
+  for (int u : free_pos)
+    if (u != lane[0] && u != lane[1] && u != lane[2]) tpos.push_back(u);
+  for (int i = 0; i < 8; i++) R.gbit[i] = (uint16_t)phys_slot(1u << tpos[i]);
+  R.ngates = 0;
+  // stash sorted positions in eoff order: callers need pos -> round-bit index
+  (void)pos;
+}
+
+static int round_bit_of(const std::vector<int> &sorted_pos, int tile_pos) {
+  for (int i = 0; i < (int)sorted_pos.size(); i++)
+    if (sorted_pos[i] == tile_pos) return i;
+  return -1;
+}
+
+// One pass: gates[sel] all fit the tile; tile_bits sorted global positions (kTB of them).
+static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::vector<int> &sel,
+                          const std::vector<int> &tile_bits) {
+  static TilePassParams p;
+  p.ntiles = s.total_amps() >> kTB;
+  p.ins.n = kTB;
+  for (int u = 0; u < kTB; u++) p.ins.pos[u] = (uint8_t)tile_bits[u];
+  for (int u = 0; u < 7; u++) p.goff_lo[u] = 1ull << tile_bits[u];
+  for (int m = 0; m < 32; m++) {
+    uint64_t go = 0;
+    for (int b = 0; b < 5; b++)
+      if ((m >> b) & 1) go |= 1ull << tile_bits[7 + b];
+    p.goff_hi[m] = go;
+    p.soff_hi[m] = (uint16_t)phys_slot((uint32_t)m << 7);
+  }
+  auto tile_pos = [&](int q) {
+    for (int u = 0; u < kTB; u++)
+      if (tile_bits[u] == q) return u;
+    throw Error("tile pass: qubit not in tile");
+  };
+  // matrices
+  if ((int)sel.size() > kMaxTileGates) throw Error("tile pass: too many gates");
+  // rounds: scan in order, capacity 4 tile positions, respect dependencies
+  std::vector<int> rem(sel.size());
+  for (size_t i = 0; i < sel.size(); i++) rem[i] = (int)i;  // indices into sel
+  p.nrounds = 0;
+  while (!rem.empty()) {
+    if (p.nrounds >= kMaxRounds) throw Error("tile pass: too many rounds");
+    uint64_t rq = 0, blocked = 0;
+    std::vector<int> take, rest;
+    for (int li : rem) {
+      const QGate &g = gates[sel[li]];
+      const uint64_t m = qmask(g);
+      if ((m & blocked) || (int)take.size() >= kMaxRoundGates) { blocked |= m; rest.push_back(li); continue; }
+      if (__builtin_popcountll(rq | m) <= kRoundBits) { rq |= m; take.push_back(li); }
+      else { blocked |= m; rest.push_back(li); }
+    }
+    std::vector<int> rpos;
+    for (int q = 0; q < 64; q++)
+      if ((rq >> q) & 1) rpos.push_back(tile_pos(q));
+    TileRound &R = p.rounds[p.nrounds++];
+    build_round(R, rpos);
+    // recompute the padded+sorted position list exactly as build_round did
+    std::vector<int> pos = rpos;
+    for (int u = kTB - 1; (int)pos.size() < kRoundBits && u >= 0; u--)
+      if (std::find(pos.begin(), pos.end(), u) == pos.end()) pos.push_back(u);
+    std::sort(pos.begin(), pos.end());
+    for (int li : take) {
+      const QGate &g = gates[sel[li]];
+      double2 *M = p.mats[li];
+      if (g.nq == 1) {
+        const int b = round_bit_of(pos, tile_pos(g.q[0]));
+        for (int i = 0; i < 2; i++)
+          for (int j = 0; j < 2; j++) M[i * 2 + j] = mk<double>(g.mat[2 * (i + 2 * j)], g.mat[2 * (i + 2 * j) + 1]);
+        R.form[R.ngates] = (uint8_t)(6 + b);
+      } else {
+        int b0 = round_bit_of(pos, tile_pos(g.q[0])), b1 = round_bit_of(pos, tile_pos(g.q[1]));
+        const bool flip = b0 > b1;  // canonical: matrix bit0 <-> lower round bit
+        for (int i = 0; i < 4; i++)
+          for (int j = 0; j < 4; j++) {
+            const int si = flip ? ((i >> 1) | ((i & 1) << 1)) : i, sj = flip ? ((j >> 1) | ((j & 1) << 1)) : j;
+            M[i * 4 + j] = mk<double>(g.mat[2 * (si + 4 * sj)], g.mat[2 * (si + 4 * sj) + 1]);
+          }
+        if (flip) std::swap(b0, b1);
+        static const int form_of[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
+        R.form[R.ngates] = (uint8_t)form_of[b0][b1];
+      }
+      R.gate[R.ngates++] = (uint8_t)li;
+    }
+    rem.swap(rest);
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileAmps * 16));
+    attr_set = true;
+  }
+  const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms * 3);
+  tile_pass_kernel<<<grid, kTileThreads, kTileAmps * 16, s.stream>>>((double2 *)s.data, p);
+  B200_CUDA(cudaGetLastError());
+}
+
+// Partition a gate sequence into tile passes (in-order greedy with dependency blocking) and run them.
+// Returns the number of HBM passes used.
+int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats,
+                        int low_bits) {
+  std::vector<QGate> gates(ngates);
+  for (int i = 0; i < ngates; i++) {
+    if (nq[i] != 1 && nq[i] != 2) throw Error("apply_gate_sequence: gates must act on 1 or 2 qubits");
+    gates[i].nq = nq[i];
+    for (int j = 0; j < nq[i]; j++) {
+      if (qubits[2 * i + j] >= (uint64_t)s.nq) throw Error("apply_gate_sequence: qubit out of range");
+      gates[i].q[j] = (int)qubits[2 * i + j];
+    }
+    if (nq[i] == 2 && gates[i].q[0] == gates[i].q[1]) throw Error("apply_gate_sequence: duplicate qubit");
+    gates[i].mat = mats + 32 * (size_t)i;
+  }
+  const bool tiled = s.precision == B200SV_F64 && s.nq >= kTB;
+  if (!tiled) {  // small or single-precision states: one streaming pass per gate
+    for (auto &g : gates) launch_dense(s, g.q, g.nq, nullptr, 0, g.mat);
+    return ngates;
+  }
+  low_bits = std::max(1, std::min(low_bits, 5));
+  std::vector<int> rem(ngates);
+  for (int i = 0; i < ngates; i++) rem[i] = i;
+  int passes = 0;
+  while (!rem.empty()) {
+    uint64_t Q = (1ull << low_bits) - 1, blocked = 0;
+    std::vector<int> sel, rest;
+    for (int i : rem) {
+      const uint64_t m = qmask(gates[i]);
+      if ((m & blocked) || (int)sel.size() >= kMaxTileGates) { blocked |= m; rest.push_back(i); continue; }
+      if (__builtin_popcountll(Q | m) <= kTB) { Q |= m; sel.push_back(i); }
+      else { blocked |= m; rest.push_back(i); }
+    }
+    // fill the tile with the lowest unused global bits
+    for (int q = 0; q < s.nq && __builtin_popcountll(Q) < kTB; q++) Q |= 1ull << q;
+    std::vector<int> tile_bits;
+    for (int q = 0; q < 64; q++)
+      if ((Q >> q) & 1) tile_bits.push_back(q);
+    run_tile_pass(s, gates, sel, tile_bits);
+    passes++;
+    rem.swap(rest);
+  }
+  return passes;
+}
+
+}  // namespace b200sv

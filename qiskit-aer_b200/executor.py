@@ -49,3 +49,45 @@ def op_h2d_bytes(op):
     if op[0] == "diagonal":
         return 16 * len(op[2])
     return 64
+
+
+def _small_dense(op):
+    """(qubits, column-major matrix) if `op` is a dense 1- or 2-qubit gate the tile engine can queue."""
+    if op[0] == "unitary" and len(op[1]) <= 2:
+        return list(op[1]), colmajor(op[2])
+    if op[0] == "gate" and op[1] in ("h", "sx", "x") and len(op[2]) == 1:
+        return list(op[2]), colmajor(gate_matrix(op[1], op[3]))
+    return None
+
+
+def apply_ops_queued(qv, ops, stats=None, special=None):
+    """Like apply_ops, but consecutive dense 1-/2-qubit gates are queued and flushed through
+    b200sv_apply_gate_sequence (tile-blocked multi-gate passes) -- the B200 engine's analogue of the
+    reference's blocked-gate queue (qubitvector_thrust.hpp:1102-1111,1511-1512).  `stats`, if given,
+    accumulates {"passes": n, "launches": n}.  `special` maps extra op kinds (e.g. the sharded runner's
+    "swap") to handlers returning the number of launches they issued."""
+    queue = []
+
+    def flush():
+        if queue:
+            passes = qv.apply_gate_sequence(queue)
+            if stats is not None:
+                stats["passes"] = stats.get("passes", 0) + passes
+                stats["launches"] = stats.get("launches", 0) + passes
+            queue.clear()
+
+    for op in ops:
+        g = _small_dense(op)
+        if g is not None:
+            queue.append(g)
+            continue
+        flush()
+        if special is not None and op[0] in special:
+            n_launch = special[op[0]](op)
+        else:
+            apply_op(qv, op)
+            n_launch = 1
+        if stats is not None:
+            stats["launches"] = stats.get("launches", 0) + n_launch
+            stats[op[0]] = stats.get(op[0], 0) + 1
+    flush()

@@ -170,6 +170,24 @@ class QubitVectorB200:
         c = complex(coeff)
         capi.check(self._lib.b200sv_apply_pauli(self.h, qp, k, pauli.encode(), c.real, c.imag))
 
+    def apply_gate_sequence(self, gates):
+        """gates: list of (qubits, column-major matrix) with 1 or 2 qubits each; applied in order, as few
+        HBM passes as possible (b200sv_apply_gate_sequence).  Returns the number of passes used."""
+        ng = len(gates)
+        nq = np.zeros(ng, dtype=np.int32)
+        qs = np.zeros(2 * ng, dtype=np.uint64)
+        mats = np.zeros((ng, 16), dtype=np.complex128)
+        for i, (q, m) in enumerate(gates):
+            nq[i] = len(q)
+            qs[2 * i:2 * i + len(q)] = q
+            m = np.asarray(m, dtype=np.complex128).reshape(-1)
+            mats[i, :m.size] = m
+        passes = C.c_int(0)
+        capi.check(self._lib.b200sv_apply_gate_sequence(self.h, ng, nq.ctypes.data_as(C.POINTER(C.c_int)),
+                                                        qs.ctypes.data_as(_u64p), mats.ctypes.data_as(_f64p),
+                                                        C.byref(passes)))
+        return passes.value
+
     def apply_batched_pauli_ops(self, masks4):
         """masks4: [num_states][4] = x_mask, z_mask, num_y, apply (qubitvector_thrust.hpp:2892)."""
         a = np.ascontiguousarray(masks4, dtype=np.uint64).reshape(-1)

@@ -127,6 +127,18 @@ class ShardedRunner:
         apply_op(self.qv, op)
         return 1
 
+    def run_plan(self, plan, stats=None, queued=True):
+        """Execute a plan; with `queued`, dense 1-/2-qubit gates between exchanges are flushed through the
+        tile-blocked multi-gate passes (b200sv_apply_gate_sequence)."""
+        from .executor import apply_ops_queued
+        if queued:
+            apply_ops_queued(self.qv, plan, stats, special={"swap": self.apply})
+        else:
+            for op in plan:
+                n_launch = self.apply(op)
+                if stats is not None:
+                    stats["launches"] = stats.get("launches", 0) + n_launch
+
     def _staging(self, count):
         if self._tmp is None or self._tmp[0].shape[0] < count:
             self._tmp = [torch.empty((count, 2), dtype=self.amps.dtype, device=self.amps.device) for _ in range(2)]

@@ -372,3 +372,59 @@ def test_large_state_size_independent_properties(n):
     s = gpu.sample_measure(np.random.default_rng(1).random(20000))
     frac = np.mean((s >> np.uint64(n - 1)) & np.uint64(1))
     assert abs(frac - p1[1]) < 0.02
+
+
+@pytest.mark.parametrize("n", [12, 13, 16, 19])
+def test_gate_sequence_tile_passes(n):
+    """b200sv_apply_gate_sequence (tile-blocked multi-gate passes) == the same gates applied one by one."""
+    rng = np.random.default_rng(200 + n)
+    psi0 = opgen.random_state(rng, n)
+    for trial in range(4):
+        gates = []
+        for _ in range(int(rng.integers(1, 40))):
+            k = int(rng.integers(1, 3))
+            if trial == 1:   # stress the low (lane / bank) bits
+                qs = [int(q) for q in rng.choice(min(n, 6), size=k, replace=False)]
+            elif trial == 2:  # chains on a few qubits: many dependent rounds
+                qs = [int(q) for q in rng.choice(4, size=k, replace=False) + (n - 4)]
+            else:
+                qs = opgen.pick(rng, n, k)
+            gates.append((qs, opgen.colmajor(opgen.haar_unitary(rng, 1 << k))))
+        ora, gpu = OracleQV(n), gpu_qv(n)
+        ora.set_state(psi0)
+        gpu.set_state(psi0)
+        for qs, m in gates:
+            ora.apply_matrix(qs, m)
+        passes = gpu.apply_gate_sequence(gates)
+        assert 1 <= passes <= len(gates)
+        assert np.max(np.abs(ora.vector() - gpu.vector())) < 1e-12, (trial, len(gates))
+        assert opgen.fidelity_gap(ora.vector(), gpu.vector()) < 1e-10
+
+
+def test_gate_sequence_quantum_volume_uses_few_passes():
+    from qiskit_aer_b200 import circuits, executor
+    n = 20
+    ops = circuits.quantum_volume(n, 10, seed=3)
+    ora, gpu = OracleQV(n), gpu_qv(n)
+    executor.apply_ops(ora, ops)
+    stats = {}
+    executor.apply_ops_queued(gpu, ops, stats)
+    assert opgen.fidelity_gap(ora.vector(), gpu.vector()) < 1e-10
+    assert stats["passes"] < len(ops) // 3, stats  # 100 gates must not need 100 passes
+
+
+def test_gate_sequence_small_and_batched_states():
+    rng = np.random.default_rng(9)
+    for n, S in ((5, 1), (12, 3)):
+        states = [opgen.random_state(rng, n) for _ in range(S)]
+        gpu = gpu_qv(n, num_states=S)
+        gpu.set_state(np.concatenate(states))
+        gates = [(opgen.pick(rng, n, 2), opgen.colmajor(opgen.haar_unitary(rng, 4))) for _ in range(12)]
+        gpu.apply_gate_sequence(gates)
+        got = gpu.vector().reshape(S, -1)
+        for i, st in enumerate(states):
+            o = OracleQV(n)
+            o.set_state(st)
+            for qs, m in gates:
+                o.apply_matrix(qs, m)
+            assert np.max(np.abs(got[i] - o.vector())) < 1e-12

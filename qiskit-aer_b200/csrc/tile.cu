@@ -34,7 +34,9 @@ namespace b200sv {
 
 constexpr int kTB = 12;               // tile bits
 constexpr int kTileAmps = 1 << kTB;
-constexpr int kTileThreads = 128;
+constexpr int kTileThreads = 256;
+constexpr int kLoBits = 8;            // tile-local bits covered by the thread id
+constexpr int kHiCount = kTileAmps / kTileThreads;  // staging iterations per thread
 constexpr int kRoundBits = 4;
 constexpr int kMaxRounds = 16;
 constexpr int kMaxTileGates = 16;   // == kMaxRounds: worst case one gate per round
@@ -60,10 +62,10 @@ struct TileRound {
 };
 struct TilePassParams {
   double2 mats[kMaxTileGates][16];  // 2q: row-major 4x4 with matrix bit0 <-> lower round bit; 1q: first 4 entries
-  uint64_t goff_hi[32];             // global offset of tile-local bits 7..11 (index m = j >> 7)
-  uint64_t goff_lo[7];              // global offset of tile-local bit u < 7
+  uint64_t goff_hi[kHiCount];       // global offset of tile-local bits kLoBits..11 (index m = j >> kLoBits)
+  uint64_t goff_lo[kLoBits];        // global offset of tile-local bit u < kLoBits
   uint64_t ntiles;
-  uint16_t soff_hi[32];             // phys(m << 7)
+  uint16_t soff_hi[kHiCount];       // phys(m << kLoBits)
   InsertList ins;                   // sorted tile bits (global positions)
   int nrounds;
   TileRound rounds[kMaxRounds];
@@ -121,28 +123,27 @@ __device__ __forceinline__ void apply1(double2 (&a)[16], const double2 *__restri
   }
 }
 
-__global__ void __launch_bounds__(kTileThreads, 3)
+__global__ void __launch_bounds__(kTileThreads, 2)
 tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassParams p) {
   extern __shared__ __align__(16) double2 tile[];
   const int tid = threadIdx.x;
   uint64_t glo = 0;
 #pragma unroll
-  for (int u = 0; u < 7; u++)
+  for (int u = 0; u < kLoBits; u++)
     if ((tid >> u) & 1) glo |= p.goff_lo[u];
   const uint32_t slo = phys_slot((uint32_t)tid);
 
   for (uint64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     double2 *gt = psi + (insert_zeros(t, p.ins) | glo);
-#pragma unroll 8
-    for (int m = 0; m < 32; m++) cp_async16(&tile[slo ^ p.soff_hi[m]], gt + p.goff_hi[m]);
+#pragma unroll
+    for (int m = 0; m < kHiCount; m++) cp_async16(&tile[slo ^ p.soff_hi[m]], gt + p.goff_hi[m]);
     cp_async_wait_all();
     __syncthreads();
 
     for (int r = 0; r < p.nrounds; r++) {
       const TileRound &R = p.rounds[r];
-#pragma unroll 1
-      for (int s = 0; s < 2; s++) {
-        const int g = tid + kTileThreads * s;
+      {
+        const int g = tid;
         uint32_t base = 0;
 #pragma unroll
         for (int i = 0; i < 8; i++)
@@ -171,8 +172,8 @@ tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
       __syncthreads();
     }
 
-#pragma unroll 8
-    for (int m = 0; m < 32; m++) gt[p.goff_hi[m]] = tile[slo ^ p.soff_hi[m]];
+#pragma unroll
+    for (int m = 0; m < kHiCount; m++) gt[p.goff_hi[m]] = tile[slo ^ p.soff_hi[m]];
     __syncthreads();
   }
 }
@@ -240,13 +241,13 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
   p.ntiles = s.total_amps() >> kTB;
   p.ins.n = kTB;
   for (int u = 0; u < kTB; u++) p.ins.pos[u] = (uint8_t)tile_bits[u];
-  for (int u = 0; u < 7; u++) p.goff_lo[u] = 1ull << tile_bits[u];
-  for (int m = 0; m < 32; m++) {
+  for (int u = 0; u < kLoBits; u++) p.goff_lo[u] = 1ull << tile_bits[u];
+  for (int m = 0; m < kHiCount; m++) {
     uint64_t go = 0;
-    for (int b = 0; b < 5; b++)
-      if ((m >> b) & 1) go |= 1ull << tile_bits[7 + b];
+    for (int b = 0; b < kTB - kLoBits; b++)
+      if ((m >> b) & 1) go |= 1ull << tile_bits[kLoBits + b];
     p.goff_hi[m] = go;
-    p.soff_hi[m] = (uint16_t)phys_slot((uint32_t)m << 7);
+    p.soff_hi[m] = (uint16_t)phys_slot((uint32_t)m << kLoBits);
   }
   auto tile_pos = [&](int q) {
     for (int u = 0; u < kTB; u++)
@@ -309,7 +310,7 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
     B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileAmps * 16));
     attr_set = true;
   }
-  const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms * 3);
+  const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms * 2);
   tile_pass_kernel<<<grid, kTileThreads, kTileAmps * 16, s.stream>>>((double2 *)s.data, p);
   B200_CUDA(cudaGetLastError());
 }
@@ -335,6 +336,12 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
     return ngates;
   }
   low_bits = std::max(1, std::min(low_bits, 5));
+  // tuning knobs (read once): B200SV_TILE_MAX_GATES caps the gates riding on one pass (FP64/HBM balance),
+  // B200SV_TILE_LOW_BITS the number of low global bits forced into every tile (coalescing run length)
+  static const int env_max_gates = [] { const char *e = getenv("B200SV_TILE_MAX_GATES"); return e ? atoi(e) : 0; }();
+  static const int env_low_bits = [] { const char *e = getenv("B200SV_TILE_LOW_BITS"); return e ? atoi(e) : 0; }();
+  const int max_gates = env_max_gates > 0 ? std::min(env_max_gates, kMaxTileGates) : kMaxTileGates;
+  if (env_low_bits > 0) low_bits = std::min(env_low_bits, 5);
   std::vector<int> rem(ngates);
   for (int i = 0; i < ngates; i++) rem[i] = i;
   int passes = 0;
@@ -343,7 +350,7 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
     std::vector<int> sel, rest;
     for (int i : rem) {
       const uint64_t m = qmask(gates[i]);
-      if ((m & blocked) || (int)sel.size() >= kMaxTileGates) { blocked |= m; rest.push_back(i); continue; }
+      if ((m & blocked) || (int)sel.size() >= max_gates) { blocked |= m; rest.push_back(i); continue; }
       if (__builtin_popcountll(Q | m) <= kTB) { Q |= m; sel.push_back(i); }
       else { blocked |= m; rest.push_back(i); }
     }

@@ -189,6 +189,10 @@ def b200_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # native libraries (NCCL's version banner) may write to fd 1: park stdout on stderr until the JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -408,7 +412,9 @@ def b200_arm(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg(args)
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

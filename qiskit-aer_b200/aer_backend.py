@@ -63,7 +63,7 @@ def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, m
         elif op[0] == "measure":
             c.measure([int(q) for q in op[1]], [int(q) for q in op[2]], [])
         elif op[0] == "reset":
-            c.reset([int(q) for q in op[1]])
+            c.reset([int(q) for q in op[1]], -1)
         else:
             raise ValueError(op[0])
     for i, (qs, p) in enumerate(expvals):

@@ -57,7 +57,7 @@ dense_kernel(cx<T> *__restrict__ psi, const __grid_constant__ DenseParams<T, K> 
 template <typename T, int K>
 static void launch_dense_t(State &s, const int *targets, const int *controls, int nc, const double *mat) {
   constexpr int DIM = 1 << K;
-  static DenseParams<T, K> p;  // large: keep off the stack (single-threaded use per process is documented)
+  static thread_local DenseParams<T, K> p;  // large: keep off the stack; thread_local because Aer calls from OpenMP threads
   for (int i = 0; i < DIM; i++)
     for (int j = 0; j < DIM; j++)
       p.m[i * DIM + j] = mk<T>((T)mat[2 * (i + DIM * j)], (T)mat[2 * (i + DIM * j) + 1]);
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(256) perm_kernel(cx<T> *psi, const __grid_cons
 void launch_permutation(State &s, const int *qubits, int k, const uint64_t *pairs, int npairs) {
   if (k > kMaxDenseQubits) throw Error("apply_permutation_matrix: more than 10 qubits is not supported");
   if (npairs > 1024) throw Error("apply_permutation_matrix: more than 1024 pairs is not supported");
-  static PermParams p;
+  static thread_local PermParams p;
   p.k = k; p.npairs = npairs;
   std::vector<int> all(qubits, qubits + k);
   for (int b = 0; b < k; b++) p.off_bits[b] = 1ull << qubits[b];

@@ -237,7 +237,7 @@ static int round_bit_of(const std::vector<int> &sorted_pos, int tile_pos) {
 // One pass: gates[sel] all fit the tile; tile_bits sorted global positions (kTB of them).
 static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::vector<int> &sel,
                           const std::vector<int> &tile_bits) {
-  static TilePassParams p;
+  static thread_local TilePassParams p;
   p.ntiles = s.total_amps() >> kTB;
   p.ins.n = kTB;
   for (int u = 0; u < kTB; u++) p.ins.pos[u] = (uint8_t)tile_bits[u];

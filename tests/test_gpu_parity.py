@@ -428,3 +428,34 @@ def test_gate_sequence_small_and_batched_states():
             for qs, m in gates:
                 o.apply_matrix(qs, m)
             assert np.max(np.abs(got[i] - o.vector())) < 1e-12
+
+
+def test_concurrent_host_threads_on_different_handles():
+    """Aer calls the vector from OpenMP threads (one State per shot / chunk group,
+    circuit_executor.hpp:958, parallel_state_executor.hpp:831-840): the ABI must be re-entrant."""
+    import threading
+    n, nthreads = 12, 8
+    results, errors = [None] * nthreads, []
+
+    def work(t):
+        try:
+            rng = np.random.default_rng(500 + t)
+            ora, gpu = OracleQV(n), gpu_qv(n)
+            for op in opgen.random_ops(700 + t, n, 60):
+                opgen.apply(ora, op)
+                opgen.apply(gpu, op)
+            gates = [(opgen.pick(rng, n, 2), opgen.colmajor(opgen.haar_unitary(rng, 4))) for _ in range(10)]
+            for qs, m in gates:
+                ora.apply_matrix(qs, m)
+            gpu.apply_gate_sequence(gates)
+            results[t] = float(np.max(np.abs(ora.vector() - gpu.vector())))
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    assert max(results) < 1e-12, results

@@ -372,6 +372,29 @@ def b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
 
+    # ---- the same workload through the reference's own Controller + executors with the B200 vector as
+    # its device="GPU" statevector (qiskit-aer_b200/aer/): AerSimulator's C++ stack end to end.
+    e2e_aer = None
+    if world == 1 and not args.no_aer_e2e:
+        try:
+            from qiskit_aer_b200 import aer_backend
+            if aer_backend.available():
+                qv.close()
+                del buf
+                torch.cuda.empty_cache()
+                kw = dict(device="GPU", shots=SHOTS, seed=1234, fusion=False, expvals=paulis)
+                aer_backend.run_circuit(n, ops, **kw)
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    res = aer_backend.run_circuit(n, ops, **kw)
+                aer_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+                e2e_aer = {"value": amps_written / (aer_ms / 1e3), "unit": "amp-updates/s", "ms_per_step": aer_ms,
+                           "time_taken_s": float(res["time_taken"]), "device": res["metadata"].get("device"),
+                           "path": "reference Controller::execute -> Statevector::Executor<State<QubitVectorB200<double>>> "
+                                   "(fusion_enable=false: the adapter's gate queue feeds the tile engine)"}
+        except Exception as e:  # reported, never fatal
+            e2e_aer = {"value": None, "error": str(e)[:300]}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         dom = max((c for c in per_class if c.startswith(("dense", "diagonal", "tile"))), key=lambda c: per_class[c][1])
@@ -410,6 +433,8 @@ def b200_arm(args):
             "gpu_launches": gpu_launches,
             "clocks": clocks,
         }
+        if e2e_aer is not None:
+            out["e2e_aer_controller"] = e2e_aer
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg(args)
         sys.stdout.flush()
@@ -432,7 +457,10 @@ def main():
     ap.add_argument("--engine", default="tile", choices=["tile", "dense"],
                     help="tile: multi-gate shared-memory passes (default); dense: one fused dense block per pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aer-e2e", action="store_true", help="skip the run through the reference Controller")
     args = ap.parse_args()
+    if args.workload == "qft":
+        args.engine = "dense"  # QFT is mostly controlled phases: commutation-aware fusion + wide diagonal passes
     if args.impl == "reference":
         reference_arm(args)
     else:

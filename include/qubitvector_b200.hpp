@@ -45,6 +45,7 @@ public:
   QubitVectorB200 &operator=(const QubitVectorB200 &) = delete;
   QubitVectorB200 &operator=(QubitVectorB200 &&o) {
     if (this != &o) {
+      if (o.h_) o.flush();
       release();
       h_ = o.h_; num_qubits_ = o.num_qubits_; data_size_ = o.data_size_; chunk_index_ = o.chunk_index_;
       o.h_ = nullptr; o.num_qubits_ = 0; o.data_size_ = 0;
@@ -72,7 +73,7 @@ public:
   }
   bool top_of_group() { return true; }
   std::complex<data_t> *data() const { return nullptr; }  // amplitudes live in HBM
-  void *device_data() const { void *p = nullptr; ck(b200sv_device_ptr(h_, &p)); return p; }
+  void *device_data() const { void *p = nullptr; flush(); ck(b200sv_device_ptr(h_, &p)); return p; }
 
   void set_json_chop_threshold(double t) { json_chop_threshold_ = t; }
   double get_json_chop_threshold() { return json_chop_threshold_; }
@@ -87,7 +88,7 @@ public:
   int get_sample_measure_index_size() { return sample_measure_index_size_; }
   void set_max_matrix_bits(int_t) {}
   void set_max_sampling_shots(int_t) {}
-  void synchronize(void) { if (h_) ck(b200sv_synchronize(h_)); }
+  void synchronize(void) { if (h_) { flush(); ck(b200sv_synchronize(h_)); } }
   virtual bool enable_batch(bool) const { return false; }
   bool support_global_indexing(void) { return false; }
   virtual bool batched_optimization_supported(void) { return false; }
@@ -120,54 +121,54 @@ public:
       synchronize(); src.synchronize();
       std::vector<char> a(bytes), b(bytes);  // rare path (X on a global qubit): staged through the host
       ck(b200sv_download(src.h_, b.data(), 0, data_size_));
-      if (write_back) { ck(b200sv_download(h_, a.data(), 0, data_size_)); ck(b200sv_upload(src.h_, a.data(), 0, data_size_)); }
-      ck(b200sv_upload(h_, b.data(), 0, data_size_));
+      if (write_back) { flush(); ck(b200sv_download(h_, a.data(), 0, data_size_)); ck(b200sv_upload(src.h_, a.data(), 0, data_size_)); }
+      flush(); ck(b200sv_upload(h_, b.data(), 0, data_size_));
       return;
     }
     // this (lower chunk: its q0=1 half) <-> src (q0=0 half); the kernel moves both directions
     const bool this_is_upper = !(chunk_index_ < src.chunk_index_);
     src.synchronize();
-    ck(b200sv_chunk_swap_peer(h_, (int)q0, src.device_data(), this_is_upper ? 1 : 0, 0));
-    ck(b200sv_chunk_swap_peer(h_, (int)q0, src.device_data(), this_is_upper ? 1 : 0, 1));
+    flush(); ck(b200sv_chunk_swap_peer(h_, (int)q0, src.device_data(), this_is_upper ? 1 : 0, 0));
+    flush(); ck(b200sv_chunk_swap_peer(h_, (int)q0, src.device_data(), this_is_upper ? 1 : 0, 1));
     synchronize();
   }
   void apply_chunk_swap(const reg_t &, uint_t) { throw std::runtime_error("QubitVectorB200: remote (MPI) chunk swap is not supported"); }
   void apply_chunk_swap(QubitVectorB200<data_t> &, uint_t, uint_t, uint_t) { throw std::runtime_error("QubitVectorB200: multi chunk swap is not supported"); }
 
   //---------------------------------------------------------------- data
-  void zero() { ck(b200sv_zero(h_)); }
-  void initialize() { ck(b200sv_initialize(h_)); }
+  void zero() { flush(); ck(b200sv_zero(h_)); }
+  void initialize() { flush(); ck(b200sv_initialize(h_)); }
   void initialize(const QubitVectorB200<data_t> &obj) {
     set_num_qubits(obj.num_qubits_);
     auto v = obj.copy_to_vector();
-    ck(b200sv_upload(h_, v.data(), 0, data_size_));
+    flush(); ck(b200sv_upload(h_, v.data(), 0, data_size_));
   }
   template <typename list_t> void initialize_from_vector(const list_t &vec) {
     if (data_size_ != vec.size()) throw std::runtime_error("QubitVector::initialize input vector is incorrect length");
     std::vector<std::complex<data_t>> tmp(vec.size());
     for (size_t i = 0; i < vec.size(); i++) tmp[i] = std::complex<data_t>(vec[i]);
-    ck(b200sv_upload(h_, tmp.data(), 0, data_size_));
+    flush(); ck(b200sv_upload(h_, tmp.data(), 0, data_size_));
   }
   void initialize_from_vector(std::vector<std::complex<data_t>> &&vec) { initialize_from_data(vec.data(), vec.size()); }
   void initialize_from_vector(AER::Vector<std::complex<data_t>> &&vec) { initialize_from_data(vec.data(), vec.size()); }
   virtual void move_from_vector(AER::Vector<std::complex<data_t>> &&vec) { initialize_from_data(vec.data(), vec.size()); }
   void initialize_from_data(const std::complex<data_t> *data, const size_t num_states) {
     if (data_size_ != num_states) throw std::runtime_error("QubitVector::initialize input vector is incorrect length");
-    ck(b200sv_upload(h_, data, 0, data_size_));
+    flush(); ck(b200sv_upload(h_, data, 0, data_size_));
   }
   virtual void initialize_creg(uint_t, uint_t) {}
   virtual void initialize_creg(uint_t, uint_t, const std::string &, const std::string &) {}
   void initialize_component(const reg_t &qubits, const cvector_t<double> &state) {
-    ck(b200sv_initialize_component(h_, qubits.data(), (int)qubits.size(), (const double *)state.data()));
+    flush(); ck(b200sv_initialize_component(h_, qubits.data(), (int)qubits.size(), (const double *)state.data()));
   }
   cvector_t<data_t> vector() const {
     cvector_t<data_t> ret(data_size_);
-    ck(b200sv_download(h_, ret.data(), 0, data_size_));
+    flush(); ck(b200sv_download(h_, ret.data(), 0, data_size_));
     return ret;
   }
   AER::Vector<std::complex<data_t>> copy_to_vector() const {
     AER::Vector<std::complex<data_t>> ret(data_size_, false);
-    ck(b200sv_download(h_, ret.data(), 0, data_size_));
+    flush(); ck(b200sv_download(h_, ret.data(), 0, data_size_));
     return ret;
   }
   AER::Vector<std::complex<data_t>> move_to_vector() { return copy_to_vector(); }
@@ -183,43 +184,48 @@ public:
   }
   std::complex<data_t> get_state(uint_t pos) const {
     std::complex<data_t> v;
-    ck(b200sv_download(h_, &v, pos, 1));
+    flush(); ck(b200sv_download(h_, &v, pos, 1));
     return v;
   }
-  void set_state(uint_t pos, std::complex<data_t> &val) { ck(b200sv_upload(h_, &val, pos, 1)); }
-  void checkpoint() { ck(b200sv_checkpoint(h_)); }
-  void revert(bool keep) { ck(b200sv_revert(h_, keep ? 1 : 0)); }
+  void set_state(uint_t pos, std::complex<data_t> &val) { flush(); ck(b200sv_upload(h_, &val, pos, 1)); }
+  void checkpoint() { flush(); ck(b200sv_checkpoint(h_)); }
+  void revert(bool keep) { flush(); ck(b200sv_revert(h_, keep ? 1 : 0)); }
   std::complex<double> inner_product() const {
     double re, im;
-    ck(b200sv_inner_product(h_, &re, &im));
+    flush(); ck(b200sv_inner_product(h_, &re, &im));
     return {re, im};
   }
 
   //---------------------------------------------------------------- gates (qubitvector.hpp:225-294)
   void apply_matrix(const reg_t &qubits, const cvector_t<double> &mat) {
+    if (enqueue(qubits, mat)) return;
+    flush();
     ck(b200sv_apply_matrix(h_, qubits.data(), (int)qubits.size(), (const double *)mat.data()));
   }
   void apply_multiplexer(const reg_t &control_qubits, const reg_t &target_qubits, const cvector_t<double> &mat) {
-    ck(b200sv_apply_multiplexer(h_, control_qubits.data(), (int)control_qubits.size(), target_qubits.data(),
+    flush(); ck(b200sv_apply_multiplexer(h_, control_qubits.data(), (int)control_qubits.size(), target_qubits.data(),
                                 (int)target_qubits.size(), (const double *)mat.data()));
   }
   void apply_diagonal_matrix(const reg_t &qubits, const cvector_t<double> &mat) {
-    ck(b200sv_apply_diagonal(h_, qubits.data(), (int)qubits.size(), (const double *)mat.data()));
+    flush(); ck(b200sv_apply_diagonal(h_, qubits.data(), (int)qubits.size(), (const double *)mat.data()));
   }
   void apply_permutation_matrix(const reg_t &qubits, const std::vector<std::pair<uint_t, uint_t>> &pairs) {
     std::vector<uint64_t> flat;
     for (auto &p : pairs) { flat.push_back(p.first); flat.push_back(p.second); }
-    ck(b200sv_apply_permutation(h_, qubits.data(), (int)qubits.size(), flat.data(), (int)pairs.size()));
+    flush(); ck(b200sv_apply_permutation(h_, qubits.data(), (int)qubits.size(), flat.data(), (int)pairs.size()));
   }
-  void apply_mcx(const reg_t &qubits) { ck(b200sv_apply_mcx(h_, qubits.data(), (int)qubits.size())); }
-  void apply_mcy(const reg_t &qubits) { ck(b200sv_apply_mcy(h_, qubits.data(), (int)qubits.size())); }
+  void apply_mcx(const reg_t &qubits) { flush(); ck(b200sv_apply_mcx(h_, qubits.data(), (int)qubits.size())); }
+  void apply_mcy(const reg_t &qubits) { flush(); ck(b200sv_apply_mcy(h_, qubits.data(), (int)qubits.size())); }
   void apply_mcphase(const reg_t &qubits, const std::complex<double> phase) {
-    ck(b200sv_apply_mcphase(h_, qubits.data(), (int)qubits.size(), phase.real(), phase.imag()));
+    flush(); ck(b200sv_apply_mcphase(h_, qubits.data(), (int)qubits.size(), phase.real(), phase.imag()));
   }
   void apply_mcu(const reg_t &qubits, const cvector_t<double> &mat) {
+    // an uncontrolled, non-diagonal 2x2 is a plain 1-qubit matrix (qubitvector.hpp:1676-1680): queue it
+    if (qubits.size() == 1 && !(mat[1] == 0.0 && mat[2] == 0.0) && enqueue(qubits, mat)) return;
+    flush();
     ck(b200sv_apply_mcu(h_, qubits.data(), (int)qubits.size(), (const double *)mat.data()));
   }
-  void apply_mcswap(const reg_t &qubits) { ck(b200sv_apply_mcswap(h_, qubits.data(), (int)qubits.size())); }
+  void apply_mcswap(const reg_t &qubits) { flush(); ck(b200sv_apply_mcswap(h_, qubits.data(), (int)qubits.size())); }
   void apply_multi_swaps(const reg_t &qubits) {  // pairs of qubits, qubitvector.hpp:1843-1876
     for (size_t i = 0; i + 1 < qubits.size(); i += 2) apply_mcswap({qubits[i], qubits[i + 1]});
   }
@@ -236,7 +242,7 @@ public:
     }
   }
   void apply_pauli(const reg_t &qubits, const std::string &pauli, const complex_t &coeff = 1) {
-    ck(b200sv_apply_pauli(h_, qubits.data(), (int)qubits.size(), pauli.c_str(), coeff.real(), coeff.imag()));
+    flush(); ck(b200sv_apply_pauli(h_, qubits.data(), (int)qubits.size(), pauli.c_str(), coeff.real(), coeff.imag()));
   }
 
   //---------------------------------------------------------------- reductions (qubitvector.hpp:302-411)
@@ -248,19 +254,19 @@ public:
   }
   virtual std::vector<double> probabilities(const reg_t &qubits) const {
     std::vector<double> p(1ull << qubits.size());
-    ck(b200sv_probabilities(h_, qubits.data(), (int)qubits.size(), p.data()));
+    flush(); ck(b200sv_probabilities(h_, qubits.data(), (int)qubits.size(), p.data()));
     return p;
   }
   virtual reg_t sample_measure(const std::vector<double> &rnds) const {
     reg_t s(rnds.size());
-    ck(b200sv_sample_measure(h_, rnds.data(), (int64_t)rnds.size(), s.data()));
+    flush(); ck(b200sv_sample_measure(h_, rnds.data(), (int64_t)rnds.size(), s.data()));
     return s;
   }
-  double norm() const { double v; ck(b200sv_norm(h_, &v)); return v; }
+  double norm() const { double v; flush(); ck(b200sv_norm(h_, &v)); return v; }
   double norm(const uint_t qubit, const cvector_t<double> &mat) const { return norm(reg_t({qubit}), mat); }
   double norm(const reg_t &qubits, const cvector_t<double> &mat) const {
     double v;
-    ck(b200sv_norm_matrix(h_, qubits.data(), (int)qubits.size(), (const double *)mat.data(), &v));
+    flush(); ck(b200sv_norm_matrix(h_, qubits.data(), (int)qubits.size(), (const double *)mat.data(), &v));
     return v;
   }
   double norm_diagonal(const uint_t qubit, const cvector_t<double> &mat) const { return norm_diagonal(reg_t({qubit}), mat); }
@@ -272,7 +278,7 @@ public:
   }
   double expval_pauli(const reg_t &qubits, const std::string &pauli, const complex_t initial_phase = 1.0) const {
     double v;
-    ck(b200sv_expval_pauli(h_, qubits.data(), (int)qubits.size(), pauli.c_str(), initial_phase.real(),
+    flush(); ck(b200sv_expval_pauli(h_, qubits.data(), (int)qubits.size(), pauli.c_str(), initial_phase.real(),
                            initial_phase.imag(), &v));
     return v;
   }
@@ -280,7 +286,7 @@ public:
                       const uint_t z_count, const uint_t z_count_pair, const complex_t initial_phase = 1.0) const {
     double v;
     pair_chunk.sync_const();
-    ck(b200sv_expval_pauli_pair(h_, qubits.data(), (int)qubits.size(), pauli.c_str(), pair_chunk.device_data(), z_count,
+    flush(); ck(b200sv_expval_pauli_pair(h_, qubits.data(), (int)qubits.size(), pauli.c_str(), pair_chunk.device_data(), z_count,
                                 z_count_pair, initial_phase.real(), initial_phase.imag(), &v));
     return v;
   }
@@ -300,12 +306,46 @@ public:
   void batched_expval_pauli(std::vector<double> &, const reg_t &, const std::string &, bool, std::complex<double>, bool,
                             const complex_t = 1.0) const {}
 
+  //---------------------------------------------------------------- gate queue (tile-blocked multi-gate passes)
+  // Dense 1-/2-qubit gates are queued and flushed through b200sv_apply_gate_sequence, which packs them
+  // into as few HBM passes as possible; every other method flushes first, so the observable semantics
+  // are those of immediate application (cf. the reference's blocked-gate queue,
+  // qubitvector_thrust.hpp:1102-1111,1511-1512).  Disable with B200SV_GATE_QUEUE=0.
+  static bool queue_enabled() {
+    static const bool on = [] { const char *e = getenv("B200SV_GATE_QUEUE"); return !(e && e[0] == '0'); }();
+    return on;
+  }
+  void flush() const {
+    if (q_nq_.empty()) return;
+    const int ng = (int)q_nq_.size();
+    const int rc = b200sv_apply_gate_sequence(h_, ng, q_nq_.data(), q_qubits_.data(), q_mats_.data(), nullptr);
+    q_nq_.clear(); q_qubits_.clear(); q_mats_.clear();
+    ck(rc);
+  }
+
 protected:
+  bool enqueue(const reg_t &qubits, const cvector_t<double> &mat) {
+    if (!queue_enabled() || qubits.size() < 1 || qubits.size() > 2 || mat.size() != (1ull << (2 * qubits.size())))
+      return false;
+    q_nq_.push_back((int)qubits.size());
+    q_qubits_.push_back(qubits[0]);
+    q_qubits_.push_back(qubits.size() == 2 ? qubits[1] : 0);
+    const size_t off = q_mats_.size();
+    q_mats_.resize(off + 32, 0.0);
+    std::memcpy(&q_mats_[off], mat.data(), mat.size() * sizeof(std::complex<double>));
+    if (q_nq_.size() >= 4096) flush();
+    return true;
+  }
+  mutable std::vector<int> q_nq_;
+  mutable std::vector<uint64_t> q_qubits_;
+  mutable std::vector<double> q_mats_;
+
   static void ck(int rc) {
     if (rc) throw std::runtime_error(std::string("b200sv: ") + b200sv_last_error());
   }
-  void sync_const() const { if (h_) ck(b200sv_synchronize(h_)); }
+  void sync_const() const { if (h_) { flush(); ck(b200sv_synchronize(h_)); } }
   void release() {
+    q_nq_.clear(); q_qubits_.clear(); q_mats_.clear();
     if (h_) { b200sv_destroy(h_); h_ = nullptr; }
   }
   b200sv_handle h_ = nullptr;

@@ -75,6 +75,7 @@ class Block:
     def __init__(self):
         self.qubits = []
         self.gates = []  # (qubits, U)
+        self.diag = True
 
     def matrix(self):
         M = np.eye(1 << len(self.qubits), dtype=np.complex128)
@@ -86,16 +87,25 @@ class Block:
         return all(np.count_nonzero(U - np.diag(np.diag(U))) == 0 for _, U in self.gates)
 
 
-def fuse(ops, max_qubit=5, window=64):
-    """Returns a list of ("unitary", qubits, U) / ("diagonal", qubits, d) ops equivalent to `ops`."""
+def _is_diag(U):
+    return np.count_nonzero(U - np.diag(np.diag(U))) == 0
+
+
+def fuse(ops, max_qubit=5, window=64, max_diag_qubit=10):
+    """Returns a list of ("unitary", qubits, U) / ("diagonal", qubits, d) ops equivalent to `ops`.
+
+    Commutation aware: diagonal gates commute with each other, so a diagonal gate only depends on the
+    last NON-diagonal block that shares a qubit with it, and purely diagonal blocks may grow to
+    `max_diag_qubit` qubits (the streaming diagonal kernel keeps a 2^10 table in shared memory)."""
     blocks = []
     for op in ops:
         q, U = op_matrix(op)
         qs = set(q)
+        gdiag = _is_diag(U)
         lo = max(0, len(blocks) - window)
         last_dep = -1
         for i in range(len(blocks) - 1, lo - 1, -1):
-            if qs & set(blocks[i].qubits):
+            if qs & set(blocks[i].qubits) and not (gdiag and blocks[i].diag):
                 last_dep = i
                 break
         if lo > 0 and last_dep < 0:
@@ -103,20 +113,37 @@ def fuse(ops, max_qubit=5, window=64):
         target = None
         cands = ([last_dep] if last_dep >= lo else []) + list(range(max(last_dep + 1, lo), len(blocks)))
         for i in cands:
-            if len(set(blocks[i].qubits) | qs) <= max_qubit:
-                target = blocks[i]
+            b = blocks[i]
+            union = len(set(b.qubits) | qs)
+            if b.diag and gdiag:
+                ok = union <= max(max_diag_qubit, max_qubit)
+            else:
+                ok = union <= max_qubit
+                # a non-diagonal gate may only join a later diagonal block if it overlaps nothing there
+                # that is ordered before it -- blocks after last_dep never overlap non-commutingly, fine.
+            if ok:
+                target = b
                 break
         if target is None:
             target = Block()
+            target.diag = True
             blocks.append(target)
         for x in q:
             if x not in target.qubits:
                 target.qubits.append(x)
         target.gates.append((q, U))
+        target.diag = target.diag and gdiag
     out = []
     for b in blocks:
-        if b.is_diagonal():
-            out.append(("diagonal", list(b.qubits), np.diag(b.matrix()).copy()))
+        if b.diag:
+            d = np.ones(1 << len(b.qubits), dtype=np.complex128)
+            idx = np.arange(1 << len(b.qubits))
+            for gq, U in b.gates:  # product of diagonals without building 2^k x 2^k matrices
+                sub = np.zeros_like(idx)
+                for i, x in enumerate(gq):
+                    sub |= ((idx >> b.qubits.index(x)) & 1) << i
+                d *= np.diag(U)[sub]
+            out.append(("diagonal", list(b.qubits), d))
         else:
             out.append(("unitary", list(b.qubits), b.matrix()))
     return out

@@ -210,13 +210,20 @@ def b200_arm(args):
             % (name, len(ops), len(fused), n_local, AMP_BYTES * 2.0 ** n_local / 2 ** 30))
 
     stream = torch.cuda.Stream(device=dev)
-    with torch.cuda.stream(stream):
-        buf = torch.empty((1 << n_local) * 2, dtype=torch.float64, device=dev)
-    qv = q.QubitVectorB200(n_local, np.complex128, device=local_rank, external_ptr=buf.data_ptr(),
-                           stream=stream.cuda_stream)
+    if world > 1 and args.exchange == "p2p":
+        # library-owned allocation (exportable over CUDA IPC), kernels ordered on the torch stream NCCL uses
+        qv = q.QubitVectorB200(n_local, np.complex128, device=local_rank)
+        qv.set_stream(stream.cuda_stream)
+        buf = qv.torch_view()
+    else:
+        with torch.cuda.stream(stream):
+            buf = torch.empty((1 << n_local) * 2, dtype=torch.float64, device=dev)
+        qv = q.QubitVectorB200(n_local, np.complex128, device=local_rank, external_ptr=buf.data_ptr(),
+                               stream=stream.cuda_stream)
     if world > 1:
         from qiskit_aer_b200 import sharded
-        runner = sharded.ShardedRunner(qv, n, rank, world, stream, buf)
+        with torch.cuda.stream(stream):
+            runner = sharded.ShardedRunner(qv, n, rank, world, stream, buf, exchange=args.exchange)
         plan = runner.plan(fused)
         final_phys = list(runner.phys)
         if rank == 0:
@@ -419,7 +426,8 @@ def b200_arm(args):
                                   if tile else "dense blocks, max_qubit=%d" % args.fusion_max_qubit),
                        "shots": SHOTS,
                        "l2": "state (%.0f GiB per GPU) is larger than L2; no flush needed" % (AMP_BYTES * 2.0 ** n_local / 2 ** 30),
-                       "sharding": "top %d qubits select the GPU" % int(np.log2(world))},
+                       "sharding": "top %d qubits select the GPU" % int(np.log2(world)),
+                       "exchange": (args.exchange if world > 1 else None)},
             "wall_time_s": ms_per_step / 1e3,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": dom, "launches": cnt, "avg_ms": avg_ms,
@@ -456,6 +464,8 @@ def main():
     ap.add_argument("--fusion-max-qubit", type=int, default=4)
     ap.add_argument("--engine", default="tile", choices=["tile", "dense"],
                     help="tile: multi-gate shared-memory passes (default); dense: one fused dense block per pass")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="global-qubit exchange: in-place NVLink peer swap kernel over CUDA IPC, or ncclSend/Recv slices")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aer-e2e", action="store_true", help="skip the run through the reference Controller")
     args = ap.parse_args()

@@ -156,6 +156,17 @@ int b200sv_chunk_swap_peer(b200sv_handle h, int local_q, void *peer_dev_ptr, int
 int b200sv_pack_half(b200sv_handle h, int local_q, int bit, uint64_t begin, uint64_t count, void *dev_buf);
 int b200sv_unpack_half(b200sv_handle h, int local_q, int bit, uint64_t begin, uint64_t count, const void *dev_buf);
 
+/* CUDA-IPC plumbing for one-process-per-GPU sharding: export this handle's allocation (64-byte
+ * cudaIpcMemHandle_t; only for memory the library allocated itself), map a partner process's
+ * allocation into this process (peer access over NVLink is enabled lazily) and unmap it.  The mapped
+ * pointer is what b200sv_chunk_swap_peer takes.  Replaces the in-process peer pointers of
+ * chunk/device_chunk_container.hpp:336-351 (cudaDeviceEnablePeerAccess) for the multi-process layout. */
+int b200sv_ipc_export(b200sv_handle h, void *handle64);
+int b200sv_ipc_open(b200sv_handle h, const void *handle64, void **peer_dev_ptr);
+int b200sv_ipc_close(b200sv_handle h, void *peer_dev_ptr);
+/* run this handle's kernels on a caller-owned stream from now on (e.g. the torch stream NCCL is ordered on) */
+int b200sv_set_stream(b200sv_handle h, void *cuda_stream);
+
 /* ---- host RNG identical to Aer's RngEngine (framework/rng.hpp:31-99) ------ */
 /* n draws of rand(0,1) from std::mt19937_64 seeded with `seed` (what
  * State::sample_measure consumes, statevector_state.hpp:1026-1027). */

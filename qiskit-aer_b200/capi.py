@@ -52,6 +52,10 @@ SIGNATURES = {
     "b200sv_chunk_swap_peer": [_vp, C.c_int, _vp, C.c_int, C.c_int],
     "b200sv_pack_half": [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _vp],
     "b200sv_unpack_half": [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _vp],
+    "b200sv_ipc_export": [_vp, _vp],
+    "b200sv_ipc_open": [_vp, _vp, C.POINTER(_vp)],
+    "b200sv_ipc_close": [_vp, _vp],
+    "b200sv_set_stream": [_vp, _vp],
     "b200sv_rng_uniform": [C.c_uint64, C.c_int64, _f64p],
 }
 

@@ -540,6 +540,35 @@ int b200sv_unpack_half(b200sv_handle h, int local_q, int bit, uint64_t begin, ui
   });
 }
 
+int b200sv_ipc_export(b200sv_handle h, void *handle64) {
+  return guard([&] {
+    select(H);
+    if (!H->owns_data) throw Error("ipc_export: only library-owned allocations can be exported");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+    B200_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, H->data));
+  });
+}
+int b200sv_ipc_open(b200sv_handle h, const void *handle64, void **peer) {
+  return guard([&] {
+    select(H);
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, sizeof(hd));
+    B200_CUDA(cudaIpcOpenMemHandle(peer, hd, cudaIpcMemLazyEnablePeerAccess));
+  });
+}
+int b200sv_ipc_close(b200sv_handle h, void *peer) {
+  return guard([&] { select(H); B200_CUDA(cudaIpcCloseMemHandle(peer)); });
+}
+int b200sv_set_stream(b200sv_handle h, void *cuda_stream) {
+  return guard([&] {
+    select(H);
+    B200_CUDA(cudaStreamSynchronize(H->stream));
+    if (H->owns_stream && H->stream) B200_CUDA(cudaStreamDestroy(H->stream));
+    H->stream = (cudaStream_t)cuda_stream;
+    H->owns_stream = false;
+  });
+}
+
 // ------------------------------------------------------------------ RNG (host)
 int b200sv_rng_uniform(uint64_t seed, int64_t n, double *out) {
   return guard([&] {

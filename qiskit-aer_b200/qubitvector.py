@@ -234,6 +234,34 @@ class QubitVectorB200:
         return self._ret(out)
 
     # ---- exchange --------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        capi.check(self._lib.b200sv_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+
+    def ipc_export(self):
+        buf = C.create_string_buffer(64)
+        capi.check(self._lib.b200sv_ipc_export(self.h, buf))
+        return bytes(buf.raw)
+
+    def ipc_open(self, handle_bytes):
+        p = C.c_void_p()
+        capi.check(self._lib.b200sv_ipc_open(self.h, C.c_char_p(handle_bytes), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        capi.check(self._lib.b200sv_ipc_close(self.h, C.c_void_p(int(ptr))))
+
+    def torch_view(self):
+        """Zero-copy torch tensor (float64/float32 pairs) over the library-owned amplitudes."""
+        import torch
+        comp = "<f8" if self.dtype == np.complex128 else "<f4"
+
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": ((self.num_states << self.n) * 2,), "typestr": comp,
+                                      "data": (self.device_ptr(), False), "version": 3}
+        return torch.as_tensor(a, device="cuda")
+
     def pack_half(self, local_q, bit, begin, count, dev_buf):
         capi.check(self._lib.b200sv_pack_half(self.h, int(local_q), int(bit), int(begin), int(count),
                                               C.c_void_p(int(dev_buf))))

@@ -31,7 +31,7 @@ def _insert_zero(v, pos):
 
 
 class ShardedRunner:
-    def __init__(self, qv, n, rank, world, stream, buf, slice_amps=1 << 26, min_run_bits=20):
+    def __init__(self, qv, n, rank, world, stream, buf, slice_amps=1 << 26, min_run_bits=20, exchange="nccl"):
         """qv: chunk backend (QubitVectorB200 or a CPU stand-in with the same methods);
         buf: torch tensor viewing the chunk's amplitudes as float64 pairs (exchange source/target)."""
         self.qv, self.n, self.rank, self.world = qv, int(n), int(rank), int(world)
@@ -47,38 +47,80 @@ class ShardedRunner:
         self._tmp = None
         qv.chunk_setup(self.n, self.rank)
         self.bytes_exchanged = 0
+        self.exchange = exchange
+        self._peer_ptr = {}
+        if exchange == "p2p":
+            # CUDA-IPC: map every exchange partner's chunk into this process (NVLink peer access)
+            handles = [None] * world
+            dist.all_gather_object(handles, qv.ipc_export())
+            for gb in range(self.gbits):
+                self._peer_ptr[gb] = qv.ipc_open(handles[self.rank ^ (1 << gb)])
+            self._flag = torch.zeros(1, dtype=torch.float32, device=self.amps.device)
 
     # ---------------------------------------------------------------- planning (host, deterministic)
     def plan(self, ops, phys=None):
         """Rewrite logical ops to physical ones, inserting ("swap", local_pos, global_bit) steps.
-        Updates self.phys to the mapping valid after the plan has run."""
+
+        Epoch scheduling: run EVERY gate that is executable under the current qubit map (respecting
+        dependencies through shared qubits), then bring in the global qubit(s) the blocked gates wait
+        for, evicting the local qubits whose next use is farthest away (Belady), and repeat.  Long
+        epochs matter twice: fewer exchanges, and the tile engine packs a whole epoch's gates into
+        few HBM passes.  Diagonal gates and controls never block on a global qubit (they are resolved
+        from the chunk index).  Updates self.phys to the mapping valid after the plan has run."""
         phys = list(self.phys if phys is None else phys)
         nl = self.nl
-        uses = {}  # logical qubit -> sorted op indices where it must be local
-        for i, op in enumerate(ops):
-            if op[0] == "unitary" or (op[0] == "gate" and op[1] not in ("cp",)):
-                for q in (op[1] if op[0] == "unitary" else op[2]):
-                    uses.setdefault(q, []).append(i)
-        out = []
-        for i, op in enumerate(ops):
-            if op[0] == "diagonal":
-                out.append(("diagonal", [phys[q] for q in op[1]], op[2]))
-                continue
-            if op[0] == "gate" and op[1] == "cp":
-                out.append(("gate", op[1], [phys[q] for q in op[2]], op[3]))
-                continue
-            qs = op[1] if op[0] == "unitary" else op[2]
-            need_local = qs if op[0] == "unitary" else self._gate_targets(op)
-            for q in need_local:
-                if phys[q] >= nl:
-                    victim = self._pick_victim(phys, set(qs), uses, i)
-                    lpos, gpos = phys[victim], phys[q]
-                    out.append(("swap", lpos, gpos - nl))
-                    phys[victim], phys[q] = gpos, lpos
+
+        def qubits_of(op):
+            return list(op[1]) if op[0] in ("unitary", "diagonal") else list(op[2])
+
+        def need_local(op):
+            if op[0] == "diagonal" or (op[0] == "gate" and op[1] == "cp"):
+                return []
+            return list(op[1]) if op[0] == "unitary" else self._gate_targets(op)
+
+        def emit(op):
+            qs = [phys[q] for q in qubits_of(op)]
             if op[0] == "unitary":
-                out.append(("unitary", [phys[q] for q in qs], op[2]))
-            else:
-                out.append(("gate", op[1], [phys[q] for q in qs], op[3]))
+                return ("unitary", qs, op[2])
+            if op[0] == "diagonal":
+                return ("diagonal", qs, op[2])
+            return ("gate", op[1], qs, op[3])
+
+        out = []
+        remaining = list(range(len(ops)))
+        while remaining:
+            blocked, rest, wanted, frontier = set(), [], [], set()
+            for i in remaining:
+                qs = qubits_of(ops[i])
+                if blocked.intersection(qs):
+                    blocked.update(qs)
+                    rest.append(i)
+                    continue
+                glob = [q for q in need_local(ops[i]) if phys[q] >= nl]
+                if glob:
+                    blocked.update(qs)
+                    rest.append(i)
+                    frontier.update(qs)  # never evict a partner of the gate we are swapping for
+                    for q in glob:
+                        if q not in wanted:
+                            wanted.append(q)
+                    continue
+                out.append(emit(ops[i]))
+            remaining = rest
+            if not remaining:
+                break
+            # next use (position in `remaining`) of every logical qubit that must be local there
+            uses = {}
+            for pos, i in enumerate(remaining):
+                for q in need_local(ops[i]):
+                    uses.setdefault(q, []).append(pos)
+            busy = set(wanted) | frontier
+            for q in wanted[:self.gbits]:
+                victim = self._pick_victim(phys, busy, uses, -1)
+                busy.add(victim)
+                lpos, gpos = phys[victim], phys[q]
+                out.append(("swap", lpos, gpos - nl))
+                phys[victim], phys[q] = gpos, lpos
         self.phys = phys
         return out
 
@@ -154,6 +196,16 @@ class ShardedRunner:
         bit = 0 if upper else 1
         half = 1 << (nl - 1)
         launches = 0
+        if self.exchange == "p2p":
+            # In-place swap kernel over the peer mapping: each rank moves half of the pairs, so both NVLink
+            # directions carry S*2^(nl-1) bytes and nothing is staged.  The tiny all-reduces are
+            # stream-ordered rendezvous: the partner's earlier kernels are complete before its memory is
+            # touched, and nobody runs ahead before the partner's half of the swap has landed.
+            dist.all_reduce(self._flag)
+            self.qv.chunk_swap_peer(lpos, self._peer_ptr[gbit], upper, upper)
+            dist.all_reduce(self._flag)
+            self.bytes_exchanged += half * self.amps.element_size() * 2
+            return 3
         if lpos >= self.min_run_bits or (1 << lpos) >= self.slice_amps:
             c = min(self.slice_amps, 1 << lpos)
             tmp = self._staging(c)

@@ -34,13 +34,17 @@ def main():
     n = args.qubits
     nl = n - int(np.log2(world))
     stream = torch.cuda.Stream(device=dev)
-    with torch.cuda.stream(stream):
-        buf = torch.empty((1 << nl) * 2, dtype=torch.float64, device=dev)
-    qv = q.QubitVectorB200(nl, np.complex128, device=local, external_ptr=buf.data_ptr(), stream=stream.cuda_stream)
+    qv = q.QubitVectorB200(nl, np.complex128, device=local)   # library-owned memory (IPC exportable)
+    qv.set_stream(stream.cuda_stream)
+    buf = qv.torch_view()
     ok = True
-    for min_run_bits in (args.min_run_bits, 40):  # contiguous-run path, then the pack/unpack path
-        run = sharded.ShardedRunner(qv, n, rank, world, stream, buf, slice_amps=args.slice_amps,
-                                    min_run_bits=min_run_bits)
+    runners = {}
+    # NVLink peer-swap kernel over CUDA IPC, NCCL contiguous-run slices, NCCL pack/unpack slices
+    for mode, min_run_bits in (("p2p", args.min_run_bits), ("nccl", args.min_run_bits), ("nccl", 40)):
+        with torch.cuda.stream(stream):
+            run = sharded.ShardedRunner(qv, n, rank, world, stream, buf, slice_amps=args.slice_amps,
+                                        min_run_bits=min_run_bits, exchange=mode)
+        runners[(mode, min_run_bits)] = run
         ops = circuits.quantum_volume(n, 5, seed=11) + circuits.qft(n)
         fused = fusion.fuse(ops, max_qubit=4)
         run.initialize()
@@ -61,8 +65,8 @@ def main():
         nsw = sum(1 for p in plan if p[0] == "swap")
         good = err < 1e-12 and ev_err < 1e-10 and same and nsw > 0
         ok = ok and good
-        print("rank %d min_run_bits=%d swaps=%d max|err|=%.2e ev_err=%.2e samples_equal=%s" %
-              (rank, min_run_bits, nsw, err, ev_err, same), flush=True)
+        print("rank %d %s min_run_bits=%d swaps=%d max|err|=%.2e ev_err=%.2e samples_equal=%s" %
+              (rank, mode, min_run_bits, nsw, err, ev_err, same), flush=True)
     t = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(t)
     if rank == 0:

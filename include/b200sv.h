@@ -125,6 +125,15 @@ int b200sv_apply_batched_pauli(b200sv_handle h, const uint64_t *masks4);
 int b200sv_apply_gate_sequence(b200sv_handle h, int ngates, const int *nq, const uint64_t *qubits,
                                const double *mats, int *passes_out);
 
+/* Batched noisy shots: the same queue flush, with sampled Pauli noise riding on the passes.  kind[i] = 1 / 2
+ * (dense 1-/2-qubit gate, as above) or 3 = a per-state Pauli on qubits[2*i]: state s applies
+ * codes[slot[i]*num_states + s] (0..3 = I, X, Y, Z).  One launch covers every shot of the container; the Pauli
+ * costs no extra HBM traffic.  Replaces apply_batched_pauli_ops + the per-op launches of
+ * BatchShotsExecutor::apply_ops_batched_shots_for_group (src/simulators/batch_shots_executor.hpp:500-603;
+ * qubitvector_thrust.hpp:2892, batched_pauli_func :2819).  The draws stay on the host (Aer's RngEngine). */
+int b200sv_apply_op_sequence(b200sv_handle h, int nops, const int *kind, const uint64_t *qubits, const double *mats,
+                             const int *slot, const uint8_t *codes, int nslots, int *passes_out);
+
 /* ---- reductions (out has num_states entries unless noted) --------------- */
 int b200sv_norm(b200sv_handle h, double *out);          /* norm() (qubitvector.hpp:1879) */
 /* norm(qubits, mat) (qubitvector.hpp:1889) -- Kraus probability ||M psi||^2 */

@@ -30,6 +30,10 @@ def load():
             for p in sorted(glob.glob(os.path.join(libs, pat))):
                 ctypes.CDLL(p, mode=ctypes.RTLD_GLOBAL)
         sys.path.insert(0, os.path.join(_HERE, "_ref"))
+        try:
+            import qiskit_aer  # noqa: F401
+        except ImportError:  # two-class stub so that dict noise models parse (pybind_json.hpp:224-229)
+            sys.path.insert(0, os.path.join(os.path.dirname(_HERE), "qiskit-aer_b200", "aer", "pystub"))
         import controller_wrappers  # noqa
         _cw = controller_wrappers
     return _cw
@@ -37,7 +41,7 @@ def load():
 
 def run_circuit(n, ops, shots=0, seed=1234, threads=0, fusion=True, fusion_max_qubit=5, fusion_threshold=14,
                 expvals=(), save_statevector=False, measure=True, precision="double",
-                blocking_qubits=None):
+                blocking_qubits=None, noise_model=None):
     """ops: list of ("unitary", qubits, U) | ("diagonal", qubits, d) | ("gate", name, qubits, params).
 
     Mirrors the reference's own lowering conventions (qiskit_aer/backends/aer_compiler.py:875-1050).
@@ -81,7 +85,7 @@ def run_circuit(n, ops, shots=0, seed=1234, threads=0, fusion=True, fusion_max_q
     if blocking_qubits is not None:
         cfg.blocking_enable = True
         cfg.blocking_qubits = int(blocking_qubits)
-    out = cw.aer_controller_execute().execute([c], None, cfg)
+    out = cw.aer_controller_execute().execute([c], noise_model, cfg)
     if not out.get("success", False):
         raise RuntimeError("reference controller failed: %s" % out.get("status"))
     return out["results"][0]

@@ -38,6 +38,10 @@ def load():
             for p in sorted(glob.glob(os.path.join(libs, pat))):
                 ctypes.CDLL(p, mode=ctypes.RTLD_GLOBAL)
         ctypes.CDLL(os.path.join(_HERE, "libb200sv.so"), mode=ctypes.RTLD_GLOBAL)
+        try:
+            import qiskit_aer  # noqa: F401  (a real installation wins)
+        except ImportError:  # plain-dict noise models need two class names importable (pybind_json.hpp:224-229)
+            sys.path.insert(0, os.path.join(_HERE, "aer", "pystub"))
         import importlib.util
         spec = importlib.util.spec_from_file_location("controller_wrappers",
                                                       os.path.join(_MOD_DIR, "controller_wrappers.so"))

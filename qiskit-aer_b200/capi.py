@@ -41,6 +41,8 @@ SIGNATURES = {
     "b200sv_apply_mcu": [_vp, _u64p, C.c_int, _f64p],
     "b200sv_apply_pauli": [_vp, _u64p, C.c_int, C.c_char_p, C.c_double, C.c_double],
     "b200sv_apply_batched_pauli": [_vp, _u64p],
+    "b200sv_apply_op_sequence": [_vp, C.c_int, C.POINTER(C.c_int), _u64p, _f64p, C.POINTER(C.c_int),
+                                 C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int)],
     "b200sv_apply_gate_sequence": [_vp, C.c_int, C.POINTER(C.c_int), _u64p, _f64p, C.POINTER(C.c_int)],
     "b200sv_norm": [_vp, _f64p],
     "b200sv_norm_matrix": [_vp, _u64p, C.c_int, _f64p, _f64p],

@@ -53,3 +53,23 @@ def amplitudes_written(ops, n):
         else:
             total += 1 << n
     return total
+
+
+def random_noisy_circuit(n, depth, seed):
+    """Config 5 workload: `depth` layers of {h, rz, sx} on every qubit followed by cx on a random pairing
+    (the gate set of the reference noise benchmarks, test/benchmark/noise_20q.py / simulator_benchmark.py)."""
+    rng = np.random.default_rng(seed)
+    ops = []
+    for _ in range(depth):
+        for q in range(n):
+            kind = int(rng.integers(3))
+            if kind == 0:
+                ops.append(("gate", "h", [q], []))
+            elif kind == 1:
+                ops.append(("gate", "rz", [q], [float(rng.uniform(0, 2 * np.pi))]))
+            else:
+                ops.append(("gate", "sx", [q], []))
+        perm = rng.permutation(n)
+        for i in range(n // 2):
+            ops.append(("gate", "cx", [int(perm[2 * i]), int(perm[2 * i + 1])], []))
+    return ops

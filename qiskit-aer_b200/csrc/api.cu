@@ -459,6 +459,16 @@ int b200sv_apply_gate_sequence(b200sv_handle h, int ngates, const int *nq, const
   });
 }
 
+int b200sv_apply_op_sequence(b200sv_handle h, int nops, const int *kind, const uint64_t *qubits, const double *mats,
+                             const int *slot, const uint8_t *codes, int nslots, int *passes_out) {
+  return guard([&] {
+    select(H);
+    if (nops < 0 || (nops > 0 && (!kind || !qubits || !mats))) throw Error("apply_op_sequence: bad arguments");
+    const int passes = nops ? apply_gate_sequence(*H, nops, kind, qubits, mats, 2, slot, codes, nslots) : 0;
+    if (passes_out) *passes_out = passes;
+  });
+}
+
 int b200sv_apply_batched_pauli(b200sv_handle h, const uint64_t *masks4) {
   return guard([&] { select(H); launch_batched_pauli(*H, masks4); });
 }

@@ -112,7 +112,8 @@ void launch_pack_half(State &s, int q, int bit, uint64_t begin, uint64_t count, 
 void launch_chunk_swap_peer(State &s, int q, void *peer, int upper, int half);
 
 // ---- tile-blocked multi-gate passes (tile.cu)
-int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats, int low_bits);
+int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats, int low_bits,
+                        const int *slot = nullptr, const uint8_t *codes_host = nullptr, int nslots = 0);
 
 // ---- reductions (reduce.cu) -------------------------------------------------
 void reduce_norm(State &s, double *out);

@@ -38,9 +38,9 @@ constexpr int kTileThreads = 256;
 constexpr int kLoBits = 8;            // tile-local bits covered by the thread id
 constexpr int kHiCount = kTileAmps / kTileThreads;  // staging iterations per thread
 constexpr int kRoundBits = 4;
-constexpr int kMaxRounds = 16;
+constexpr int kMaxRounds = 24;
 constexpr int kMaxTileGates = 16;   // == kMaxRounds: worst case one gate per round
-constexpr int kMaxRoundGates = 8;
+constexpr int kMaxRoundGates = 12;  // dense gates + per-state Pauli ops in one round
 
 __host__ __device__ constexpr int swz_vec(int u) {
   return u < 3 ? (1 << u) : u == 3 ? 1 : u == 4 ? 2 : u == 5 ? 4 : u == 6 ? 3 : u == 7 ? 6 : u == 8 ? 5 : u == 9 ? 7
@@ -57,8 +57,9 @@ struct TileRound {
   uint16_t eoff[16];            // phys(sum_i bit_i(e) << pos[i]) for the 16 elements of a sub-block
   uint16_t gbit[8];             // phys(1 << tpos[i]): contribution of group-id bit i
   uint8_t ngates;
-  uint8_t gate[kMaxRoundGates]; // index into mats
-  uint8_t form[kMaxRoundGates]; // 0..5: 2-qubit on round-bit pair; 6..9: 1-qubit on round bit (form-6)
+  uint8_t form[kMaxRoundGates];  // 0..5: 2-qubit on round-bit pair; 6..9: 1-qubit on round bit (form-6);
+                                 // 10..13: per-state Pauli on round bit (form-10), code table slot in gate[]
+  uint16_t gate[kMaxRoundGates]; // index into mats (dense) or error-code slot (Pauli)
 };
 struct TilePassParams {
   double2 mats[kMaxTileGates][16];  // 2q: row-major 4x4 with matrix bit0 <-> lower round bit; 1q: first 4 entries
@@ -67,6 +68,9 @@ struct TilePassParams {
   uint64_t ntiles;
   uint16_t soff_hi[kHiCount];       // phys(m << kLoBits)
   InsertList ins;                   // sorted tile bits (global positions)
+  const uint8_t *codes;             // [slot][state] Pauli codes 0..3 = I,X,Y,Z (batched noisy shots), or null
+  uint64_t nstates;
+  int state_shift;                  // tile index >> state_shift = state (tile bits are all < num_qubits)
   int nrounds;
   TileRound rounds[kMaxRounds];
 };
@@ -123,6 +127,21 @@ __device__ __forceinline__ void apply1(double2 (&a)[16], const double2 *__restri
   }
 }
 
+// per-state Pauli on round bit P (apply_pauli semantics, qubitvector.hpp:2393-2437: swap, Z sign, (-i)^num_y):
+// pure moves and sign flips.  `code` is uniform over the CTA (a tile never straddles two states).
+template <int P>
+__device__ __forceinline__ void apply_pauli_reg(double2 (&a)[16], int code) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    if (i & (1 << P)) continue;
+    const int j = i | (1 << P);
+    const double2 x0 = a[i], x1 = a[j];
+    if (code == 1) { a[i] = x1; a[j] = x0; }
+    else if (code == 2) { a[i] = mk<double>(x1.y, -x1.x); a[j] = mk<double>(-x0.y, x0.x); }
+    else { a[j] = mk<double>(-x1.x, -x1.y); }
+  }
+}
+
 __global__ void __launch_bounds__(kTileThreads, 2)
 tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassParams p) {
   extern __shared__ __align__(16) double2 tile[];
@@ -152,8 +171,21 @@ tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
 #pragma unroll
         for (int e = 0; e < 16; e++) a[e] = tile[base ^ R.eoff[e]];
         for (int k = 0; k < R.ngates; k++) {
+          const int form = R.form[k];
+          if (form >= 10) {  // sampled noise: Pauli chosen per state (shot)
+            const int code = p.codes[(size_t)R.gate[k] * p.nstates + (t >> p.state_shift)];
+            if (code) {
+              switch (form) {
+              case 10: apply_pauli_reg<0>(a, code); break;
+              case 11: apply_pauli_reg<1>(a, code); break;
+              case 12: apply_pauli_reg<2>(a, code); break;
+              default: apply_pauli_reg<3>(a, code); break;
+              }
+            }
+            continue;
+          }
           const double2 *m = p.mats[R.gate[k]];
-          switch (R.form[k]) {
+          switch (form) {
           case 0: apply2<0, 1>(a, m); break;
           case 1: apply2<0, 2>(a, m); break;
           case 2: apply2<0, 3>(a, m); break;
@@ -182,7 +214,8 @@ tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
 struct QGate {
   int nq;
   int q[2];
-  const double *mat;  // column-major complex<double>, 4 or 16 entries
+  const double *mat;  // column-major complex<double>, 4 or 16 entries; null for a per-state Pauli
+  int slot;           // error-code table slot for a per-state Pauli (kind 3)
 };
 
 static uint64_t qmask(const QGate &g) { return (1ull << g.q[0]) | (g.nq == 2 ? (1ull << g.q[1]) : 0); }
@@ -236,9 +269,12 @@ static int round_bit_of(const std::vector<int> &sorted_pos, int tile_pos) {
 
 // One pass: gates[sel] all fit the tile; tile_bits sorted global positions (kTB of them).
 static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::vector<int> &sel,
-                          const std::vector<int> &tile_bits) {
+                          const std::vector<int> &tile_bits, const uint8_t *dev_codes) {
   static thread_local TilePassParams p;
   p.ntiles = s.total_amps() >> kTB;
+  p.codes = dev_codes;
+  p.nstates = (uint64_t)s.nstates;
+  p.state_shift = s.nq - kTB;
   p.ins.n = kTB;
   for (int u = 0; u < kTB; u++) p.ins.pos[u] = (uint8_t)tile_bits[u];
   for (int u = 0; u < kLoBits; u++) p.goff_lo[u] = 1ull << tile_bits[u];
@@ -254,8 +290,7 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
       if (tile_bits[u] == q) return u;
     throw Error("tile pass: qubit not in tile");
   };
-  // matrices
-  if ((int)sel.size() > kMaxTileGates) throw Error("tile pass: too many gates");
+  int ndense = 0;
   // rounds: scan in order, capacity 4 tile positions, respect dependencies
   std::vector<int> rem(sel.size());
   for (size_t i = 0; i < sel.size(); i++) rem[i] = (int)i;  // indices into sel
@@ -283,7 +318,14 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
     std::sort(pos.begin(), pos.end());
     for (int li : take) {
       const QGate &g = gates[sel[li]];
-      double2 *M = p.mats[li];
+      if (!g.mat) {  // per-state Pauli
+        R.form[R.ngates] = (uint8_t)(10 + round_bit_of(pos, tile_pos(g.q[0])));
+        R.gate[R.ngates++] = (uint16_t)g.slot;
+        continue;
+      }
+      if (ndense >= kMaxTileGates) throw Error("tile pass: too many dense gates");
+      const int mi = ndense++;
+      double2 *M = p.mats[mi];
       if (g.nq == 1) {
         const int b = round_bit_of(pos, tile_pos(g.q[0]));
         for (int i = 0; i < 2; i++)
@@ -301,7 +343,7 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
         static const int form_of[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
         R.form[R.ngates] = (uint8_t)form_of[b0][b1];
       }
-      R.gate[R.ngates++] = (uint8_t)li;
+      R.gate[R.ngates++] = (uint16_t)mi;
     }
     rem.swap(rest);
   }
@@ -315,28 +357,58 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
   B200_CUDA(cudaGetLastError());
 }
 
-// Partition a gate sequence into tile passes (in-order greedy with dependency blocking) and run them.
+// Partition an op sequence into tile passes (in-order greedy with dependency blocking) and run them.
+// kind[i]: 1 = dense 1-qubit, 2 = dense 2-qubit, 3 = per-state Pauli on one qubit (code table slot[i]).
 // Returns the number of HBM passes used.
 int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats,
-                        int low_bits) {
+                        int low_bits, const int *slot, const uint8_t *codes_host, int nslots) {
   std::vector<QGate> gates(ngates);
+  bool any_pauli = false;
   for (int i = 0; i < ngates; i++) {
-    if (nq[i] != 1 && nq[i] != 2) throw Error("apply_gate_sequence: gates must act on 1 or 2 qubits");
-    gates[i].nq = nq[i];
-    for (int j = 0; j < nq[i]; j++) {
+    if (nq[i] < 1 || nq[i] > 3) throw Error("apply_gate_sequence: op kind must be 1, 2 (dense) or 3 (per-state Pauli)");
+    const bool pauli = nq[i] == 3;
+    gates[i].nq = pauli ? 1 : nq[i];
+    for (int j = 0; j < gates[i].nq; j++) {
       if (qubits[2 * i + j] >= (uint64_t)s.nq) throw Error("apply_gate_sequence: qubit out of range");
       gates[i].q[j] = (int)qubits[2 * i + j];
     }
     if (nq[i] == 2 && gates[i].q[0] == gates[i].q[1]) throw Error("apply_gate_sequence: duplicate qubit");
-    gates[i].mat = mats + 32 * (size_t)i;
+    gates[i].mat = pauli ? nullptr : mats + 32 * (size_t)i;
+    gates[i].slot = 0;
+    if (pauli) {
+      if (!slot || !codes_host || slot[i] < 0 || slot[i] >= nslots) throw Error("apply_gate_sequence: bad Pauli slot");
+      gates[i].slot = slot[i];
+      any_pauli = true;
+    }
   }
   const bool tiled = s.precision == B200SV_F64 && s.nq >= kTB;
-  if (!tiled) {  // small or single-precision states: one streaming pass per gate
-    for (auto &g : gates) launch_dense(s, g.q, g.nq, nullptr, 0, g.mat);
+  if (!tiled) {  // small or single-precision states: one streaming pass per op
+    for (auto &g : gates) {
+      if (g.mat) { launch_dense(s, g.q, g.nq, nullptr, 0, g.mat); continue; }
+      std::vector<uint64_t> m4(4 * (size_t)s.nstates, 0);  // batched_pauli_func masks (qubitvector_thrust.hpp:2819)
+      for (int64_t st = 0; st < s.nstates; st++) {
+        const int code = codes_host[(size_t)g.slot * s.nstates + st];
+        const uint64_t bit = 1ull << g.q[0];
+        m4[4 * st] = (code == 1 || code == 2) ? bit : 0;
+        m4[4 * st + 1] = (code == 2 || code == 3) ? bit : 0;
+        m4[4 * st + 2] = code == 2;
+        m4[4 * st + 3] = code != 0;
+      }
+      launch_batched_pauli(s, m4.data());
+    }
     return ngates;
   }
+  uint8_t *dev_codes = nullptr;
+  if (any_pauli) {
+    const size_t bytes = (size_t)nslots * s.nstates;
+    void *hm = s.ensure_pinned(bytes);
+    dev_codes = (uint8_t *)s.ensure_scratch(bytes);
+    B200_CUDA(cudaStreamSynchronize(s.stream));
+    memcpy(hm, codes_host, bytes);
+    B200_CUDA(cudaMemcpyAsync(dev_codes, hm, bytes, cudaMemcpyHostToDevice, s.stream));
+  }
   low_bits = std::max(1, std::min(low_bits, 5));
-  // tuning knobs (read once): B200SV_TILE_MAX_GATES caps the gates riding on one pass (FP64/HBM balance),
+  // tuning knobs (read once): B200SV_TILE_MAX_GATES caps the dense gates riding on one pass (FP64/HBM balance),
   // B200SV_TILE_LOW_BITS the number of low global bits forced into every tile (coalescing run length)
   static const int env_max_gates = [] { const char *e = getenv("B200SV_TILE_MAX_GATES"); return e ? atoi(e) : 0; }();
   static const int env_low_bits = [] { const char *e = getenv("B200SV_TILE_LOW_BITS"); return e ? atoi(e) : 0; }();
@@ -348,10 +420,14 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
   while (!rem.empty()) {
     uint64_t Q = (1ull << low_bits) - 1, blocked = 0;
     std::vector<int> sel, rest;
+    int ndense = 0;
     for (int i : rem) {
       const uint64_t m = qmask(gates[i]);
-      if ((m & blocked) || (int)sel.size() >= max_gates) { blocked |= m; rest.push_back(i); continue; }
-      if (__builtin_popcountll(Q | m) <= kTB) { Q |= m; sel.push_back(i); }
+      const bool dense = gates[i].mat != nullptr;
+      if ((m & blocked) || (dense && ndense >= max_gates) || (int)sel.size() >= 4 * kMaxTileGates) {
+        blocked |= m; rest.push_back(i); continue;
+      }
+      if (__builtin_popcountll(Q | m) <= kTB) { Q |= m; sel.push_back(i); ndense += dense; }
       else { blocked |= m; rest.push_back(i); }
     }
     // fill the tile with the lowest unused global bits
@@ -359,7 +435,7 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
     std::vector<int> tile_bits;
     for (int q = 0; q < 64; q++)
       if ((Q >> q) & 1) tile_bits.push_back(q);
-    run_tile_pass(s, gates, sel, tile_bits);
+    run_tile_pass(s, gates, sel, tile_bits, dev_codes);
     passes++;
     rem.swap(rest);
   }

@@ -188,6 +188,40 @@ class QubitVectorB200:
                                                         C.byref(passes)))
         return passes.value
 
+    def apply_op_sequence(self, ops, codes=None):
+        """ops: list of ("dense", qubits, column-major matrix) | ("pauli", qubit, slot); codes: uint8 array
+        [nslots][num_states] of per-state Pauli codes (0..3 = I, X, Y, Z).  Returns the passes used."""
+        nops = len(ops)
+        kind = np.zeros(nops, dtype=np.int32)
+        qs = np.zeros(2 * nops, dtype=np.uint64)
+        mats = np.zeros((nops, 16), dtype=np.complex128)
+        slot = np.zeros(nops, dtype=np.int32)
+        for i, op in enumerate(ops):
+            if op[0] == "dense":
+                q = list(op[1])
+                kind[i] = len(q)
+                qs[2 * i:2 * i + len(q)] = q
+                m = np.asarray(op[2], dtype=np.complex128).reshape(-1)
+                mats[i, :m.size] = m
+            elif op[0] == "pauli":
+                kind[i] = 3
+                qs[2 * i] = op[1]
+                slot[i] = op[2]
+            else:
+                raise ValueError(op[0])
+        if codes is None:
+            codes_arr, nslots, cp = None, 0, None
+        else:
+            codes_arr = np.ascontiguousarray(codes, dtype=np.uint8).reshape(-1, self.num_states)
+            nslots = codes_arr.shape[0]
+            cp = codes_arr.ctypes.data_as(C.POINTER(C.c_uint8))
+        passes = C.c_int(0)
+        capi.check(self._lib.b200sv_apply_op_sequence(self.h, nops, kind.ctypes.data_as(C.POINTER(C.c_int)),
+                                                      qs.ctypes.data_as(_u64p), mats.ctypes.data_as(_f64p),
+                                                      slot.ctypes.data_as(C.POINTER(C.c_int)), cp, nslots,
+                                                      C.byref(passes)))
+        return passes.value
+
     def apply_batched_pauli_ops(self, masks4):
         """masks4: [num_states][4] = x_mask, z_mask, num_y, apply (qubitvector_thrust.hpp:2892)."""
         a = np.ascontiguousarray(masks4, dtype=np.uint64).reshape(-1)

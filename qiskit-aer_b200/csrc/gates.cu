@@ -204,8 +204,43 @@ diag_kernel(cx<T> *__restrict__ psi, const cx<T> *__restrict__ big_table, const 
   }
 }
 
+// large diagonals (k > 10, e.g. the 2^m projector of a per-shot measurement of m qubits,
+// statevector_state.hpp:960-1014): table stays in global memory (L2 resident), same streaming pass
+struct BigDiagParams {
+  uint64_t total;
+  int k;
+  uint8_t q[32];
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+diag_big_kernel(cx<T> *__restrict__ psi, const cx<T> *__restrict__ table, const __grid_constant__ BigDiagParams p) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < p.total; idx += stride) {
+    uint32_t iv = 0;
+    for (int j = 0; j < p.k; j++) iv |= (uint32_t)((idx >> p.q[j]) & 1ull) << j;
+    psi[idx] = cmul(psi[idx], table[iv]);
+  }
+}
+static void launch_diagonal_big(State &s, const int *qubits, int k, const double *diag) {
+  if (k > 28) throw Error("apply_diagonal_matrix: more than 28 qubits is not supported");
+  const size_t dim = 1ull << k, bytes = dim * s.amp_bytes();
+  void *hm = s.ensure_pinned(bytes);
+  void *dm = s.ensure_scratch(bytes);
+  B200_CUDA(cudaStreamSynchronize(s.stream));
+  if (s.precision == B200SV_F64) memcpy(hm, diag, bytes);
+  else for (size_t i = 0; i < 2 * dim; i++) ((float *)hm)[i] = (float)diag[i];
+  B200_CUDA(cudaMemcpyAsync(dm, hm, bytes, cudaMemcpyHostToDevice, s.stream));
+  BigDiagParams p;
+  p.k = k; p.total = s.total_amps();
+  for (int j = 0; j < k; j++) p.q[j] = (uint8_t)qubits[j];
+  const int grid = grid_for(s, p.total, 256, 16);
+  if (s.precision == B200SV_F64) diag_big_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, (const double2 *)dm, p);
+  else diag_big_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, (const float2 *)dm, p);
+  B200_CUDA(cudaGetLastError());
+}
+
 void launch_diagonal(State &s, const int *qubits, int k, const double *diag) {
-  if (k > kMaxDiagQubits) throw Error("apply_diagonal_matrix: more than 10 qubits is not supported");
+  if (k > kMaxDiagQubits) { launch_diagonal_big(s, qubits, k, diag); return; }
   const int dim = 1 << k;
   const bool f64 = s.precision == B200SV_F64;
   void *big = nullptr;

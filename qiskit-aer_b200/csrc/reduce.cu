@@ -342,7 +342,7 @@ prob_kernel(const cx<T> *__restrict__ psi, const __grid_constant__ ProbParams p,
   }
 }
 void reduce_probabilities(State &s, const int *qubits, int k, double *out) {
-  if (k > 20) throw Error("probabilities(qubits): more than 20 measured qubits per call is not supported");
+  if (k > 26) throw Error("probabilities(qubits): more than 26 measured qubits per call is not supported");
   ProbParams p;
   p.nq = s.nq; p.k = k;
   p.LB = std::min(8, s.nq);

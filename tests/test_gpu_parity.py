@@ -101,7 +101,7 @@ def test_dense_matrix_generic_large_k(k):
     assert np.max(np.abs(ora.vector() - gpu.vector())) < 1e-12
 
 
-@pytest.mark.parametrize("k", [1, 3, 5, 7, 10])
+@pytest.mark.parametrize("k", [1, 3, 5, 7, 10, 12, 13])
 def test_diagonal_sizes(k):
     n = 13
     rng = np.random.default_rng(70 + k)

@@ -415,6 +415,14 @@ def b200_arm(args):
             ent = json.load(open(tp)).get(dom)
             if ent:  # per-amplitude DRAM bytes from the committed ncu --set full capture, scaled to this launch
                 traffic = ent["bytes_per_amp"] * 2.0 ** n_local
+        fp64 = None
+        if dom == "tile_pass":
+            # the tile pass carries several gates per HBM pass and is FP64-pipe bound: report that roofline too
+            flops = sum(8.0 * 2 ** len(op[1] if op[0] == "unitary" else op[2]) for op in ops) * 2.0 ** n_local
+            tf = flops * args.steps / (tot / 1e3) / 1e12
+            fp64 = {"achieved_tflops": tf, "peak_tflops": 37.0, "frac": tf / 37.0,
+                    "peak_source": "measured DFMA/DMMA issue peak on B200, tools/micro/dfma_operands.cu (profiles/r01_fp64_pipe_microbench.md)",
+                    "gates_per_pass": len(ops) * args.steps / max(cnt, 1)}
         out = {
             "metric": "amplitude_updates_per_s", "value": value, "unit": "amp-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -432,7 +440,7 @@ def b200_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": dom, "launches": cnt, "avg_ms": avg_ms,
                          "bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
-                         "frac_of_nominal_8000": achieved / 8000.0},
+                         "frac_of_nominal_8000": achieved / 8000.0, "fp64": fp64},
             "per_kernel": {c: {"launches": v[0], "avg_ms": v[1] / v[0],
                                "GBps": (bytes_per_launch / (v[1] / v[0] / 1e3) / 1e9) if c.startswith(("dense", "diagonal", "tile")) else None}
                            for c, v in sorted(per_class.items())},

@@ -35,7 +35,7 @@ template <typename T, int K> struct DenseParams {
 };
 
 template <typename T, int K>
-__global__ void __launch_bounds__(K >= 5 ? 128 : 256)
+__global__ void __launch_bounds__(K >= 5 ? 128 : 256, (K == 3 || K == 4) ? 2 : 1)
 dense_kernel(cx<T> *__restrict__ psi, const __grid_constant__ DenseParams<T, K> p) {
   constexpr int DIM = 1 << K;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;

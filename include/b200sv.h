@@ -134,6 +134,17 @@ int b200sv_apply_gate_sequence(b200sv_handle h, int ngates, const int *nq, const
 int b200sv_apply_op_sequence(b200sv_handle h, int nops, const int *kind, const uint64_t *qubits, const double *mats,
                              const int *slot, const uint8_t *codes, int nslots, int *passes_out);
 
+/* Per-state measurement collapse for batched containers (apply_batched_measure / apply_batched_reset,
+ * qubitvector_thrust.hpp:2251-2460: check_measure_probability_func + reset_after_measure_func): for every
+ * state s with active[s] != 0, amplitudes whose `qubits` bits differ from outcomes[s] are zeroed and the
+ * rest are multiplied by scales[s] (= 1/sqrt(p_outcome)).  One launch for all states. */
+int b200sv_collapse(b200sv_handle h, const uint64_t *qubits, int k, const uint64_t *outcomes, const double *scales,
+                    const uint8_t *active);
+/* A handle onto states [first_state, first_state + num_states) of a batched container, sharing its memory
+ * and stream (per-shot fallbacks of the batched executor, batch_shots_executor.hpp:594-603; per-parameter
+ * matrices, apply_batched_matrix qubitvector_thrust.hpp:1578-1611).  Destroy it before the parent. */
+int b200sv_create_view(b200sv_handle *out, b200sv_handle parent, int64_t first_state, int64_t num_states);
+
 /* ---- reductions (out has num_states entries unless noted) --------------- */
 int b200sv_norm(b200sv_handle h, double *out);          /* norm() (qubitvector.hpp:1879) */
 /* norm(qubits, mat) (qubitvector.hpp:1889) -- Kraus probability ||M psi||^2 */

@@ -3,38 +3,102 @@
 // A header-only `statevec_t` for `AER::Statevector::State<statevec_t>`
 // (src/simulators/statevector/statevector_state.hpp:100-101) exposing the same
 // method set as AER::QV::QubitVector<data_t> (src/simulators/statevector/
-// qubitvector.hpp:62-480 -- signatures mirrored one for one) and forwarding
+// qubitvector.hpp:62-480 -- signatures mirrored one for one) plus the batched
+// multi-shot hooks of QubitVectorThrust (src/simulators/statevector/
+// qubitvector_thrust.hpp:1184-1214,2251-2484,2683-2713,2892-3402), forwarding
 // every amplitude operation to the C ABI of the B200 engine (include/b200sv.h).
 // Errors come back as the std::runtime_error the executors already catch
 // (src/simulators/circuit_executor.hpp:574,726).
 //
 // Needs the Aer source tree on the include path (it uses Aer's own types:
-// reg_t, cvector_t, AER::Vector, Operations::Op, RngEngine, QV::Rotation).
-// One object = one statevector (= one chunk in cache-blocking mode); like the
-// CPU class it reports support_global_indexing() == false, so the State
-// rewrites global-qubit diagonals/controls per chunk on the host
-// (statevector_state.hpp:735-753) and chunk swaps arrive through
-// apply_chunk_swap(qubits, other_chunk, write_back).
+// reg_t, cvector_t, AER::Vector, Operations::Op, RngEngine, ClassicalRegister,
+// QV::Rotation).
+//
+// Three modes, chosen by how the executors call chunk_setup():
+//  * single state (Executor::run_circuit_*): one vector = one handle;
+//  * cache blocking (ParallelStateExecutor): one vector = one chunk = one handle;
+//    like the CPU class it reports support_global_indexing() == false, so the
+//    State rewrites global-qubit diagonals/controls per chunk on the host
+//    (statevector_state.hpp:735-753) and chunk swaps arrive through
+//    apply_chunk_swap(qubits, other_chunk, write_back);
+//  * batched shots (BatchShotsExecutor, `batched_shots_gpu`): every vector of a
+//    group is a view on ONE container handle with num_states = shots.  With
+//    enable_batch(true) the first vector executes for all states in one launch
+//    and the others return immediately (the get_chunk_count() contract,
+//    qubitvector_thrust.hpp:1201-1214); with enable_batch(false) a vector acts
+//    on its own state only.  Classical registers live on the host, one
+//    AER::ClassicalRegister per shot.
+//
+// Gate queue: dense 1-/2-qubit gates (and, in batched mode, cx / small
+// diagonals / sampled Pauli noise) are queued and flushed through
+// b200sv_apply_op_sequence, which packs them into as few HBM passes as possible;
+// every other method flushes first, so observable semantics are those of
+// immediate application.  Disable with B200SV_GATE_QUEUE=0.
 #ifndef _qv_qubit_vector_b200_hpp_
 #define _qv_qubit_vector_b200_hpp_
 
 #include <complex>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "b200sv.h"
+#include "framework/creg.hpp"
 #include "framework/json.hpp"
 #include "framework/linalg/vector.hpp"
 #include "framework/operations.hpp"
 #include "framework/rng.hpp"
 #include "framework/types.hpp"
 #include "framework/utils.hpp"
-#include "simulators/statevector/qubitvector.hpp"  // QV::Rotation, Linalg::VMatrix helpers
+#include "simulators/statevector/qubitvector.hpp"  // QV::Rotation, pauli_masks_and_phase, Linalg::VMatrix
 
 namespace AER {
 namespace QV {
+
+namespace b200detail {
+inline void ck(int rc) {
+  if (rc) throw std::runtime_error(std::string("b200sv: ") + b200sv_last_error());
+}
+// ops waiting for the next flush: dense 1-/2-qubit gates and per-state Pauli ops
+struct OpQueue {
+  std::vector<int> kind, slot;
+  std::vector<uint64_t> qubits;
+  std::vector<double> mats;
+  std::vector<uint8_t> codes;  // [nslots][nstates]
+  int nslots = 0;
+  bool empty() const { return kind.empty(); }
+  void clear() { kind.clear(); slot.clear(); qubits.clear(); mats.clear(); codes.clear(); nslots = 0; }
+  void push_dense(const uint64_t *q, int k, const std::complex<double> *m) {
+    kind.push_back(k);
+    slot.push_back(0);
+    qubits.push_back(q[0]);
+    qubits.push_back(k == 2 ? q[1] : 0);
+    const size_t off = mats.size();
+    mats.resize(off + 32, 0.0);
+    std::memcpy(&mats[off], m, ((size_t)1 << (2 * k)) * sizeof(std::complex<double>));
+  }
+  void flush(b200sv_handle h) {
+    if (kind.empty()) return;
+    const int rc = b200sv_apply_op_sequence(h, (int)kind.size(), kind.data(), qubits.data(), mats.data(), slot.data(),
+                                            codes.empty() ? nullptr : codes.data(), nslots, nullptr);
+    clear();
+    ck(rc);
+  }
+};
+// one batched-shot container shared by the vectors of a group
+struct Batch {
+  b200sv_handle h = nullptr;
+  size_t nq = 0, nstates = 0;
+  uint_t first_index = 0;
+  std::vector<ClassicalRegister> cregs;
+  int_t cond_reg = -1;
+  bool on = true;
+  OpQueue queue;
+  ~Batch() { if (h) b200sv_destroy(h); }
+};
+}  // namespace b200detail
 
 template <typename data_t = double> class QubitVectorB200 {
 public:
@@ -48,7 +112,8 @@ public:
       if (o.h_) o.flush();
       release();
       h_ = o.h_; num_qubits_ = o.num_qubits_; data_size_ = o.data_size_; chunk_index_ = o.chunk_index_;
-      o.h_ = nullptr; o.num_qubits_ = 0; o.data_size_ = 0;
+      batch_ = std::move(o.batch_); batch_pos_ = o.batch_pos_; view_ = o.view_; tmp_view_ = o.tmp_view_;
+      o.h_ = nullptr; o.view_ = nullptr; o.tmp_view_ = nullptr; o.num_qubits_ = 0; o.data_size_ = 0;
     }
     return *this;
   }
@@ -58,6 +123,12 @@ public:
 
   //---------------------------------------------------------------- size / config
   virtual void set_num_qubits(size_t num_qubits) {
+    if (batch_) {
+      if (num_qubits != batch_->nq) throw std::runtime_error("QubitVectorB200: batched container holds a different qubit count");
+      num_qubits_ = num_qubits;
+      data_size_ = 1ull << num_qubits;
+      return;
+    }
     if (h_ && num_qubits == num_qubits_) return;
     release();
     ck(b200sv_create(&h_, (int)num_qubits, 1, sizeof(data_t) == 8 ? B200SV_F64 : B200SV_F32, device()));
@@ -71,9 +142,9 @@ public:
     size_t shift_mb = std::max<int_t>(0, num_qubits + unit - 20);
     return 1ULL << shift_mb;
   }
-  bool top_of_group() { return true; }
+  bool top_of_group() { return batch_ ? batch_pos_ == 0 : true; }
   std::complex<data_t> *data() const { return nullptr; }  // amplitudes live in HBM
-  void *device_data() const { void *p = nullptr; flush(); ck(b200sv_device_ptr(h_, &p)); return p; }
+  void *device_data() const { void *p = nullptr; flush(); ck(b200sv_device_ptr(Hs(), &p)); return p; }
 
   void set_json_chop_threshold(double t) { json_chop_threshold_ = t; }
   double get_json_chop_threshold() { return json_chop_threshold_; }
@@ -88,18 +159,49 @@ public:
   int get_sample_measure_index_size() { return sample_measure_index_size_; }
   void set_max_matrix_bits(int_t) {}
   void set_max_sampling_shots(int_t) {}
-  void synchronize(void) { if (h_) { flush(); ck(b200sv_synchronize(h_)); } }
-  virtual bool enable_batch(bool) const { return false; }
+  void synchronize(void) { if (batch_ || h_) { flush(); ck(b200sv_synchronize(Hs())); } }
   bool support_global_indexing(void) { return false; }
-  virtual bool batched_optimization_supported(void) { return false; }
+  virtual bool batched_optimization_supported(void) { return sizeof(data_t) == 8; }
 
-  //---------------------------------------------------------------- chunks
-  uint_t chunk_setup(int, int, uint_t chunk_index, uint_t num_local_chunks) {
+  // enable_batch (qubitvector_thrust.hpp:1184-1198): returns the previous setting
+  virtual bool enable_batch(bool flg) const {
+    if (!batch_) return false;
+    const bool prev = batch_->on;
+    if (prev != flg) batch_->queue.flush(batch_->h);
+    batch_->on = flg;
+    return prev;
+  }
+
+  //---------------------------------------------------------------- chunks / containers
+  // chunk_setup (qubitvector.hpp:1045; thrust :860-935).  chunk_bits == num_qubits with several local
+  // "chunks" is the multi-shot container of BatchShotsExecutor (chunk_manager.hpp:223-264).
+  uint_t chunk_setup(int chunk_bits, int num_qubits, uint_t chunk_index, uint_t num_local_chunks) {
     chunk_index_ = chunk_index;
+    drop_batch();
+    if (chunk_bits == num_qubits && num_local_chunks > 1 && sizeof(data_t) == 8) {
+      release();
+      batch_ = std::make_shared<b200detail::Batch>();
+      ck(b200sv_create(&batch_->h, chunk_bits, (int64_t)num_local_chunks, B200SV_F64, device()));
+      batch_->nq = chunk_bits;
+      batch_->nstates = num_local_chunks;
+      batch_->first_index = chunk_index;
+      batch_->cregs.resize(num_local_chunks);
+      batch_pos_ = 0;
+      num_qubits_ = chunk_bits;
+      data_size_ = 1ull << chunk_bits;
+    }
     return num_local_chunks;
   }
-  uint_t chunk_setup(QubitVectorB200<data_t> &, const uint_t chunk_index) {
+  uint_t chunk_setup(QubitVectorB200<data_t> &base, const uint_t chunk_index) {
     chunk_index_ = chunk_index;
+    drop_batch();
+    if (base.batch_) {
+      release();
+      batch_ = base.batch_;
+      batch_pos_ = chunk_index - batch_->first_index;
+      num_qubits_ = batch_->nq;
+      data_size_ = 1ull << batch_->nq;
+    }
     return 0;
   }
   uint_t chunk_index(void) { return chunk_index_; }
@@ -116,59 +218,58 @@ public:
   void apply_chunk_swap(const reg_t &qubits, QubitVectorB200<data_t> &src, bool write_back = true) {
     uint_t q0 = qubits[qubits.size() - 2], q1 = qubits[qubits.size() - 1];
     if (q0 > q1) std::swap(q0, q1);
+    synchronize();
+    src.synchronize();
     if (q0 >= num_qubits_) {  // both global: exchange (or copy) whole chunks
       const size_t bytes = data_size_ * sizeof(std::complex<data_t>);
-      synchronize(); src.synchronize();
       std::vector<char> a(bytes), b(bytes);  // rare path (X on a global qubit): staged through the host
-      ck(b200sv_download(src.h_, b.data(), 0, data_size_));
-      if (write_back) { flush(); ck(b200sv_download(h_, a.data(), 0, data_size_)); ck(b200sv_upload(src.h_, a.data(), 0, data_size_)); }
-      flush(); ck(b200sv_upload(h_, b.data(), 0, data_size_));
+      ck(b200sv_download(src.Hs(), b.data(), 0, data_size_));
+      if (write_back) { ck(b200sv_download(Hs(), a.data(), 0, data_size_)); ck(b200sv_upload(src.Hs(), a.data(), 0, data_size_)); }
+      ck(b200sv_upload(Hs(), b.data(), 0, data_size_));
       return;
     }
     // this (lower chunk: its q0=1 half) <-> src (q0=0 half); the kernel moves both directions
     const bool this_is_upper = !(chunk_index_ < src.chunk_index_);
-    src.synchronize();
-    flush(); ck(b200sv_chunk_swap_peer(h_, (int)q0, src.device_data(), this_is_upper ? 1 : 0, 0));
-    flush(); ck(b200sv_chunk_swap_peer(h_, (int)q0, src.device_data(), this_is_upper ? 1 : 0, 1));
+    void *peer = src.device_data();
+    ck(b200sv_chunk_swap_peer(Hs(), (int)q0, peer, this_is_upper ? 1 : 0, 0));
+    ck(b200sv_chunk_swap_peer(Hs(), (int)q0, peer, this_is_upper ? 1 : 0, 1));
     synchronize();
   }
   void apply_chunk_swap(const reg_t &, uint_t) { throw std::runtime_error("QubitVectorB200: remote (MPI) chunk swap is not supported"); }
   void apply_chunk_swap(QubitVectorB200<data_t> &, uint_t, uint_t, uint_t) { throw std::runtime_error("QubitVectorB200: multi chunk swap is not supported"); }
 
   //---------------------------------------------------------------- data
-  void zero() { flush(); ck(b200sv_zero(h_)); }
-  void initialize() { flush(); ck(b200sv_initialize(h_)); }
+  void zero() { if (idle()) return; drop_queue(); ck(b200sv_zero(H())); }
+  void initialize() { if (idle()) return; drop_queue(); ck(b200sv_initialize(H())); }
   void initialize(const QubitVectorB200<data_t> &obj) {
     set_num_qubits(obj.num_qubits_);
     auto v = obj.copy_to_vector();
-    flush(); ck(b200sv_upload(h_, v.data(), 0, data_size_));
+    flush(); ck(b200sv_upload(Hs(), v.data(), 0, data_size_));
   }
   template <typename list_t> void initialize_from_vector(const list_t &vec) {
     if (data_size_ != vec.size()) throw std::runtime_error("QubitVector::initialize input vector is incorrect length");
     std::vector<std::complex<data_t>> tmp(vec.size());
     for (size_t i = 0; i < vec.size(); i++) tmp[i] = std::complex<data_t>(vec[i]);
-    flush(); ck(b200sv_upload(h_, tmp.data(), 0, data_size_));
+    upload_all(tmp.data());
   }
   void initialize_from_vector(std::vector<std::complex<data_t>> &&vec) { initialize_from_data(vec.data(), vec.size()); }
   void initialize_from_vector(AER::Vector<std::complex<data_t>> &&vec) { initialize_from_data(vec.data(), vec.size()); }
   virtual void move_from_vector(AER::Vector<std::complex<data_t>> &&vec) { initialize_from_data(vec.data(), vec.size()); }
   void initialize_from_data(const std::complex<data_t> *data, const size_t num_states) {
     if (data_size_ != num_states) throw std::runtime_error("QubitVector::initialize input vector is incorrect length");
-    flush(); ck(b200sv_upload(h_, data, 0, data_size_));
+    upload_all(data);
   }
-  virtual void initialize_creg(uint_t, uint_t) {}
-  virtual void initialize_creg(uint_t, uint_t, const std::string &, const std::string &) {}
   void initialize_component(const reg_t &qubits, const cvector_t<double> &state) {
-    flush(); ck(b200sv_initialize_component(h_, qubits.data(), (int)qubits.size(), (const double *)state.data()));
+    for_target([&](b200sv_handle h) { ck(b200sv_initialize_component(h, qubits.data(), (int)qubits.size(), (const double *)state.data())); });
   }
   cvector_t<data_t> vector() const {
     cvector_t<data_t> ret(data_size_);
-    flush(); ck(b200sv_download(h_, ret.data(), 0, data_size_));
+    flush(); ck(b200sv_download(Hs(), ret.data(), 0, data_size_));
     return ret;
   }
   AER::Vector<std::complex<data_t>> copy_to_vector() const {
     AER::Vector<std::complex<data_t>> ret(data_size_, false);
-    flush(); ck(b200sv_download(h_, ret.data(), 0, data_size_));
+    flush(); ck(b200sv_download(Hs(), ret.data(), 0, data_size_));
     return ret;
   }
   AER::Vector<std::complex<data_t>> move_to_vector() { return copy_to_vector(); }
@@ -184,48 +285,94 @@ public:
   }
   std::complex<data_t> get_state(uint_t pos) const {
     std::complex<data_t> v;
-    flush(); ck(b200sv_download(h_, &v, pos, 1));
+    flush(); ck(b200sv_download(Hs(), &v, pos, 1));
     return v;
   }
-  void set_state(uint_t pos, std::complex<data_t> &val) { flush(); ck(b200sv_upload(h_, &val, pos, 1)); }
-  void checkpoint() { flush(); ck(b200sv_checkpoint(h_)); }
-  void revert(bool keep) { flush(); ck(b200sv_revert(h_, keep ? 1 : 0)); }
+  void set_state(uint_t pos, std::complex<data_t> &val) { flush(); ck(b200sv_upload(Hs(), &val, pos, 1)); }
+  void checkpoint() { flush(); ck(b200sv_checkpoint(Hs())); }
+  void revert(bool keep) { flush(); ck(b200sv_revert(Hs(), keep ? 1 : 0)); }
   std::complex<double> inner_product() const {
     double re, im;
-    flush(); ck(b200sv_inner_product(h_, &re, &im));
+    flush(); ck(b200sv_inner_product(Hs(), &re, &im));
     return {re, im};
+  }
+
+  //---------------------------------------------------------------- classical registers (batched mode keeps them per shot)
+  virtual void initialize_creg(uint_t num_memory, uint_t num_register) {
+    if (batch_) batch_->cregs[batch_pos_].initialize(num_memory, num_register);
+  }
+  virtual void initialize_creg(uint_t num_memory, uint_t num_register, const std::string &memory_hex,
+                               const std::string &register_hex) {
+    if (batch_) batch_->cregs[batch_pos_].initialize(num_memory, num_register, memory_hex, register_hex);
+  }
+  // read_measured_data (qubitvector_thrust.hpp:2463-2484): this shot's bits into the State's creg
+  template <typename storage_t> void read_measured_data(storage_t &creg) { read_creg(creg); }
+  virtual void set_conditional(int_t reg) { if (batch_ && !idle()) batch_->cond_reg = reg; }
+  virtual int_t set_batched_system_conditional(int_t, reg_t &) { return -1; }
+  virtual void apply_bfunc(const Operations::Op &op) {  // bfunc_kernel (:3180)
+    if (!batch_ || idle()) return;
+    for_states([&](size_t s) { batch_->cregs[s].apply_bfunc(op); });
+  }
+  virtual void apply_roerror(const Operations::Op &op, std::vector<RngEngine> &rng) {  // roerror_kernel (:3302)
+    if (!batch_ || idle()) return;
+    for_states([&](size_t s) { batch_->cregs[s].apply_roerror(op, rng[s]); });
   }
 
   //---------------------------------------------------------------- gates (qubitvector.hpp:225-294)
   void apply_matrix(const reg_t &qubits, const cvector_t<double> &mat) {
-    if (enqueue(qubits, mat)) return;
-    flush();
-    ck(b200sv_apply_matrix(h_, qubits.data(), (int)qubits.size(), (const double *)mat.data()));
+    if (idle()) return;
+    if (enqueue(qubits, mat.data(), mat.size())) return;
+    for_target([&](b200sv_handle h) { ck(b200sv_apply_matrix(h, qubits.data(), (int)qubits.size(), (const double *)mat.data())); });
   }
   void apply_multiplexer(const reg_t &control_qubits, const reg_t &target_qubits, const cvector_t<double> &mat) {
-    flush(); ck(b200sv_apply_multiplexer(h_, control_qubits.data(), (int)control_qubits.size(), target_qubits.data(),
-                                (int)target_qubits.size(), (const double *)mat.data()));
+    for_target([&](b200sv_handle h) {
+      ck(b200sv_apply_multiplexer(h, control_qubits.data(), (int)control_qubits.size(), target_qubits.data(),
+                                  (int)target_qubits.size(), (const double *)mat.data()));
+    });
   }
   void apply_diagonal_matrix(const reg_t &qubits, const cvector_t<double> &mat) {
-    flush(); ck(b200sv_apply_diagonal(h_, qubits.data(), (int)qubits.size(), (const double *)mat.data()));
+    if (idle()) return;
+    if (batch_queueing() && qubits.size() <= 2 && mat.size() == (1ull << qubits.size())) {  // ride on the tile passes
+      const size_t dim = mat.size();
+      std::vector<std::complex<double>> full(dim * dim, 0.0);
+      for (size_t i = 0; i < dim; i++) full[i + dim * i] = mat[i];
+      if (enqueue(qubits, full.data(), full.size())) return;
+    }
+    for_target([&](b200sv_handle h) { ck(b200sv_apply_diagonal(h, qubits.data(), (int)qubits.size(), (const double *)mat.data())); });
   }
   void apply_permutation_matrix(const reg_t &qubits, const std::vector<std::pair<uint_t, uint_t>> &pairs) {
     std::vector<uint64_t> flat;
     for (auto &p : pairs) { flat.push_back(p.first); flat.push_back(p.second); }
-    flush(); ck(b200sv_apply_permutation(h_, qubits.data(), (int)qubits.size(), flat.data(), (int)pairs.size()));
+    for_target([&](b200sv_handle h) { ck(b200sv_apply_permutation(h, qubits.data(), (int)qubits.size(), flat.data(), (int)pairs.size())); });
   }
-  void apply_mcx(const reg_t &qubits) { flush(); ck(b200sv_apply_mcx(h_, qubits.data(), (int)qubits.size())); }
-  void apply_mcy(const reg_t &qubits) { flush(); ck(b200sv_apply_mcy(h_, qubits.data(), (int)qubits.size())); }
+  void apply_mcx(const reg_t &qubits) {
+    if (idle()) return;
+    if (batch_queueing() && qubits.size() <= 2) {  // noisy batches: x / cx as dense gates share passes with the noise
+      static const std::complex<double> X[4] = {0, 1, 1, 0};
+      static const std::complex<double> CX[16] = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0};  // control = qubits[0]
+      if (enqueue(qubits, qubits.size() == 1 ? X : CX, qubits.size() == 1 ? 4 : 16)) return;
+    }
+    for_target([&](b200sv_handle h) { ck(b200sv_apply_mcx(h, qubits.data(), (int)qubits.size())); });
+  }
+  void apply_mcy(const reg_t &qubits) { for_target([&](b200sv_handle h) { ck(b200sv_apply_mcy(h, qubits.data(), (int)qubits.size())); }); }
   void apply_mcphase(const reg_t &qubits, const std::complex<double> phase) {
-    flush(); ck(b200sv_apply_mcphase(h_, qubits.data(), (int)qubits.size(), phase.real(), phase.imag()));
+    if (idle()) return;
+    if (batch_queueing() && qubits.size() <= 2) {
+      std::complex<double> d[16] = {};
+      const size_t dim = 1ull << qubits.size();
+      for (size_t i = 0; i < dim; i++) d[i + dim * i] = 1.0;
+      d[dim * dim - 1] = phase;
+      if (enqueue(qubits, d, dim * dim)) return;
+    }
+    for_target([&](b200sv_handle h) { ck(b200sv_apply_mcphase(h, qubits.data(), (int)qubits.size(), phase.real(), phase.imag())); });
   }
   void apply_mcu(const reg_t &qubits, const cvector_t<double> &mat) {
+    if (idle()) return;
     // an uncontrolled, non-diagonal 2x2 is a plain 1-qubit matrix (qubitvector.hpp:1676-1680): queue it
-    if (qubits.size() == 1 && !(mat[1] == 0.0 && mat[2] == 0.0) && enqueue(qubits, mat)) return;
-    flush();
-    ck(b200sv_apply_mcu(h_, qubits.data(), (int)qubits.size(), (const double *)mat.data()));
+    if (qubits.size() == 1 && (batch_queueing() || !(mat[1] == 0.0 && mat[2] == 0.0)) && enqueue(qubits, mat.data(), mat.size())) return;
+    for_target([&](b200sv_handle h) { ck(b200sv_apply_mcu(h, qubits.data(), (int)qubits.size(), (const double *)mat.data())); });
   }
-  void apply_mcswap(const reg_t &qubits) { flush(); ck(b200sv_apply_mcswap(h_, qubits.data(), (int)qubits.size())); }
+  void apply_mcswap(const reg_t &qubits) { for_target([&](b200sv_handle h) { ck(b200sv_apply_mcswap(h, qubits.data(), (int)qubits.size())); }); }
   void apply_multi_swaps(const reg_t &qubits) {  // pairs of qubits, qubitvector.hpp:1843-1876
     for (size_t i = 0; i + 1 < qubits.size(); i += 2) apply_mcswap({qubits[i], qubits[i + 1]});
   }
@@ -242,10 +389,10 @@ public:
     }
   }
   void apply_pauli(const reg_t &qubits, const std::string &pauli, const complex_t &coeff = 1) {
-    flush(); ck(b200sv_apply_pauli(h_, qubits.data(), (int)qubits.size(), pauli.c_str(), coeff.real(), coeff.imag()));
+    for_target([&](b200sv_handle h) { ck(b200sv_apply_pauli(h, qubits.data(), (int)qubits.size(), pauli.c_str(), coeff.real(), coeff.imag())); });
   }
 
-  //---------------------------------------------------------------- reductions (qubitvector.hpp:302-411)
+  //---------------------------------------------------------------- reductions (qubitvector.hpp:302-411); a vector's own state
   virtual double probability(const uint_t outcome) const { return std::norm(std::complex<double>(get_state(outcome))); }
   virtual std::vector<double> probabilities() const {
     reg_t all(num_qubits_);
@@ -254,19 +401,29 @@ public:
   }
   virtual std::vector<double> probabilities(const reg_t &qubits) const {
     std::vector<double> p(1ull << qubits.size());
-    flush(); ck(b200sv_probabilities(h_, qubits.data(), (int)qubits.size(), p.data()));
+    flush(); ck(b200sv_probabilities(Hs(), qubits.data(), (int)qubits.size(), p.data()));
     return p;
   }
   virtual reg_t sample_measure(const std::vector<double> &rnds) const {
     reg_t s(rnds.size());
-    flush(); ck(b200sv_sample_measure(h_, rnds.data(), (int64_t)rnds.size(), s.data()));
+    flush(); ck(b200sv_sample_measure(Hs(), rnds.data(), (int64_t)rnds.size(), s.data()));
     return s;
   }
-  double norm() const { double v; flush(); ck(b200sv_norm(h_, &v)); return v; }
+  double norm() const {
+    if (batch_ && batch_->on) {  // per-vector partial sums contract: only the first vector reports (thrust :1974-1987)
+      if (batch_pos_ != 0) return 0.0;
+      std::vector<double> v(batch_->nstates);
+      flush(); ck(b200sv_norm(batch_->h, v.data()));
+      double s = 0;
+      for (double x : v) s += x;
+      return s;
+    }
+    double v; flush(); ck(b200sv_norm(Hs(), &v)); return v;
+  }
   double norm(const uint_t qubit, const cvector_t<double> &mat) const { return norm(reg_t({qubit}), mat); }
   double norm(const reg_t &qubits, const cvector_t<double> &mat) const {
     double v;
-    flush(); ck(b200sv_norm_matrix(h_, qubits.data(), (int)qubits.size(), (const double *)mat.data(), &v));
+    flush(); ck(b200sv_norm_matrix(Hs(), qubits.data(), (int)qubits.size(), (const double *)mat.data(), &v));
     return v;
   }
   double norm_diagonal(const uint_t qubit, const cvector_t<double> &mat) const { return norm_diagonal(reg_t({qubit}), mat); }
@@ -278,74 +435,280 @@ public:
   }
   double expval_pauli(const reg_t &qubits, const std::string &pauli, const complex_t initial_phase = 1.0) const {
     double v;
-    flush(); ck(b200sv_expval_pauli(h_, qubits.data(), (int)qubits.size(), pauli.c_str(), initial_phase.real(),
-                           initial_phase.imag(), &v));
+    flush(); ck(b200sv_expval_pauli(Hs(), qubits.data(), (int)qubits.size(), pauli.c_str(), initial_phase.real(),
+                                    initial_phase.imag(), &v));
     return v;
   }
   double expval_pauli(const reg_t &qubits, const std::string &pauli, const QubitVectorB200<data_t> &pair_chunk,
                       const uint_t z_count, const uint_t z_count_pair, const complex_t initial_phase = 1.0) const {
     double v;
-    pair_chunk.sync_const();
-    flush(); ck(b200sv_expval_pauli_pair(h_, qubits.data(), (int)qubits.size(), pauli.c_str(), pair_chunk.device_data(), z_count,
-                                z_count_pair, initial_phase.real(), initial_phase.imag(), &v));
+    const_cast<QubitVectorB200<data_t> &>(pair_chunk).synchronize();
+    void *pair = pair_chunk.device_data();
+    flush(); ck(b200sv_expval_pauli_pair(Hs(), qubits.data(), (int)qubits.size(), pauli.c_str(), pair, z_count,
+                                         z_count_pair, initial_phase.real(), initial_phase.imag(), &v));
     return v;
   }
 
-  //---------------------------------------------------------------- batched-shot hooks (not enabled yet: CPU-class stubs)
-  virtual void apply_bfunc(const Operations::Op &) {}
-  virtual void set_conditional(int_t) {}
-  virtual void apply_roerror(const Operations::Op &, std::vector<RngEngine> &) {}
-  virtual void apply_batched_measure(const reg_t &, std::vector<RngEngine> &, const reg_t &, const reg_t &) {}
-  virtual void apply_batched_reset(const reg_t &, std::vector<RngEngine> &) {}
-  template <typename storage_t> void read_measured_data(storage_t &) {}
-  virtual int_t set_batched_system_conditional(int_t, reg_t &) { return -1; }
-  virtual void apply_batched_pauli_ops(const std::vector<std::vector<Operations::Op>> &) {}
-  void apply_batched_kraus(const reg_t &, const std::vector<cmatrix_t> &, std::vector<RngEngine> &) {}
-  void apply_batched_matrix(const reg_t &, const cvector_t<double> &, const uint_t, const uint_t) {}
-  void apply_batched_diagonal_matrix(const reg_t &, const cvector_t<double> &, const uint_t, const uint_t) {}
-  void batched_expval_pauli(std::vector<double> &, const reg_t &, const std::string &, bool, std::complex<double>, bool,
-                            const complex_t = 1.0) const {}
+  //---------------------------------------------------------------- batched-shot operations (first vector acts for the group)
+  // Sampled Pauli noise, one op list per shot (qubitvector_thrust.hpp:2892-2945): the Paulis become per-state
+  // codes of queued ops and ride on the same HBM passes as the surrounding gates.
+  virtual void apply_batched_pauli_ops(const std::vector<std::vector<Operations::Op>> &ops) {
+    if (!batch_ || idle()) return;
+    const size_t S = batch_->nstates;
+    std::vector<uint64_t> xm(S, 0), zm(S, 0);
+    uint64_t touched = 0;
+    for (size_t s = 0; s < ops.size() && s < S; s++) {
+      for (const auto &op : ops[s]) {
+        if (op.conditional && !batch_->cregs[s].check_conditional(op)) continue;
+        if (op.name == "x") xm[s] ^= 1ull << op.qubits[0];
+        else if (op.name == "z") zm[s] ^= 1ull << op.qubits[0];
+        else if (op.name == "y") { xm[s] ^= 1ull << op.qubits[0]; zm[s] ^= 1ull << op.qubits[0]; }
+        else if (op.name == "pauli") {
+          uint_t px, pz, ny, xmax;
+          std::tie(px, pz, ny, xmax) = pauli_masks_and_phase(op.qubits, op.string_params[0]);
+          xm[s] ^= px; zm[s] ^= pz;
+        }
+      }
+      touched |= xm[s] | zm[s];
+    }
+    if (!touched) return;
+    auto &Q = batch_->queue;
+    for (uint_t q = 0; q < num_qubits_; q++) {
+      if (!((touched >> q) & 1)) continue;
+      Q.kind.push_back(3);
+      Q.slot.push_back(Q.nslots);
+      Q.qubits.push_back(q); Q.qubits.push_back(0);
+      Q.mats.resize(Q.mats.size() + 32, 0.0);
+      const size_t off = Q.codes.size();
+      Q.codes.resize(off + S, 0);
+      for (size_t s = 0; s < S; s++) {
+        const int x = (int)((xm[s] >> q) & 1), z = (int)((zm[s] >> q) & 1);
+        Q.codes[off + s] = (uint8_t)(x ? (z ? 2 : 1) : (z ? 3 : 0));
+      }
+      Q.nslots++;
+    }
+    if (!queue_enabled() || Q.kind.size() >= 2048) Q.flush(batch_->h);
+  }
+  // apply_batched_measure (qubitvector_thrust.hpp:2251-2330): r = rng[s].rand(); outcome = first i with
+  // r < cumulative probability; collapse + renormalise; store bits.
+  virtual void apply_batched_measure(const reg_t &qubits, std::vector<RngEngine> &rng, const reg_t &cmemory,
+                                     const reg_t &cregs) {
+    if (!batch_ || idle()) return;
+    measure_impl(qubits, rng, &cmemory, &cregs, false);
+  }
+  // apply_batched_reset (qubitvector_thrust.hpp:2386-2460): measure without storing, then flip back to |0>
+  virtual void apply_batched_reset(const reg_t &qubits, std::vector<RngEngine> &rng) {
+    if (!batch_ || idle()) return;
+    measure_impl(qubits, rng, nullptr, nullptr, true);
+  }
+  // apply_batched_kraus (qubitvector_thrust.hpp:3096-3177): per shot, r = rng.rand(); accumulate
+  // p_j = ||K_j psi||^2 until it exceeds r; apply K_j / sqrt(p_j).
+  void apply_batched_kraus(const reg_t &qubits, const std::vector<cmatrix_t> &kmats, std::vector<RngEngine> &rng) {
+    if (!batch_ || idle()) return;
+    const size_t S = batch_->nstates;
+    std::vector<uint8_t> active = take_conditional();
+    batch_->queue.flush(batch_->h);
+    std::vector<double> r(S), accum(S, 0.0), p(S);
+    std::vector<int> chosen(S, -1);
+    for (size_t s = 0; s < S; s++) r[s] = rng[s].rand(0., 1.);
+    for (size_t j = 0; j < kmats.size(); j++) {
+      cvector_t<double> vmat = Utils::vectorize_matrix(kmats[j]);
+      const bool last = j + 1 == kmats.size();
+      if (!last) ck(b200sv_norm_matrix(batch_->h, qubits.data(), (int)qubits.size(), (const double *)vmat.data(), p.data()));
+      for (size_t s = 0; s < S; s++) {
+        if (!active[s] || chosen[s] >= 0) continue;
+        const double pj = last ? 1.0 - accum[s] : p[s];
+        accum[s] += pj;
+        if (last || accum[s] > r[s]) {
+          chosen[s] = (int)j;
+          const double renorm = 1.0 / std::sqrt(pj);
+          cvector_t<double> scaled = vmat;
+          for (auto &x : scaled) x *= renorm;
+          ck(b200sv_apply_matrix(state_view(s), qubits.data(), (int)qubits.size(), (const double *)scaled.data()));
+        }
+      }
+    }
+  }
+  // per-parameter matrices (runtime parameter binding): apply_batched_matrix (qubitvector_thrust.hpp:1578-1611)
+  void apply_batched_matrix(const reg_t &qubits, const cvector_t<double> &mat, const uint_t num_matrices,
+                            const uint_t num_shots_per_matrix) {
+    if (!batch_ || idle()) return;
+    batch_->queue.flush(batch_->h);
+    const size_t msize = 1ull << (2 * qubits.size());
+    for (uint_t m = 0; m < num_matrices; m++) {
+      b200sv_handle v = nullptr;
+      ck(b200sv_create_view(&v, batch_->h, (int64_t)(m * num_shots_per_matrix), (int64_t)num_shots_per_matrix));
+      const int rc = b200sv_apply_matrix(v, qubits.data(), (int)qubits.size(), (const double *)(mat.data() + m * msize));
+      b200sv_destroy(v);
+      ck(rc);
+    }
+  }
+  void apply_batched_diagonal_matrix(const reg_t &qubits, const cvector_t<double> &mat, const uint_t num_matrices,
+                                     const uint_t num_shots_per_matrix) {
+    if (!batch_ || idle()) return;
+    batch_->queue.flush(batch_->h);
+    const size_t msize = 1ull << qubits.size();
+    for (uint_t m = 0; m < num_matrices; m++) {
+      b200sv_handle v = nullptr;
+      ck(b200sv_create_view(&v, batch_->h, (int64_t)(m * num_shots_per_matrix), (int64_t)num_shots_per_matrix));
+      const int rc = b200sv_apply_diagonal(v, qubits.data(), (int)qubits.size(), (const double *)(mat.data() + m * msize));
+      b200sv_destroy(v);
+      ck(rc);
+    }
+  }
+  // batched_expval_pauli (qubitvector_thrust.hpp:2683-2713; batched_expval_*_func thrust_kernels.hpp:2472-2600):
+  // val[s] += Re(param) * <P>_s  (and val[2s+1] += Im(param) * <P>_s when the variance is requested)
+  void batched_expval_pauli(std::vector<double> &val, const reg_t &qubits, const std::string &pauli, bool variance,
+                            std::complex<double> param, bool /*last*/, const complex_t initial_phase = 1.0) const {
+    if (batch_ && batch_->on && batch_pos_ != 0) return;
+    const size_t S = (batch_ && batch_->on) ? batch_->nstates : 1;
+    if (val.empty()) val.assign(variance ? 2 * S : S, 0.0);
+    std::vector<double> e(S);
+    flush();
+    ck(b200sv_expval_pauli((batch_ && batch_->on) ? batch_->h : Hs(), qubits.data(), (int)qubits.size(), pauli.c_str(),
+                           initial_phase.real(), initial_phase.imag(), e.data()));
+    for (size_t s = 0; s < S; s++) {
+      if (variance) { val[2 * s] += param.real() * e[s]; val[2 * s + 1] += param.imag() * e[s]; }
+      else val[s] += param.real() * e[s];
+    }
+  }
 
-  //---------------------------------------------------------------- gate queue (tile-blocked multi-gate passes)
-  // Dense 1-/2-qubit gates are queued and flushed through b200sv_apply_gate_sequence, which packs them
-  // into as few HBM passes as possible; every other method flushes first, so the observable semantics
-  // are those of immediate application (cf. the reference's blocked-gate queue,
-  // qubitvector_thrust.hpp:1102-1111,1511-1512).  Disable with B200SV_GATE_QUEUE=0.
+  //---------------------------------------------------------------- gate queue
   static bool queue_enabled() {
     static const bool on = [] { const char *e = getenv("B200SV_GATE_QUEUE"); return !(e && e[0] == '0'); }();
     return on;
   }
   void flush() const {
-    if (q_nq_.empty()) return;
-    const int ng = (int)q_nq_.size();
-    const int rc = b200sv_apply_gate_sequence(h_, ng, q_nq_.data(), q_qubits_.data(), q_mats_.data(), nullptr);
-    q_nq_.clear(); q_qubits_.clear(); q_mats_.clear();
-    ck(rc);
+    if (batch_) batch_->queue.flush(batch_->h);
+    else if (h_) queue_.flush(h_);
   }
 
 protected:
-  bool enqueue(const reg_t &qubits, const cvector_t<double> &mat) {
-    if (!queue_enabled() || qubits.size() < 1 || qubits.size() > 2 || mat.size() != (1ull << (2 * qubits.size())))
-      return false;
-    q_nq_.push_back((int)qubits.size());
-    q_qubits_.push_back(qubits[0]);
-    q_qubits_.push_back(qubits.size() == 2 ? qubits[1] : 0);
-    const size_t off = q_mats_.size();
-    q_mats_.resize(off + 32, 0.0);
-    std::memcpy(&q_mats_[off], mat.data(), mat.size() * sizeof(std::complex<double>));
-    if (q_nq_.size() >= 4096) flush();
+  static void ck(int rc) { b200detail::ck(rc); }
+  // handle the next call acts on: the container (batched, first vector), this vector's state view, or its own handle
+  b200sv_handle H() const { return batch_ ? (batch_->on ? batch_->h : state_view(batch_pos_)) : h_; }
+  // handle for operations that always concern THIS vector's state only (data access, reductions)
+  b200sv_handle Hs() const { return batch_ ? state_view(batch_pos_) : h_; }
+  bool idle() const { return batch_ && batch_->on && batch_pos_ != 0; }
+  bool batch_queueing() const { return batch_ && batch_->on && batch_->cond_reg < 0 && queue_enabled(); }
+  b200sv_handle state_view(size_t s) const {
+    if (s == batch_pos_) {
+      if (!view_) ck(b200sv_create_view(&view_, batch_->h, (int64_t)s, 1));
+      return view_;
+    }
+    if (tmp_view_ && tmp_view_state_ != s) { b200sv_destroy(tmp_view_); tmp_view_ = nullptr; }
+    if (!tmp_view_) { ck(b200sv_create_view(&tmp_view_, batch_->h, (int64_t)s, 1)); tmp_view_state_ = s; }
+    return tmp_view_;
+  }
+  // one-shot conditional (chunk_container.hpp:416-420): which states execute the next batched op
+  std::vector<uint8_t> take_conditional() {
+    const size_t S = batch_->nstates;
+    std::vector<uint8_t> active(S, 1);
+    if (batch_->cond_reg >= 0) {
+      for (size_t s = 0; s < S; s++) {
+        const auto &reg = batch_->cregs[s].creg_register();
+        active[s] = reg.size() > (size_t)batch_->cond_reg && reg[reg.size() - batch_->cond_reg - 1] == '1';
+      }
+      batch_->cond_reg = -1;
+    }
+    return active;
+  }
+  template <typename F> void for_states(F f) {
+    if (batch_->on) {
+      std::vector<uint8_t> active = take_conditional();
+      for (size_t s = 0; s < batch_->nstates; s++)
+        if (active[s]) f(s);
+    } else {
+      f(batch_pos_);
+    }
+  }
+  // run f on the handle(s) the call concerns, honouring the batched-mode contracts
+  template <typename F> void for_target(F f) {
+    if (!batch_) { flush(); f(h_); return; }
+    if (!batch_->on) { batch_->queue.flush(batch_->h); f(state_view(batch_pos_)); return; }
+    if (batch_pos_ != 0) return;
+    batch_->queue.flush(batch_->h);
+    if (batch_->cond_reg < 0) { f(batch_->h); return; }
+    std::vector<uint8_t> active = take_conditional();
+    for (size_t s = 0; s < batch_->nstates; s++)
+      if (active[s]) f(state_view(s));
+  }
+  bool enqueue(const reg_t &qubits, const std::complex<double> *mat, size_t mat_size) {
+    if (!queue_enabled() || qubits.size() < 1 || qubits.size() > 2 || mat_size != (1ull << (2 * qubits.size()))) return false;
+    if (batch_) {
+      if (!batch_->on || batch_->cond_reg >= 0) return false;
+      batch_->queue.push_dense(qubits.data(), (int)qubits.size(), mat);
+      if (batch_->queue.kind.size() >= 2048) batch_->queue.flush(batch_->h);
+      return true;
+    }
+    queue_.push_dense(qubits.data(), (int)qubits.size(), mat);
+    if (queue_.kind.size() >= 4096) queue_.flush(h_);
     return true;
   }
-  mutable std::vector<int> q_nq_;
-  mutable std::vector<uint64_t> q_qubits_;
-  mutable std::vector<double> q_mats_;
-
-  static void ck(int rc) {
-    if (rc) throw std::runtime_error(std::string("b200sv: ") + b200sv_last_error());
+  void drop_queue() {
+    if (!batch_) { queue_.clear(); return; }
+    if (batch_->on && batch_pos_ == 0) batch_->queue.clear();
+    else batch_->queue.flush(batch_->h);
   }
-  void sync_const() const { if (h_) { flush(); ck(b200sv_synchronize(h_)); } }
+  void upload_all(const std::complex<data_t> *data) {
+    flush();
+    if (batch_ && batch_->on) {  // set_statevec in batched mode: every shot starts from the same vector
+      if (batch_pos_ != 0) return;
+      for (size_t s = 0; s < batch_->nstates; s++) ck(b200sv_upload(batch_->h, data, s << num_qubits_, data_size_));
+      return;
+    }
+    ck(b200sv_upload(Hs(), data, 0, data_size_));
+  }
+  void read_creg(ClassicalRegister &creg) {
+    if (!batch_) return;
+    creg.creg_memory() = batch_->cregs[batch_pos_].creg_memory();
+    creg.creg_register() = batch_->cregs[batch_pos_].creg_register();
+  }
+  template <typename T> void read_creg(T &) {}
+  void measure_impl(const reg_t &qubits, std::vector<RngEngine> &rng, const reg_t *cmemory, const reg_t *cregs, bool reset) {
+    const size_t S = batch_->nstates, DIM = 1ull << qubits.size();
+    std::vector<uint8_t> active = take_conditional();
+    batch_->queue.flush(batch_->h);
+    std::vector<double> probs(S * DIM), scale(S, 1.0);
+    ck(b200sv_probabilities(batch_->h, qubits.data(), (int)qubits.size(), probs.data()));
+    std::vector<uint64_t> outcome(S, 0), masks(4 * S, 0);
+    bool any_flip = false;
+    for (size_t s = 0; s < S; s++) {
+      if (!active[s]) continue;
+      const double r = rng[s].rand();
+      double total = 0, cum = 0;
+      for (size_t i = 0; i < DIM; i++) total += probs[s * DIM + i];
+      size_t o = DIM - 1;
+      for (size_t i = 0; i + 1 < DIM; i++) {
+        cum += probs[s * DIM + i] / total;
+        if (r < cum) { o = i; break; }
+      }
+      outcome[s] = o;
+      scale[s] = 1.0 / std::sqrt(probs[s * DIM + o]);
+      if (reset) {
+        uint64_t x = 0;
+        for (size_t j = 0; j < qubits.size(); j++)
+          if ((o >> j) & 1) x |= 1ull << qubits[j];
+        masks[4 * s] = x; masks[4 * s + 3] = x != 0;
+        any_flip |= x != 0;
+      } else {
+        reg_t bits(qubits.size());
+        for (size_t j = 0; j < qubits.size(); j++) bits[j] = (o >> j) & 1;
+        batch_->cregs[s].store_measure(bits, *cmemory, *cregs);
+      }
+    }
+    ck(b200sv_collapse(batch_->h, qubits.data(), (int)qubits.size(), outcome.data(), scale.data(), active.data()));
+    if (reset && any_flip) ck(b200sv_apply_batched_pauli(batch_->h, masks.data()));
+  }
+  void drop_batch() {
+    if (view_) { b200sv_destroy(view_); view_ = nullptr; }
+    if (tmp_view_) { b200sv_destroy(tmp_view_); tmp_view_ = nullptr; }
+    batch_.reset();
+    batch_pos_ = 0;
+  }
   void release() {
-    q_nq_.clear(); q_qubits_.clear(); q_mats_.clear();
+    queue_.clear();
+    drop_batch();
     if (h_) { b200sv_destroy(h_); h_ = nullptr; }
   }
   b200sv_handle h_ = nullptr;
@@ -355,6 +718,11 @@ protected:
   uint_t omp_threads_ = 1, omp_threshold_ = 14;
   int sample_measure_index_size_ = 10;
   double json_chop_threshold_ = 0;
+  mutable b200detail::OpQueue queue_;
+  std::shared_ptr<b200detail::Batch> batch_;
+  size_t batch_pos_ = 0;
+  mutable b200sv_handle view_ = nullptr, tmp_view_ = nullptr;
+  mutable size_t tmp_view_state_ = 0;
 };
 
 }  // namespace QV

@@ -66,6 +66,8 @@ def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, m
             c.gate(op[1], [int(q) for q in op[2]], [float(p) for p in op[3]], [], -1, None, op[1])
         elif op[0] == "measure":
             c.measure([int(q) for q in op[1]], [int(q) for q in op[2]], [])
+        elif op[0] == "kraus":
+            c.kraus([int(q) for q in op[1]], [np.ascontiguousarray(k, dtype=np.complex128) for k in op[2]], -1)
         elif op[0] == "reset":
             c.reset([int(q) for q in op[1]], -1)
         else:
@@ -82,7 +84,8 @@ def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, m
 
 
 def run_circuit(n, ops, device="GPU", shots=0, seed=1234, threads=0, fusion=True, fusion_max_qubit=5,
-                fusion_threshold=14, precision="double", blocking_qubits=None, noise_model=None, **circ_kw):
+                fusion_threshold=14, precision="double", blocking_qubits=None, noise_model=None,
+                batched_shots_gpu=False, batched_shots_gpu_max_qubits=16, **circ_kw):
     """Runs through Controller::execute (src/controllers/aer_controller.hpp:458); returns experiment 0's dict."""
     cw = load()
     c = build_circuit(cw, n, ops, shots, seed, **circ_kw)
@@ -102,6 +105,9 @@ def run_circuit(n, ops, device="GPU", shots=0, seed=1234, threads=0, fusion=True
     if blocking_qubits is not None:
         cfg.blocking_enable = True
         cfg.blocking_qubits = int(blocking_qubits)
+    if batched_shots_gpu:
+        cfg.batched_shots_gpu = True
+        cfg.batched_shots_gpu_max_qubits = int(batched_shots_gpu_max_qubits)
     out = cw.aer_controller_execute().execute([c], noise_model, cfg)
     if not out.get("success", False):
         raise RuntimeError("Aer controller failed: %s" % out.get("status"))

@@ -473,6 +473,30 @@ int b200sv_apply_batched_pauli(b200sv_handle h, const uint64_t *masks4) {
   return guard([&] { select(H); launch_batched_pauli(*H, masks4); });
 }
 
+int b200sv_collapse(b200sv_handle h, const uint64_t *qubits, int k, const uint64_t *outcomes, const double *scales,
+                    const uint8_t *active) {
+  return guard([&] {
+    select(H);
+    auto q = checked_qubits(*H, qubits, k);
+    if (!outcomes || !scales || !active) throw Error("collapse: null argument");
+    launch_collapse(*H, q.data(), k, outcomes, scales, active);
+  });
+}
+
+int b200sv_create_view(b200sv_handle *out, b200sv_handle parent, int64_t first_state, int64_t num_states) {
+  return guard([&] {
+    State *P = (State *)parent;
+    select(P);
+    if (first_state < 0 || num_states < 1 || first_state + num_states > P->nstates) throw Error("create_view: state range out of bounds");
+    State *v = new State();
+    v->device = P->device; v->nq = P->nq; v->nstates = num_states; v->precision = P->precision;
+    v->global_nq = P->nq; v->num_sms = P->num_sms;
+    v->data = (char *)P->data + ((uint64_t)first_state << P->nq) * P->amp_bytes();
+    v->stream = P->stream;  // same stream: ordered with the parent's work
+    *out = (b200sv_handle)v;
+  });
+}
+
 // ------------------------------------------------------------------ reductions
 int b200sv_norm(b200sv_handle h, double *out) { return guard([&] { select(H); reduce_norm(*H, out); }); }
 

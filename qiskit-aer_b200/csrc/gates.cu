@@ -485,6 +485,55 @@ void launch_batched_pauli(State &s, const uint64_t *masks4_host) {
   B200_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------ per-state collapse (batched measure / reset)
+struct CollapseParams {
+  int nq, k;
+  uint8_t q[32];
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+collapse_kernel(cx<T> *__restrict__ psi, const __grid_constant__ CollapseParams p, const uint64_t *__restrict__ outcome,
+                const double *__restrict__ scale, const uint8_t *__restrict__ active) {
+  const uint64_t s = blockIdx.y;
+  if (!active[s]) return;
+  const uint64_t want = outcome[s];
+  const T sc = (T)scale[s];
+  cx<T> *st = psi + (s << p.nq);
+  const uint64_t n = 1ull << p.nq, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint64_t m = 0;
+    for (int j = 0; j < p.k; j++) m |= ((i >> p.q[j]) & 1ull) << j;
+    cx<T> v = st[i];
+    st[i] = m == want ? mk<T>(v.x * sc, v.y * sc) : mk<T>(0, 0);
+  }
+}
+void launch_collapse(State &s, const int *qubits, int k, const uint64_t *outcomes, const double *scales,
+                     const uint8_t *active) {
+  if (k > 32) throw Error("collapse: too many qubits");
+  if (s.nstates > 65535) throw Error("collapse: more than 65535 states per container");
+  const size_t S = (size_t)s.nstates;
+  const size_t b_out = 0, b_sc = S * 8, b_act = 2 * S * 8, total = 2 * S * 8 + ((S + 15) & ~(size_t)15);
+  char *hm = (char *)s.ensure_pinned(total);
+  char *dm = (char *)s.ensure_scratch(total);
+  B200_CUDA(cudaStreamSynchronize(s.stream));
+  memcpy(hm + b_out, outcomes, S * 8);
+  memcpy(hm + b_sc, scales, S * 8);
+  memcpy(hm + b_act, active, S);
+  B200_CUDA(cudaMemcpyAsync(dm, hm, total, cudaMemcpyHostToDevice, s.stream));
+  CollapseParams p;
+  p.nq = s.nq; p.k = k;
+  for (int j = 0; j < k; j++) p.q[j] = (uint8_t)qubits[j];
+  int gx = (int)std::min<uint64_t>((s.amps_per_state() + 255) / 256, std::max<uint64_t>(1, (uint64_t)s.num_sms * 16 / S));
+  dim3 grid(std::max(gx, 1), (unsigned)S);
+  if (s.precision == B200SV_F64)
+    collapse_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, p, (const uint64_t *)(dm + b_out),
+                                                        (const double *)(dm + b_sc), (const uint8_t *)(dm + b_act));
+  else
+    collapse_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, p, (const uint64_t *)(dm + b_out),
+                                                       (const double *)(dm + b_sc), (const uint8_t *)(dm + b_act));
+  B200_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------ init
 template <typename T> __global__ void set_ket0_kernel(cx<T> *psi, int nq, int64_t nstates) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -32,11 +32,8 @@
 
 namespace b200sv {
 
-constexpr int kTB = 12;               // tile bits
-constexpr int kTileAmps = 1 << kTB;
-constexpr int kTileThreads = 256;
-constexpr int kLoBits = 8;            // tile-local bits covered by the thread id
-constexpr int kHiCount = kTileAmps / kTileThreads;  // staging iterations per thread
+constexpr int kMaxTB = 12;            // tile bits: 12 (64 KiB, 256 threads, 2 CTAs/SM) or 11 (32 KiB, 128 threads, 4 CTAs/SM)
+constexpr int kHiCount = 16;          // staging iterations per thread = 2^TB / threads (one 16-amp group per thread)
 constexpr int kRoundBits = 4;
 constexpr int kMaxRounds = 24;
 constexpr int kMaxTileGates = 16;   // == kMaxRounds: worst case one gate per round
@@ -48,7 +45,7 @@ __host__ __device__ constexpr int swz_vec(int u) {
 }
 __host__ __device__ inline uint32_t phys_slot(uint32_t j) {
   uint32_t s = 0;
-  for (int u = 3; u < kTB; u++)
+  for (int u = 3; u < kMaxTB; u++)
     if ((j >> u) & 1u) s ^= (uint32_t)swz_vec(u);
   return j ^ s;
 }
@@ -64,7 +61,7 @@ struct TileRound {
 struct TilePassParams {
   double2 mats[kMaxTileGates][16];  // 2q: row-major 4x4 with matrix bit0 <-> lower round bit; 1q: first 4 entries
   uint64_t goff_hi[kHiCount];       // global offset of tile-local bits kLoBits..11 (index m = j >> kLoBits)
-  uint64_t goff_lo[kLoBits];        // global offset of tile-local bit u < kLoBits
+  uint64_t goff_lo[8];              // global offset of tile-local bit u < kLoBits
   uint64_t ntiles;
   uint16_t soff_hi[kHiCount];       // phys(m << kLoBits)
   InsertList ins;                   // sorted tile bits (global positions)
@@ -142,8 +139,10 @@ __device__ __forceinline__ void apply_pauli_reg(double2 (&a)[16], int code) {
   }
 }
 
-__global__ void __launch_bounds__(kTileThreads, 2)
+template <int TB>
+__global__ void __launch_bounds__(1 << (TB - 4), TB == 12 ? 2 : 4)
 tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassParams p) {
+  constexpr int kLoBits = TB - 4;  // tile-local bits covered by the thread id (= group id bits)
   extern __shared__ __align__(16) double2 tile[];
   const int tid = threadIdx.x;
   uint64_t glo = 0;
@@ -165,7 +164,7 @@ tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
         const int g = tid;
         uint32_t base = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < kLoBits; i++)
           if ((g >> i) & 1) base ^= R.gbit[i];
         double2 a[16];
 #pragma unroll
@@ -235,7 +234,7 @@ static bool pick_lane_positions(const std::vector<int> &free_pos, int out[3]) {
   return false;
 }
 
-static void build_round(TileRound &R, const std::vector<int> &round_pos /*tile-local, <=4*/) {
+static void build_round(TileRound &R, const std::vector<int> &round_pos /*tile-local, <=4*/, int kTB) {
   // pad the round to 4 positions with unused tile positions (highest first)
   std::vector<int> pos = round_pos;
   for (int u = kTB - 1; (int)pos.size() < kRoundBits && u >= 0; u--)
@@ -255,7 +254,7 @@ static void build_round(TileRound &R, const std::vector<int> &round_pos /*tile-l
   std::vector<int> tpos(lane, lane + 3);
   for (int u : free_pos)
     if (u != lane[0] && u != lane[1] && u != lane[2]) tpos.push_back(u);
-  for (int i = 0; i < 8; i++) R.gbit[i] = (uint16_t)phys_slot(1u << tpos[i]);
+  for (int i = 0; i < kTB - 4; i++) R.gbit[i] = (uint16_t)phys_slot(1u << tpos[i]);
   R.ngates = 0;
   // stash sorted positions in eoff order: callers need pos -> round-bit index
   (void)pos;
@@ -269,7 +268,8 @@ static int round_bit_of(const std::vector<int> &sorted_pos, int tile_pos) {
 
 // One pass: gates[sel] all fit the tile; tile_bits sorted global positions (kTB of them).
 static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::vector<int> &sel,
-                          const std::vector<int> &tile_bits, const uint8_t *dev_codes) {
+                          const std::vector<int> &tile_bits, const uint8_t *dev_codes, int kTB) {
+  const int kLoBits = kTB - 4;
   static thread_local TilePassParams p;
   p.ntiles = s.total_amps() >> kTB;
   p.codes = dev_codes;
@@ -310,7 +310,7 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
     for (int q = 0; q < 64; q++)
       if ((rq >> q) & 1) rpos.push_back(tile_pos(q));
     TileRound &R = p.rounds[p.nrounds++];
-    build_round(R, rpos);
+    build_round(R, rpos, kTB);
     // recompute the padded+sorted position list exactly as build_round did
     std::vector<int> pos = rpos;
     for (int u = kTB - 1; (int)pos.size() < kRoundBits && u >= 0; u--)
@@ -349,11 +349,14 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
   }
   static bool attr_set = false;
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileAmps * 16));
+    B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 12)));
+    B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 11)));
     attr_set = true;
   }
-  const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms * 2);
-  tile_pass_kernel<<<grid, kTileThreads, kTileAmps * 16, s.stream>>>((double2 *)s.data, p);
+  const int per_sm = kTB == 12 ? 2 : 4;
+  const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms * per_sm);
+  if (kTB == 12) tile_pass_kernel<12><<<grid, 256, 16 << 12, s.stream>>>((double2 *)s.data, p);
+  else tile_pass_kernel<11><<<grid, 128, 16 << 11, s.stream>>>((double2 *)s.data, p);
   B200_CUDA(cudaGetLastError());
 }
 
@@ -381,6 +384,9 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
       any_pauli = true;
     }
   }
+  // B200SV_TILE_BITS = 11 | 12 selects the tile size (default 12)
+  static const int env_tb = [] { const char *e = getenv("B200SV_TILE_BITS"); return e ? atoi(e) : 0; }();
+  const int kTB = env_tb == 11 ? 11 : 12;
   const bool tiled = s.precision == B200SV_F64 && s.nq >= kTB;
   if (!tiled) {  // small or single-precision states: one streaming pass per op
     for (auto &g : gates) {
@@ -435,7 +441,7 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
     std::vector<int> tile_bits;
     for (int q = 0; q < 64; q++)
       if ((Q >> q) & 1) tile_bits.push_back(q);
-    run_tile_pass(s, gates, sel, tile_bits, dev_codes);
+    run_tile_pass(s, gates, sel, tile_bits, dev_codes, kTB);
     passes++;
     rem.swap(rest);
   }

@@ -100,3 +100,55 @@ def test_single_precision_through_controller():
     gpu = be.run_circuit(n, ops, device="GPU", **kw)
     cpu = be.run_circuit(n, ops, device="CPU", **kw)
     assert opgen.fidelity_gap(np.asarray(cpu["data"]["sv"]), np.asarray(gpu["data"]["sv"])) < 1e-5
+
+
+def _freq(res, n, shots):
+    return _counts(res, n) / float(shots)
+
+
+def test_batched_shots_gpu_option_noisy_pauli_circuit():
+    """`batched_shots_gpu=True`: BatchShotsExecutor (batch_shots_executor.hpp:317-603) drives ONE container of
+    `shots` states: gates in one launch for all shots, sampled Pauli noise as per-state codes on the tile
+    passes, batched measure, host-side cregs.  The batched path draws differently from the per-shot path
+    (rng.rand() thresholds, qubitvector_thrust.hpp:2296-2300), so parity is statistical."""
+    from qiskit_aer_b200 import circuits, noise
+    be = _backend()
+    n, shots = 12, 3000
+    # GHZ-like circuit + a few rotations: peaked output distribution
+    ops = [("gate", "h", [0], [])] + [("gate", "cx", [q, q + 1], []) for q in range(n - 1)]
+    ops += [("gate", "rz", [q], [0.3 * q]) for q in range(n)] + [("gate", "sx", [n - 1], []), ("gate", "sx", [n - 1], [])]
+    nm = noise.noise_model_dict(0.01, 0.03)
+    obs = [([0, 1], "ZZ"), ([0, n - 2], "ZZ"), ([3], "Z")]
+    kw = dict(shots=shots, seed=5, fusion=False, noise_model=nm, expvals=obs)
+    bat = be.run_circuit(n, ops, device="GPU", batched_shots_gpu=True, **kw)
+    ref = be.run_circuit(n, ops, device="CPU", **kw)
+    assert bat["metadata"].get("batched_shots_optimization") is True
+    fb, fr = _freq(bat, n, shots), _freq(ref, n, shots)
+    # total variation distance between two 3000-shot samples of the same distribution stays small
+    assert 0.5 * np.abs(fb - fr).sum() < 0.12
+    for i in range(len(obs)):
+        assert abs(bat["data"]["ev%d" % i] - ref["data"]["ev%d" % i]) < 0.08
+    ideal = be.run_circuit(n, ops, device="CPU", shots=shots, seed=5, fusion=False, expvals=obs)
+    assert abs(ideal["data"]["ev0"] - bat["data"]["ev0"]) > 0.02  # the noise is really applied
+
+
+def test_batched_shots_mid_circuit_measure_reset_and_kraus():
+    from qiskit_aer_b200 import circuits
+    be = _backend()
+    n, shots = 6, 4000
+    g = 0.3  # amplitude damping Kraus pair on qubit 2
+    K0 = np.array([[1, 0], [0, np.sqrt(1 - g)]], dtype=complex)
+    K1 = np.array([[0, np.sqrt(g)], [0, 0]], dtype=complex)
+    ops = [("gate", "h", [q], []) for q in range(n)] + [("gate", "cx", [0, 1], []), ("gate", "rx", [2], [1.1])]
+    ops += [("measure", [0], [0]), ("reset", [1]), ("gate", "h", [1], []), ("kraus", [2], [K0, K1]),
+            ("gate", "cx", [1, 3], []), ("gate", "ry", [4], [0.7])]
+    kw = dict(shots=shots, seed=9, fusion=False)
+    bat = be.run_circuit(n, ops, device="GPU", batched_shots_gpu=True, **kw)
+    ref = be.run_circuit(n, ops, device="CPU", **kw)
+    assert bat["metadata"].get("batched_shots_optimization") is True
+    fb, fr = _freq(bat, n, shots), _freq(ref, n, shots)
+    assert 0.5 * np.abs(fb - fr).sum() < 0.1
+    # marginal of the damped qubit: P(q2 = 1) agrees
+    idx = np.arange(1 << n)
+    p1b, p1r = fb[(idx >> 2) & 1 == 1].sum(), fr[(idx >> 2) & 1 == 1].sum()
+    assert abs(p1b - p1r) < 0.04

@@ -67,7 +67,7 @@ def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, m
         elif op[0] == "measure":
             c.measure([int(q) for q in op[1]], [int(q) for q in op[2]], [])
         elif op[0] == "kraus":
-            c.kraus([int(q) for q in op[1]], [np.ascontiguousarray(k, dtype=np.complex128) for k in op[2]], -1)
+            c.kraus([int(q) for q in op[1]], [np.ascontiguousarray(k, dtype=np.complex128) for k in op[2]], -1, None)
         elif op[0] == "reset":
             c.reset([int(q) for q in op[1]], -1)
         else:

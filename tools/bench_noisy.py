@@ -60,6 +60,15 @@ def main():
         dt = time.perf_counter() - t0
         out["aer_per_shot_on_b200"] = {"seconds": dt, "shots": a.aer_shots, "shots_per_s": a.aer_shots / dt,
                                        "expval": [float(r["data"]["ev%d" % i]) for i in range(len(obs))]}
+        # the reference's BatchShotsExecutor (batched_shots_gpu=True) driving the B200 container
+        bkw = dict(kw, batched_shots_gpu=True, batched_shots_gpu_max_qubits=max(n, 16))
+        aer_backend.run_circuit(n, ops, device="GPU", shots=64, **bkw)
+        t0 = time.perf_counter()
+        r = aer_backend.run_circuit(n, ops, device="GPU", shots=a.shots, **bkw)
+        dt = time.perf_counter() - t0
+        out["aer_batched_shots_gpu_on_b200"] = {"seconds": dt, "shots": a.shots, "shots_per_s": a.shots / dt,
+                                                "batched": r["metadata"].get("batched_shots_optimization"),
+                                                "expval": [float(r["data"]["ev%d" % i]) for i in range(len(obs))]}
         t0 = time.perf_counter()
         r = aer_backend.run_circuit(n, ops, device="CPU", shots=a.cpu_shots, **kw)
         dt = time.perf_counter() - t0

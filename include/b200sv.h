@@ -137,7 +137,8 @@ int b200sv_apply_op_sequence(b200sv_handle h, int nops, const int *kind, const u
 /* Per-state measurement collapse for batched containers (apply_batched_measure / apply_batched_reset,
  * qubitvector_thrust.hpp:2251-2460: check_measure_probability_func + reset_after_measure_func): for every
  * state s with active[s] != 0, amplitudes whose `qubits` bits differ from outcomes[s] are zeroed and the
- * rest are multiplied by scales[s] (= 1/sqrt(p_outcome)).  One launch for all states. */
+ * rest are multiplied by scales[s] (= 1/sqrt(p_outcome); scales[s] <= 0 means "normalise the survivor by its
+ * own modulus", for measurements of every qubit).  One launch for all states. */
 int b200sv_collapse(b200sv_handle h, const uint64_t *qubits, int k, const uint64_t *outcomes, const double *scales,
                     const uint8_t *active);
 /* A handle onto states [first_state, first_state + num_states) of a batched container, sharing its memory

@@ -669,22 +669,11 @@ protected:
     const size_t S = batch_->nstates, DIM = 1ull << qubits.size();
     std::vector<uint8_t> active = take_conditional();
     batch_->queue.flush(batch_->h);
-    std::vector<double> probs(S * DIM), scale(S, 1.0);
-    ck(b200sv_probabilities(batch_->h, qubits.data(), (int)qubits.size(), probs.data()));
+    std::vector<double> scale(S, 1.0);
     std::vector<uint64_t> outcome(S, 0), masks(4 * S, 0);
     bool any_flip = false;
-    for (size_t s = 0; s < S; s++) {
-      if (!active[s]) continue;
-      const double r = rng[s].rand();
-      double total = 0, cum = 0;
-      for (size_t i = 0; i < DIM; i++) total += probs[s * DIM + i];
-      size_t o = DIM - 1;
-      for (size_t i = 0; i + 1 < DIM; i++) {
-        cum += probs[s * DIM + i] / total;
-        if (r < cum) { o = i; break; }
-      }
+    auto record = [&](size_t s, size_t o) {
       outcome[s] = o;
-      scale[s] = 1.0 / std::sqrt(probs[s * DIM + o]);
       if (reset) {
         uint64_t x = 0;
         for (size_t j = 0; j < qubits.size(); j++)
@@ -695,6 +684,51 @@ protected:
         reg_t bits(qubits.size());
         for (size_t j = 0; j < qubits.size(); j++) bits[j] = (o >> j) & 1;
         batch_->cregs[s].store_measure(bits, *cmemory, *cregs);
+      }
+    };
+    bool all_in_order = qubits.size() == num_qubits_;
+    for (size_t j = 0; j < qubits.size() && all_in_order; j++) all_in_order = qubits[j] == j;
+    if (all_in_order && qubits.size() > 10) {
+      // every qubit, in order: "first outcome with r < cumulative probability" IS the sampler's definition,
+      // so draw through sample_measure (no 2^n-per-shot probability table)
+      std::vector<double> r(S, 0.0);
+      for (size_t s = 0; s < S; s++) if (active[s]) r[s] = rng[s].rand();
+      reg_t smp(S);
+      ck(b200sv_sample_measure(batch_->h, r.data(), 1, smp.data()));
+      for (size_t s = 0; s < S; s++) {
+        if (!active[s]) continue;
+        scale[s] = -1.0;  // normalise the surviving amplitude by its own modulus
+        record(s, smp[s]);
+      }
+    } else {
+      // marginal probabilities in slabs of states so that the table stays small
+      const size_t slab = std::max<size_t>(1, std::min<size_t>(S, ((size_t)32 << 20) / DIM));
+      std::vector<double> probs(slab * DIM);
+      for (size_t s0 = 0; s0 < S; s0 += slab) {
+        const size_t ns = std::min(slab, S - s0);
+        if (ns == S) {
+          ck(b200sv_probabilities(batch_->h, qubits.data(), (int)qubits.size(), probs.data()));
+        } else {
+          b200sv_handle v = nullptr;
+          ck(b200sv_create_view(&v, batch_->h, (int64_t)s0, (int64_t)ns));
+          const int rc = b200sv_probabilities(v, qubits.data(), (int)qubits.size(), probs.data());
+          b200sv_destroy(v);
+          ck(rc);
+        }
+        for (size_t i = 0; i < ns; i++) {
+          const size_t s = s0 + i;
+          if (!active[s]) continue;
+          const double r = rng[s].rand();
+          double total = 0, cum = 0;
+          for (size_t o = 0; o < DIM; o++) total += probs[i * DIM + o];
+          size_t pick = DIM - 1;
+          for (size_t o = 0; o + 1 < DIM; o++) {
+            cum += probs[i * DIM + o] / total;
+            if (r < cum) { pick = o; break; }
+          }
+          scale[s] = 1.0 / std::sqrt(probs[i * DIM + pick]);
+          record(s, pick);
+        }
       }
     }
     ck(b200sv_collapse(batch_->h, qubits.data(), (int)qubits.size(), outcome.data(), scale.data(), active.data()));

@@ -504,7 +504,11 @@ collapse_kernel(cx<T> *__restrict__ psi, const __grid_constant__ CollapseParams 
     uint64_t m = 0;
     for (int j = 0; j < p.k; j++) m |= ((i >> p.q[j]) & 1ull) << j;
     cx<T> v = st[i];
-    st[i] = m == want ? mk<T>(v.x * sc, v.y * sc) : mk<T>(0, 0);
+    if (m != want) { st[i] = mk<T>(0, 0); continue; }
+    if (sc > (T)0) { st[i] = mk<T>(v.x * sc, v.y * sc); continue; }
+    // scale <= 0: every qubit was measured, the single survivor is normalised by its own modulus
+    const T r = (T)1 / sqrt(v.x * v.x + v.y * v.y);
+    st[i] = mk<T>(v.x * r, v.y * r);
   }
 }
 void launch_collapse(State &s, const int *qubits, int k, const uint64_t *outcomes, const double *scales,

@@ -459,3 +459,34 @@ def test_concurrent_host_threads_on_different_handles():
         th.join()
     assert not errors, errors
     assert max(results) < 1e-12, results
+
+
+def test_full_size_qv33_round_trip_across_engines():
+    """BASELINE size (33 qubits, 128 GiB): forward through the tile-blocked gate queue, backward (inverse gates,
+    reverse order) through the dense per-gate kernels -> the register must return to |0...0>.  Size-independent
+    property, no second copy of the state needed; also exercises 64-bit indexing at full scale."""
+    import torch
+    free, total = torch.cuda.mem_get_info()
+    n = 33
+    if free < (16 << n) + (4 << 30):
+        pytest.skip("needs a 128 GiB state")
+    from qiskit_aer_b200 import circuits
+    ops = circuits.quantum_volume(n, 2, seed=5)
+    gpu = gpu_qv(n)
+    gates = [(op[1], opgen.colmajor(op[2])) for op in ops]
+    passes = gpu.apply_gate_sequence(gates)
+    assert passes < len(gates)
+    assert abs(gpu.norm() - 1.0) < 1e-12
+    p_top = gpu.probabilities([n - 1, 0])
+    assert abs(p_top.sum() - 1.0) < 1e-12
+    for op in reversed(ops):
+        gpu.apply_matrix(op[1], opgen.colmajor(np.asarray(op[2]).conj().T))
+    amp0 = gpu.vector(offset=0, count=1)[0]
+    assert abs(1.0 - amp0) < 1e-10
+    assert abs(gpu.norm() - 1.0) < 1e-12
+    # bit-exact permutation at the top of the index range
+    gpu.apply_mcx([n - 1])
+    assert abs(gpu.vector(offset=1 << (n - 1), count=1)[0] - amp0) == 0.0
+    s = gpu.sample_measure(np.array([0.5]))
+    assert int(s[0]) == 1 << (n - 1)
+    gpu.close()

@@ -82,6 +82,11 @@ int b200sv_zero(b200sv_handle h);                       /* zero() (qubitvector.h
  * (over the whole batch), in the handle's precision. */
 int b200sv_upload(b200sv_handle h, const void *host, uint64_t offset, uint64_t count);
 int b200sv_download(b200sv_handle h, void *host, uint64_t offset, uint64_t count);
+/* Density-matrix helper: the state is vec(rho) of a 2^m x 2^m matrix (index = row + col * 2^m,
+ * densitymatrix.hpp:292-343).  Copies the 2^m entries rho[i ^ xor_mask, i] to the host: xor_mask = 0 is the
+ * diagonal used by probability()/probabilities()/sample_measure (densitymatrix.hpp:590-593) and the other
+ * masks are the lines DensityMatrix::expval_pauli walks (:470-520). */
+int b200sv_download_line(b200sv_handle h, int row_bits, uint64_t xor_mask, void *host_out);
 /* initialize_component(qubits, state) (qubitvector.hpp:879-900) */
 int b200sv_initialize_component(b200sv_handle h, const uint64_t *qubits, int k, const double *state);
 /* checkpoint()/revert(keep)/inner_product() (qubitvector.hpp:995-1041) -- device-resident copy */

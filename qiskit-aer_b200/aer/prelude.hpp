@@ -5,9 +5,9 @@
 //   * AER_THRUST_SUPPORTED / AER_THRUST_GPU switch on the reference's own GPU branches
 //     (src/controllers/aer_controller.hpp:290-330,636-647; src/simulators/circuit_executor.hpp:340-380);
 //   * the reference's Thrust containers are kept out by pre-defining their include guards, and the class
-//     names those branches instantiate are aliased: QubitVectorThrust<T> -> QubitVectorB200<T> (ours);
-//     the density-matrix / unitary / superoperator "Thrust" names fall back to the reference CPU classes
-//     (out of scope for round 1).
+//     names those branches instantiate are aliased: QubitVectorThrust<T> -> QubitVectorB200<T> and
+//     DensityMatrixThrust<T> -> DensityMatrixB200<T> (ours); the unitary / superoperator "Thrust" names
+//     fall back to the reference CPU classes (out of scope).
 //
 // This is the build-time equivalent of the two-line edit shown in INTEGRATION.md section 2; no reference
 // file is modified or copied.
@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include "qubitvector_b200.hpp"
+#include "densitymatrix_b200.hpp"
 
 #define _qv_qubit_vector_thrust_hpp_
 #define _qv_density_matrix_thrust_hpp_
@@ -32,7 +33,7 @@
 namespace AER {
 namespace QV {
 template <typename T = double> using QubitVectorThrust = QubitVectorB200<T>;
-template <typename T = double> using DensityMatrixThrust = DensityMatrix<T>;
+template <typename T = double> using DensityMatrixThrust = DensityMatrixB200<T>;
 template <typename T = double> using UnitaryMatrixThrust = UnitaryMatrix<T>;
 template <typename T = double> using SuperoperatorThrust = Superoperator<T>;
 }  // namespace QV

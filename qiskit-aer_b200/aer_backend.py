@@ -51,7 +51,8 @@ def load():
     return _cw
 
 
-def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, measure=True, save_probs=None):
+def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, measure=True, save_probs=None,
+                  save_density_matrix=False):
     c = cw.AerCircuit()
     c.num_qubits = n
     c.num_memory = n if (shots and measure) else 0
@@ -78,6 +79,8 @@ def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, m
         c.save_state([int(q) for q in save_probs], "save_probabilities", "average", "probs")
     if save_statevector:
         c.save_state(list(range(n)), "save_statevector", "single", "sv")
+    if save_density_matrix:
+        c.save_state(list(range(n)), "save_density_matrix", "average", "dm")
     if shots and measure:
         c.measure(list(range(n)), list(range(n)), [])
     return c
@@ -85,12 +88,12 @@ def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, m
 
 def run_circuit(n, ops, device="GPU", shots=0, seed=1234, threads=0, fusion=True, fusion_max_qubit=5,
                 fusion_threshold=14, precision="double", blocking_qubits=None, noise_model=None,
-                batched_shots_gpu=False, batched_shots_gpu_max_qubits=16, **circ_kw):
+                batched_shots_gpu=False, batched_shots_gpu_max_qubits=16, method="statevector", **circ_kw):
     """Runs through Controller::execute (src/controllers/aer_controller.hpp:458); returns experiment 0's dict."""
     cw = load()
     c = build_circuit(cw, n, ops, shots, seed, **circ_kw)
     cfg = cw.AerConfig()
-    cfg.method = "statevector"
+    cfg.method = method
     cfg.device = device
     cfg.precision = precision
     cfg.n_qubits = n

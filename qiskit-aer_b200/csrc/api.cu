@@ -236,6 +236,15 @@ int b200sv_download(b200sv_handle h, void *host, uint64_t offset, uint64_t count
   });
 }
 
+int b200sv_download_line(b200sv_handle h, int row_bits, uint64_t xor_mask, void *host_out) {
+  return guard([&] {
+    select(H);
+    if (2 * row_bits != H->nq || H->nstates != 1) throw Error("download_line: the state is not a 2^m x 2^m matrix");
+    if (row_bits < 63 && (xor_mask >> row_bits)) throw Error("download_line: mask out of range");
+    launch_gather_line(*H, row_bits, xor_mask, host_out);
+  });
+}
+
 int b200sv_initialize_component(b200sv_handle h, const uint64_t *qubits, int k, const double *state) {
   return guard([&] {
     select(H);

@@ -108,6 +108,7 @@ void launch_pauli(State &s, uint64_t x_mask, uint64_t z_mask, int x_max, double 
 void launch_batched_pauli(State &s, const uint64_t *masks4_host);
 void launch_collapse(State &s, const int *qubits, int k, const uint64_t *outcomes, const double *scales,
                      const uint8_t *active);
+void launch_gather_line(State &s, int row_bits, uint64_t xor_mask, void *host_out);
 void launch_init(State &s, bool ket0);
 void launch_init_component(State &s, const int *qubits, int k, const double *state);
 void launch_pack_half(State &s, int q, int bit, uint64_t begin, uint64_t count, void *buf, bool unpack);

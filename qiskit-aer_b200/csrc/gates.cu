@@ -538,6 +538,27 @@ void launch_collapse(State &s, const int *qubits, int k, const uint64_t *outcome
   B200_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------ density-matrix line gather
+template <typename T>
+__global__ void __launch_bounds__(256) gather_line_kernel(const cx<T> *__restrict__ psi, cx<T> *__restrict__ out,
+                                                          int row_bits, uint64_t xor_mask) {
+  const uint64_t n = 1ull << row_bits, stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = psi[(i ^ xor_mask) + (i << row_bits)];
+}
+void launch_gather_line(State &s, int row_bits, uint64_t xor_mask, void *host_out) {
+  const size_t n = 1ull << row_bits, bytes = n * s.amp_bytes();
+  void *dm = s.ensure_scratch(bytes);
+  void *hm = s.ensure_pinned(bytes);
+  const int grid = grid_for(s, n, 256, 16);
+  if (s.precision == B200SV_F64) gather_line_kernel<double><<<grid, 256, 0, s.stream>>>((const double2 *)s.data, (double2 *)dm, row_bits, xor_mask);
+  else gather_line_kernel<float><<<grid, 256, 0, s.stream>>>((const float2 *)s.data, (float2 *)dm, row_bits, xor_mask);
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(hm, dm, bytes, cudaMemcpyDeviceToHost, s.stream));
+  B200_CUDA(cudaStreamSynchronize(s.stream));
+  memcpy(host_out, hm, bytes);
+}
+
 // ------------------------------------------------------------------ init
 template <typename T> __global__ void set_ket0_kernel(cx<T> *psi, int nq, int64_t nstates) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

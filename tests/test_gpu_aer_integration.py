@@ -152,3 +152,33 @@ def test_batched_shots_mid_circuit_measure_reset_and_kraus():
     idx = np.arange(1 << n)
     p1b, p1r = fb[(idx >> 2) & 1 == 1].sum(), fr[(idx >> 2) & 1 == 1].sum()
     assert abs(p1b - p1r) < 0.04
+
+
+def test_density_matrix_method_on_b200():
+    """method="density_matrix", device="GPU": DensityMatrix::State<DensityMatrixB200<double>>
+    (include/densitymatrix_b200.hpp) against the reference CPU DensityMatrix on the same noisy circuit:
+    rho itself, Pauli expectation values, probabilities and fixed-seed counts."""
+    from qiskit_aer_b200 import circuits, noise
+    be = _backend()
+    n, shots = 6, 2000
+    ops = circuits.random_noisy_circuit(n, 3, seed=4)
+    ops += [("gate", "ccx", [0, 1, 2], []), ("gate", "swap", [3, 4], []), ("gate", "y", [5], []),
+            ("gate", "cz", [1, 4], []), ("gate", "cp", [2, 5], [0.7]), ("gate", "cy", [0, 3], []),
+            ("reset", [2]), ("gate", "h", [2], []), ("gate", "t", [2], []), ("gate", "ecr", [1, 2], [])]
+    nm = noise.noise_model_dict(0.02, 0.05)
+    obs = [([0, 1], "ZZ"), ([2], "X"), ([3, 5], "XY"), ([4], "Z"), ([0, 2, 4], "YZX")]
+    kw = dict(shots=shots, seed=13, fusion=True, fusion_threshold=1, noise_model=nm, expvals=obs,
+              method="density_matrix", save_density_matrix=True)
+    gpu = be.run_circuit(n, ops, device="GPU", **kw)
+    cpu = be.run_circuit(n, ops, device="CPU", **kw)
+    assert gpu["metadata"]["device"] == "GPU" and gpu["metadata"]["method"] == "density_matrix"
+    rg, rc = np.asarray(gpu["data"]["dm"]), np.asarray(cpu["data"]["dm"])
+    assert np.max(np.abs(rg - rc)) < 1e-12
+    assert abs(np.trace(rg) - 1.0) < 1e-12
+    for i in range(len(obs)):
+        assert abs(gpu["data"]["ev%d" % i] - cpu["data"]["ev%d" % i]) < 1e-12
+    assert np.array_equal(_counts(gpu, n), _counts(cpu, n))
+    # fusion off: named-gate paths (apply_cnot / apply_x / apply_phase / apply_toffoli / apply_swap ...)
+    kw["fusion"] = False
+    gpu2 = be.run_circuit(n, ops, device="GPU", **kw)
+    assert np.max(np.abs(np.asarray(gpu2["data"]["dm"]) - rc)) < 1e-12

@@ -204,7 +204,7 @@ def b200_arm(args):
 
     n, name, ops, amps_written = workload(args, world)
     n_local = n - int(np.log2(world))
-    fused = fusion.fuse(ops, max_qubit=args.fusion_max_qubit)
+    fused = fusion.fuse(ops, max_qubit=args.fusion_max_qubit, max_diag_qubit=args.max_diag_qubit)
     if rank == 0:
         log("workload %s: %d gates -> %d fused passes, n_local=%d (%.1f GiB/GPU)"
             % (name, len(ops), len(fused), n_local, AMP_BYTES * 2.0 ** n_local / 2 ** 30))
@@ -349,7 +349,7 @@ def b200_arm(args):
                 qv.initialize()
                 executor.apply_ops_queued(qv, ops)
         else:
-            f = fusion.fuse(ops, max_qubit=args.fusion_max_qubit)
+            f = fusion.fuse(ops, max_qubit=args.fusion_max_qubit, max_diag_qubit=args.max_diag_qubit)
             h2d = sum(executor.op_h2d_bytes(op) for op in f)
             if runner is not None:
                 runner.initialize()
@@ -470,6 +470,7 @@ def main():
     ap.add_argument("--qubits", type=int, default=0, help="override the total qubit count (default 33 + log2 N)")
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--fusion-max-qubit", type=int, default=4)
+    ap.add_argument("--max-diag-qubit", type=int, default=16, help="widest fused diagonal block (table in L2 above 10)")
     ap.add_argument("--engine", default="tile", choices=["tile", "dense"],
                     help="tile: multi-gate shared-memory passes (default); dense: one fused dense block per pass")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],

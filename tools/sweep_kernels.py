@@ -64,7 +64,7 @@ def main():
         for pname, pf in places.items():
             qs = pf(k)
             timeit("dense_k%d_%s" % (k, pname), lambda: qv.apply_matrix(qs, U), full)
-    for k in (1, 3, 5, 8):
+    for k in (1, 3, 5, 8, 10, 12, 14, 16):
         d = np.exp(2j * np.pi * rng.random(1 << k))
         for pname in ("low", "high"):
             qs = places[pname](k)

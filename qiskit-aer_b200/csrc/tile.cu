@@ -68,6 +68,7 @@ struct TilePassParams {
   const uint8_t *codes;             // [slot][state] Pauli codes 0..3 = I,X,Y,Z (batched noisy shots), or null
   uint64_t nstates;
   int state_shift;                  // tile index >> state_shift = state (tile bits are all < num_qubits)
+  int stagger_cycles, num_sms;      // start-up phase offset between co-resident CTAs
   int nrounds;
   TileRound rounds[kMaxRounds];
 };
@@ -150,6 +151,15 @@ tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
   for (int u = 0; u < kLoBits; u++)
     if ((tid >> u) & 1) glo |= p.goff_lo[u];
   const uint32_t slo = phys_slot((uint32_t)tid);
+
+  // Phase stagger: CTAs that share an SM (blockIdx.x / num_sms = their resident slot) start a fraction of a
+  // tile period apart, so that one CTA's load/store phases overlap another's math instead of every CTA of the
+  // grid walking load -> compute -> store in lockstep (which costs t_mem + t_fp64 per pass, not the max).
+  if (p.stagger_cycles) {
+    const long long wait = (long long)p.stagger_cycles * (blockIdx.x / p.num_sms);
+    const long long t0 = clock64();
+    while (clock64() - t0 < wait) { }
+  }
 
   for (uint64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     double2 *gt = psi + (insert_zeros(t, p.ins) | glo);
@@ -354,6 +364,13 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
     attr_set = true;
   }
   const int per_sm = kTB == 12 ? 2 : 4;
+  {
+    static const int env_stagger = [] { const char *e = getenv("B200SV_TILE_STAGGER"); return e ? atoi(e) : -1; }();
+    // one tile period per CTA ~ FP64 time of its gates (16 DFMA/amp/gate at 64 DFMA/clk/SM, shared) + load/store
+    const int period = ndense * ((16 << kTB) / 64) * per_sm + 6000;
+    p.stagger_cycles = env_stagger >= 0 ? env_stagger : period / per_sm;
+    p.num_sms = s.num_sms;
+  }
   const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms * per_sm);
   if (kTB == 12) tile_pass_kernel<12><<<grid, 256, 16 << 12, s.stream>>>((double2 *)s.data, p);
   else tile_pass_kernel<11><<<grid, 128, 16 << 11, s.stream>>>((double2 *)s.data, p);

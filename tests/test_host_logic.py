@@ -1,0 +1,94 @@
+"""CPU tests of the host-side passes: the engine's fusion (role of src/transpile/fusion.hpp), the circuit
+generators, and the sharded swap planner's invariants (role of src/transpile/cacheblocking.hpp)."""
+import numpy as np
+import pytest
+
+import opgen
+from oracle.oracle import OracleQV
+
+
+def _run(ops, n, psi):
+    import qiskit_aer_b200  # noqa: F401
+    from qiskit_aer_b200 import executor
+    o = OracleQV(n)
+    o.set_state(psi)
+    executor.apply_ops(o, ops)
+    return o.vector()
+
+
+@pytest.mark.parametrize("max_qubit", [2, 3, 4, 5])
+@pytest.mark.parametrize("max_diag", [5, 10, 12])
+def test_fusion_is_equivalent(max_qubit, max_diag):
+    import qiskit_aer_b200  # noqa: F401
+    from qiskit_aer_b200 import circuits, fusion
+    rng = np.random.default_rng(max_qubit * 31 + max_diag)
+    for n, ops in ((9, circuits.quantum_volume(9, 5, 1)), (11, circuits.qft(11)),
+                   (8, circuits.random_noisy_circuit(8, 4, 2) + circuits.qft(8))):
+        psi = opgen.random_state(rng, n)
+        fused = fusion.fuse(ops, max_qubit=max_qubit, max_diag_qubit=max_diag)
+        assert len(fused) <= len(ops)
+        assert all(len(op[1]) <= (max(max_diag, max_qubit) if op[0] == "diagonal" else max_qubit) for op in fused)
+        assert opgen.fidelity_gap(_run(ops, n, psi), _run(fused, n, psi)) < 1e-12
+
+
+def test_fusion_respects_non_commuting_order():
+    """H on a qubit between two controlled phases must not be commuted past them."""
+    import qiskit_aer_b200  # noqa: F401
+    from qiskit_aer_b200 import fusion
+    ops = [("gate", "cp", [0, 1], [0.3]), ("gate", "h", [1], []), ("gate", "cp", [1, 2], [0.9]),
+           ("gate", "h", [0], []), ("gate", "cp", [0, 2], [1.7]), ("gate", "h", [2], []), ("gate", "cp", [0, 1], [0.2])]
+    rng = np.random.default_rng(0)
+    psi = opgen.random_state(rng, 3)
+    for mq in (1, 2, 3):
+        fused = fusion.fuse(ops, max_qubit=mq, max_diag_qubit=3)
+        assert opgen.fidelity_gap(_run(ops, 3, psi), _run(fused, 3, psi)) < 1e-13
+
+
+def test_amplitude_update_accounting():
+    import qiskit_aer_b200  # noqa: F401
+    from qiskit_aer_b200 import circuits
+    n = 10
+    assert circuits.amplitudes_written(circuits.quantum_volume(n, 3, 0), n) == 3 * (n // 2) << n
+    q = circuits.qft(4)
+    # 4 H (2^n each) + 6 cp (2^(n-2) each) + 2 swaps (2^(n-1) each)   -- BASELINE.md section 3
+    assert circuits.amplitudes_written(q, 4) == 4 * 16 + 6 * 4 + 2 * 8
+
+
+@pytest.mark.parametrize("world,n", [(2, 12), (4, 13), (8, 15)])
+def test_epoch_planner_invariants(world, n):
+    """Every gate is emitted exactly once, in an order consistent with its qubit dependencies, with all of its
+    non-diagonal qubits on local physical positions; swaps are (local, global-bit) pairs."""
+    import qiskit_aer_b200  # noqa: F401
+    from qiskit_aer_b200 import circuits, sharded
+    r = sharded.ShardedRunner.__new__(sharded.ShardedRunner)
+    r.n, r.world, r.gbits, r.rank, r.min_run_bits = n, world, int(np.log2(world)), 0, 6
+    r.nl = n - r.gbits
+    r.phys = list(range(n))
+    ops = circuits.quantum_volume(n, 8, seed=world) + circuits.qft(n)
+    plan = r.plan(ops)
+    phys = list(range(n))          # replay the map
+    emitted = []
+    for p in plan:
+        if p[0] == "swap":
+            lpos, gpos = p[1], p[2] + r.nl
+            assert 0 <= lpos < r.nl and r.nl <= gpos < n
+            inv = {pp: q for q, pp in enumerate(phys)}
+            a, b = inv[lpos], inv[gpos]
+            phys[a], phys[b] = gpos, lpos
+            continue
+        qs = p[1] if p[0] in ("unitary", "diagonal") else p[2]
+        inv = {pp: q for q, pp in enumerate(phys)}
+        logical = [inv[x] for x in qs]
+        if p[0] == "unitary":
+            assert all(x < r.nl for x in qs)
+        elif p[0] == "gate" and p[1] in ("h", "swap"):
+            assert all(x < r.nl for x in (qs if p[1] == "swap" else qs[-1:]))
+        emitted.append((p[0], p[1] if p[0] == "gate" else None, tuple(logical)))
+    assert phys == r.phys
+    want = [(op[0], op[1] if op[0] == "gate" else None, tuple(op[1] if op[0] != "gate" else op[2])) for op in ops]
+    assert sorted(map(str, emitted)) == sorted(map(str, want))
+    # dependency order: for every qubit, the subsequence of gates touching it is unchanged
+    for q in range(n):
+        assert [e for e in emitted if q in e[2]] == [w for w in want if q in w[2]]
+    nsw = sum(1 for p in plan if p[0] == "swap")
+    assert 0 < nsw <= 4 * r.gbits * 9  # far fewer than one exchange per layer and global qubit

@@ -68,7 +68,6 @@ struct TilePassParams {
   const uint8_t *codes;             // [slot][state] Pauli codes 0..3 = I,X,Y,Z (batched noisy shots), or null
   uint64_t nstates;
   int state_shift;                  // tile index >> state_shift = state (tile bits are all < num_qubits)
-  int stagger_cycles, num_sms;      // start-up phase offset between co-resident CTAs
   int nrounds;
   TileRound rounds[kMaxRounds];
 };
@@ -140,6 +139,15 @@ __device__ __forceinline__ void apply_pauli_reg(double2 (&a)[16], int code) {
   }
 }
 
+#ifdef B200SV_TILE_PROFILE
+__device__ unsigned long long g_tile_prof[4];  // load-wait, rounds, store, tiles (thread 0 of every CTA)
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(i, v) if (threadIdx.x == 0) atomicAdd(&g_tile_prof[i], (unsigned long long)(v))
+#else
+#define PROF_T(var)
+#define PROF_ADD(i, v)
+#endif
+
 template <int TB>
 __global__ void __launch_bounds__(1 << (TB - 4), TB == 12 ? 2 : 4)
 tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassParams p) {
@@ -152,21 +160,14 @@ tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
     if ((tid >> u) & 1) glo |= p.goff_lo[u];
   const uint32_t slo = phys_slot((uint32_t)tid);
 
-  // Phase stagger: CTAs that share an SM (blockIdx.x / num_sms = their resident slot) start a fraction of a
-  // tile period apart, so that one CTA's load/store phases overlap another's math instead of every CTA of the
-  // grid walking load -> compute -> store in lockstep (which costs t_mem + t_fp64 per pass, not the max).
-  if (p.stagger_cycles) {
-    const long long wait = (long long)p.stagger_cycles * (blockIdx.x / p.num_sms);
-    const long long t0 = clock64();
-    while (clock64() - t0 < wait) { }
-  }
-
   for (uint64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     double2 *gt = psi + (insert_zeros(t, p.ins) | glo);
+    PROF_T(c0);
 #pragma unroll
     for (int m = 0; m < kHiCount; m++) cp_async16(&tile[slo ^ p.soff_hi[m]], gt + p.goff_hi[m]);
     cp_async_wait_all();
     __syncthreads();
+    PROF_T(c1);
 
     for (int r = 0; r < p.nrounds; r++) {
       const TileRound &R = p.rounds[r];
@@ -213,9 +214,12 @@ tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
       __syncthreads();
     }
 
+    PROF_T(c2);
 #pragma unroll
     for (int m = 0; m < kHiCount; m++) gt[p.goff_hi[m]] = tile[slo ^ p.soff_hi[m]];
     __syncthreads();
+    PROF_T(c3);
+    PROF_ADD(0, c1 - c0); PROF_ADD(1, c2 - c1); PROF_ADD(2, c3 - c2); PROF_ADD(3, 1);
   }
 }
 
@@ -364,13 +368,6 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
     attr_set = true;
   }
   const int per_sm = kTB == 12 ? 2 : 4;
-  {
-    static const int env_stagger = [] { const char *e = getenv("B200SV_TILE_STAGGER"); return e ? atoi(e) : -1; }();
-    // one tile period per CTA ~ FP64 time of its gates (16 DFMA/amp/gate at 64 DFMA/clk/SM, shared) + load/store
-    const int period = ndense * ((16 << kTB) / 64) * per_sm + 6000;
-    p.stagger_cycles = env_stagger >= 0 ? env_stagger : period / per_sm;
-    p.num_sms = s.num_sms;
-  }
   const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms * per_sm);
   if (kTB == 12) tile_pass_kernel<12><<<grid, 256, 16 << 12, s.stream>>>((double2 *)s.data, p);
   else tile_pass_kernel<11><<<grid, 128, 16 << 11, s.stream>>>((double2 *)s.data, p);
@@ -464,5 +461,12 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
   }
   return passes;
 }
+
+#ifdef B200SV_TILE_PROFILE
+extern "C" void b200sv_tile_profile(unsigned long long *out4, int reset) {
+  cudaMemcpyFromSymbol(out4, g_tile_prof, sizeof(g_tile_prof));
+  if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_tile_prof, z, sizeof(z)); }
+}
+#endif
 
 }  // namespace b200sv

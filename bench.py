@@ -227,7 +227,7 @@ def b200_arm(args):
         plan = runner.plan(fused)
         final_phys = list(runner.phys)
         if rank == 0:
-            log("sharded plan: %d global-qubit exchanges" % sum(1 for p in plan if p[0] == "swap"))
+            log("sharded plan: %d global-qubit exchanges" % sum(1 for p in plan if p[0] in ("swap", "mswap")))
     else:
         runner, plan = None, fused
 
@@ -246,7 +246,9 @@ def b200_arm(args):
             plan = runner.plan(ops)
             final_phys = list(runner.phys)
             if rank == 0:
-                log("sharded plan (tile engine): %d global-qubit exchanges" % sum(1 for p in plan if p[0] == "swap"))
+                log("sharded plan (tile engine): %d exchange steps (%d qubit swaps)" % (
+                    sum(1 for p in plan if p[0] in ("swap", "mswap")),
+                    sum(1 if p[0] == "swap" else len(p[1]) if p[0] == "mswap" else 0 for p in plan)))
         else:
             plan = ops
 
@@ -279,7 +281,7 @@ def b200_arm(args):
                 seg.clear()
 
             for op in plan:
-                if op[0] == "swap":
+                if op[0] in ("swap", "mswap"):
                     flush_seg()
                     if timed:
                         e0, e1 = ev_pair()
@@ -287,7 +289,7 @@ def b200_arm(args):
                     launches[0] += runner.apply(op)
                     if timed:
                         e1.record(stream)
-                        evs.append(("swap", e0, e1, 1))
+                        evs.append((op[0], e0, e1, 1))
                 else:
                     seg.append(op)
             flush_seg()

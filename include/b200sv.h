@@ -176,6 +176,15 @@ int b200sv_expval_pauli_pair(b200sv_handle h, const uint64_t *qubits, int k, con
  * chunk).  `this_is_upper` = this chunk has the global bit set.  Each side calls it once and
  * moves half of the pairs (`half` = 0/1) so both NVLink directions are used. */
 int b200sv_chunk_swap_peer(b200sv_handle h, int local_q, void *peer_dev_ptr, int this_is_upper, int half);
+/* Several global qubits at once (apply_multi_chunk_swap, parallel_state_executor.hpp:1339-1552, the
+ * "all-to-all shuffle of 2^nswap sub-blocks"): local qubits local_q[0..k) trade places with the k global bits
+ * that select among 2^k ranks.  An amplitude whose local bits read l and whose rank's global bits read g moves
+ * to the rank whose global bits read l, local bits g.  `my_g` is this rank's value of the k global bits;
+ * peer_dev_ptrs[v] is the peer-mapped slice of the rank whose global bits read v (entry my_g is ignored).
+ * Every rank calls it once; each unordered pair of sub-blocks is moved by exactly one of its two owners
+ * (balanced), in place, both NVLink directions busy: (1 - 2^-k) of the slice crosses the links once instead
+ * of k half-slice exchanges. */
+int b200sv_multi_swap_peer(b200sv_handle h, int k, const int *local_q, uint32_t my_g, void *const *peer_dev_ptrs);
 /* staging variant for NCCL send/recv: gather/scatter the half-slice of amplitudes whose
  * local qubit `local_q` equals `bit`, slice [begin, begin+count) of that half, to/from a
  * contiguous device buffer (send_buffer/recv_buffer, qubitvector.hpp:1061-1081). */

@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200sv_expval_pauli_pair": [_vp, _u64p, C.c_int, C.c_char_p, _vp, C.c_uint64, C.c_uint64, C.c_double,
                                  C.c_double, _f64p],
     "b200sv_chunk_swap_peer": [_vp, C.c_int, _vp, C.c_int, C.c_int],
+    "b200sv_multi_swap_peer": [_vp, C.c_int, C.POINTER(C.c_int), C.c_uint32, C.POINTER(_vp)],
     "b200sv_pack_half": [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _vp],
     "b200sv_unpack_half": [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _vp],
     "b200sv_ipc_export": [_vp, _vp],

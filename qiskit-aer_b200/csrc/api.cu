@@ -566,6 +566,20 @@ int b200sv_chunk_swap_peer(b200sv_handle h, int local_q, void *peer, int upper, 
     launch_chunk_swap_peer(*H, local_q, peer, upper, half);
   });
 }
+int b200sv_multi_swap_peer(b200sv_handle h, int k, const int *local_q, uint32_t my_g, void *const *peers) {
+  return guard([&] {
+    select(H);
+    if (H->nstates != 1) throw Error("multi swap: not available on batched containers");
+    if (k < 1 || k > 4 || H->nq <= k) throw Error("multi swap: bad qubit count");
+    for (int b = 0; b < k; b++) {
+      if (local_q[b] < 0 || local_q[b] >= H->nq) throw Error("multi swap: local qubit out of range");
+      for (int c = 0; c < b; c++)
+        if (local_q[c] == local_q[b]) throw Error("multi swap: duplicate local qubit");
+    }
+    if (my_g >> k) throw Error("multi swap: my_g out of range");
+    launch_multi_swap_peer(*H, k, local_q, my_g, peers);
+  });
+}
 int b200sv_pack_half(b200sv_handle h, int local_q, int bit, uint64_t begin, uint64_t count, void *buf) {
   return guard([&] {
     select(H);

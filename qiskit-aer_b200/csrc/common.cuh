@@ -113,6 +113,7 @@ void launch_init(State &s, bool ket0);
 void launch_init_component(State &s, const int *qubits, int k, const double *state);
 void launch_pack_half(State &s, int q, int bit, uint64_t begin, uint64_t count, void *buf, bool unpack);
 void launch_chunk_swap_peer(State &s, int q, void *peer, int upper, int half);
+void launch_multi_swap_peer(State &s, int k, const int *local_q, uint32_t my_g, void *const *peers);
 
 // ---- tile-blocked multi-gate passes (tile.cu)
 int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats, int low_bits,

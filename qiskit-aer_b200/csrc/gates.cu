@@ -669,4 +669,59 @@ void launch_chunk_swap_peer(State &s, int q, void *peer, int upper, int half) {
   B200_CUDA(cudaGetLastError());
 }
 
+// k global qubits <-> k local qubits in one in-place pass over peer mappings
+struct MultiSwapParams {
+  void *peer[16];       // by global-bit value
+  uint32_t lvals[16];   // the l classes this rank initiates
+  int nl_classes;
+  uint32_t my_g;
+  int k;
+  uint8_t lq[4];
+  InsertList ins;       // sorted local swap positions
+  uint64_t count;       // 2^(nq-k) indices per class
+};
+template <typename T>
+__global__ void __launch_bounds__(256) multi_swap_kernel(cx<T> *__restrict__ mine, const __grid_constant__ MultiSwapParams p) {
+  const uint32_t l = p.lvals[blockIdx.y];
+  uint64_t lmask = 0, gmask = 0;
+  for (int b = 0; b < p.k; b++) {
+    if ((l >> b) & 1) lmask |= 1ull << p.lq[b];
+    if ((p.my_g >> b) & 1) gmask |= 1ull << p.lq[b];
+  }
+  cx<T> *peer = (cx<T> *)p.peer[l];
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < p.count; j += stride) {
+    const uint64_t base = insert_zeros(j, p.ins);
+    const cx<T> a = mine[base | lmask];
+    const cx<T> b = peer[base | gmask];
+    mine[base | lmask] = b;
+    peer[base | gmask] = a;
+  }
+}
+void launch_multi_swap_peer(State &s, int k, const int *local_q, uint32_t my_g, void *const *peers) {
+  if (k < 1 || k > 4) throw Error("multi swap: 1..4 qubits");
+  MultiSwapParams p;
+  p.k = k; p.my_g = my_g;
+  std::vector<int> sorted(local_q, local_q + k);
+  for (int b = 0; b < k; b++) p.lq[b] = (uint8_t)local_q[b];
+  std::sort(sorted.begin(), sorted.end());
+  p.ins.n = k;
+  for (int b = 0; b < k; b++) p.ins.pos[b] = (uint8_t)sorted[b];
+  p.count = s.amps_per_state() >> k;
+  const uint32_t dim = 1u << k, half = dim >> 1;
+  p.nl_classes = 0;
+  for (uint32_t l = 0; l < dim; l++) {
+    if (l == my_g) continue;
+    const uint32_t d = (l - my_g) & (dim - 1);
+    if (d < half || (d == half && my_g < l)) p.lvals[p.nl_classes++] = l;
+    p.peer[l] = peers[l];
+  }
+  if (p.nl_classes == 0) return;
+  int gx = (int)std::min<uint64_t>((p.count + 255) / 256, std::max<uint64_t>(1, (uint64_t)s.num_sms * 16 / p.nl_classes));
+  dim3 grid(std::max(gx, 1), p.nl_classes);
+  if (s.precision == B200SV_F64) multi_swap_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, p);
+  else multi_swap_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, p);
+  B200_CUDA(cudaGetLastError());
+}
+
 }  // namespace b200sv

@@ -304,6 +304,14 @@ class QubitVectorB200:
         capi.check(self._lib.b200sv_unpack_half(self.h, int(local_q), int(bit), int(begin), int(count),
                                                 C.c_void_p(int(dev_buf))))
 
+    def multi_swap_peer(self, local_qs, my_g, peer_ptrs):
+        """k local qubits <-> k global bits in one pass; peer_ptrs[v] = mapped slice of the rank whose k global
+        bits read v (b200sv_multi_swap_peer)."""
+        k = len(local_qs)
+        lq = (C.c_int * k)(*[int(q) for q in local_qs])
+        pp = (C.c_void_p * (1 << k))(*[C.c_void_p(int(p) if p else 0) for p in peer_ptrs])
+        capi.check(self._lib.b200sv_multi_swap_peer(self.h, k, lq, int(my_g), pp))
+
     def chunk_swap_peer(self, local_q, peer_ptr, this_is_upper, half):
         capi.check(self._lib.b200sv_chunk_swap_peer(self.h, int(local_q), C.c_void_p(int(peer_ptr)),
                                                     int(this_is_upper), int(half)))

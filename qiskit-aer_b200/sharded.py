@@ -48,13 +48,18 @@ class ShardedRunner:
         qv.chunk_setup(self.n, self.rank)
         self.bytes_exchanged = 0
         self.exchange = exchange
+        self.multi_swap = True   # fold the swaps of one epoch boundary into one all-to-all pass
         self._peer_ptr = {}
         if exchange == "p2p":
             # CUDA-IPC: map every exchange partner's chunk into this process (NVLink peer access)
             handles = [None] * world
             dist.all_gather_object(handles, qv.ipc_export())
+            self._rank_ptr = {}
+            for r in range(world):
+                if r != self.rank:
+                    self._rank_ptr[r] = qv.ipc_open(handles[r])
             for gb in range(self.gbits):
-                self._peer_ptr[gb] = qv.ipc_open(handles[self.rank ^ (1 << gb)])
+                self._peer_ptr[gb] = self._rank_ptr[self.rank ^ (1 << gb)]
             self._flag = torch.zeros(1, dtype=torch.float32, device=self.amps.device)
 
     # ---------------------------------------------------------------- planning (host, deterministic)
@@ -115,12 +120,17 @@ class ShardedRunner:
                 for q in need_local(ops[i]):
                     uses.setdefault(q, []).append(pos)
             busy = set(wanted) | frontier
+            pairs = []
             for q in wanted[:self.gbits]:
                 victim = self._pick_victim(phys, busy, uses, -1)
                 busy.add(victim)
                 lpos, gpos = phys[victim], phys[q]
-                out.append(("swap", lpos, gpos - nl))
+                pairs.append((lpos, gpos - nl))
                 phys[victim], phys[q] = gpos, lpos
+            if len(pairs) > 1 and self.multi_swap:
+                out.append(("mswap", [a for a, _ in pairs], [b for _, b in pairs]))
+            else:
+                out.extend(("swap", a, b) for a, b in pairs)
         self.phys = phys
         return out
 
@@ -166,15 +176,39 @@ class ShardedRunner:
         if op[0] == "swap":
             with self._ctx():
                 return self.swap_global(op[1], op[2])
+        if op[0] == "mswap":
+            with self._ctx():
+                return self.multi_swap_global(op[1], op[2])
         apply_op(self.qv, op)
         return 1
+
+    def multi_swap_global(self, lposs, gbits):
+        """k local qubits <-> k global bits in ONE in-place pass over the peer mappings (all-to-all among the
+        2^k ranks that differ in those bits); falls back to k pairwise exchanges without peer mappings."""
+        if self.exchange != "p2p":
+            return sum(self.swap_global(a, b) for a, b in zip(lposs, gbits))
+        k = len(lposs)
+        my_g = 0
+        for i, gb in enumerate(gbits):
+            my_g |= ((self.rank >> gb) & 1) << i
+        peers = []
+        for v in range(1 << k):
+            r = self.rank
+            for i, gb in enumerate(gbits):
+                r = (r & ~(1 << gb)) | (((v >> i) & 1) << gb)
+            peers.append(self._rank_ptr.get(r, 0))
+        dist.all_reduce(self._flag)
+        self.qv.multi_swap_peer(lposs, my_g, peers)
+        dist.all_reduce(self._flag)
+        self.bytes_exchanged += int((1 << self.nl) * (1 - 0.5 ** k)) * self.amps.element_size() * 2
+        return 3
 
     def run_plan(self, plan, stats=None, queued=True):
         """Execute a plan; with `queued`, dense 1-/2-qubit gates between exchanges are flushed through the
         tile-blocked multi-gate passes (b200sv_apply_gate_sequence)."""
         from .executor import apply_ops_queued
         if queued:
-            apply_ops_queued(self.qv, plan, stats, special={"swap": self.apply})
+            apply_ops_queued(self.qv, plan, stats, special={"swap": self.apply, "mswap": self.apply})
         else:
             for op in plan:
                 n_launch = self.apply(op)

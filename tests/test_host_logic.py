@@ -64,17 +64,21 @@ def test_epoch_planner_invariants(world, n):
     r.n, r.world, r.gbits, r.rank, r.min_run_bits = n, world, int(np.log2(world)), 0, 6
     r.nl = n - r.gbits
     r.phys = list(range(n))
+    r.multi_swap = True
     ops = circuits.quantum_volume(n, 8, seed=world) + circuits.qft(n)
     plan = r.plan(ops)
     phys = list(range(n))          # replay the map
     emitted = []
     for p in plan:
-        if p[0] == "swap":
-            lpos, gpos = p[1], p[2] + r.nl
-            assert 0 <= lpos < r.nl and r.nl <= gpos < n
-            inv = {pp: q for q, pp in enumerate(phys)}
-            a, b = inv[lpos], inv[gpos]
-            phys[a], phys[b] = gpos, lpos
+        if p[0] in ("swap", "mswap"):
+            pairs = [(p[1], p[2])] if p[0] == "swap" else list(zip(p[1], p[2]))
+            assert len({a for a, _ in pairs}) == len(pairs) and len({b for _, b in pairs}) == len(pairs)
+            for lpos, gb in pairs:
+                gpos = gb + r.nl
+                assert 0 <= lpos < r.nl and r.nl <= gpos < n
+                inv = {pp: q for q, pp in enumerate(phys)}
+                a, b = inv[lpos], inv[gpos]
+                phys[a], phys[b] = gpos, lpos
             continue
         qs = p[1] if p[0] in ("unitary", "diagonal") else p[2]
         inv = {pp: q for q, pp in enumerate(phys)}
@@ -90,5 +94,5 @@ def test_epoch_planner_invariants(world, n):
     # dependency order: for every qubit, the subsequence of gates touching it is unchanged
     for q in range(n):
         assert [e for e in emitted if q in e[2]] == [w for w in want if q in w[2]]
-    nsw = sum(1 for p in plan if p[0] == "swap")
+    nsw = sum(1 if p[0] == "swap" else len(p[1]) if p[0] == "mswap" else 0 for p in plan)
     assert 0 < nsw <= 4 * r.gbits * 9  # far fewer than one exchange per layer and global qubit

@@ -35,7 +35,7 @@ def _worker(rank, world, port, n, min_run_bits, slice_amps, q):
         fused = fusion.fuse(ops, max_qubit=3)
         run.initialize()
         plan = run.plan(fused)
-        nswaps = sum(1 for p in plan if p[0] == "swap")
+        nswaps = sum(1 for p in plan if p[0] in ("swap", "mswap"))
         for p in plan:
             run.apply(p)
         # reference: the same circuit on one unsharded oracle state

@@ -62,7 +62,7 @@ def main():
         mine = qv.vector()
         want = ref.vector()[rank << nl:(rank + 1) << nl]
         err = float(np.max(np.abs(mine - want)))
-        nsw = sum(1 for p in plan if p[0] == "swap")
+        nsw = sum(1 for p in plan if p[0] in ("swap", "mswap"))
         good = err < 1e-12 and ev_err < 1e-10 and same and nsw > 0
         ok = ok and good
         print("rank %d %s min_run_bits=%d swaps=%d max|err|=%.2e ev_err=%.2e samples_equal=%s" %

@@ -648,12 +648,21 @@ __global__ void __launch_bounds__(256) chunk_swap_peer_kernel(cx<T> *__restrict_
                                                               uint64_t mine_mask, uint64_t peer_mask, uint64_t begin,
                                                               uint64_t count) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count; j += stride) {
-    const uint64_t iz = insert_zero(begin + j, q);
-    const cx<T> a = mine[iz | mine_mask];
-    const cx<T> b = peer[iz | peer_mask];
-    mine[iz | mine_mask] = b;
-    peer[iz | peer_mask] = a;
+  constexpr int U = 4;  // remote loads in flight per thread
+  for (uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < count; j0 += stride * U) {
+    cx<T> a[U], b[U];
+    uint64_t iz[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t j = j0 + u * stride;
+      iz[u] = insert_zero(begin + (j < count ? j : 0), q);
+      if (j < count) { b[u] = peer[iz[u] | peer_mask]; a[u] = mine[iz[u] | mine_mask]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t j = j0 + u * stride;
+      if (j < count) { mine[iz[u] | mine_mask] = b[u]; peer[iz[u] | peer_mask] = a[u]; }
+    }
   }
 }
 void launch_chunk_swap_peer(State &s, int q, void *peer, int upper, int half) {
@@ -690,12 +699,21 @@ __global__ void __launch_bounds__(256) multi_swap_kernel(cx<T> *__restrict__ min
   }
   cx<T> *peer = (cx<T> *)p.peer[l];
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < p.count; j += stride) {
-    const uint64_t base = insert_zeros(j, p.ins);
-    const cx<T> a = mine[base | lmask];
-    const cx<T> b = peer[base | gmask];
-    mine[base | lmask] = b;
-    peer[base | gmask] = a;
+  constexpr int U = 4;  // remote loads in flight per thread (NVLink latency ~2 us)
+  for (uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < p.count; j0 += stride * U) {
+    cx<T> a[U], b[U];
+    uint64_t base[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t j = j0 + u * stride;
+      base[u] = insert_zeros(j < p.count ? j : 0, p.ins);
+      if (j < p.count) { b[u] = peer[base[u] | gmask]; a[u] = mine[base[u] | lmask]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t j = j0 + u * stride;
+      if (j < p.count) { mine[base[u] | lmask] = b[u]; peer[base[u] | gmask] = a[u]; }
+    }
   }
 }
 void launch_multi_swap_peer(State &s, int k, const int *local_q, uint32_t my_g, void *const *peers) {

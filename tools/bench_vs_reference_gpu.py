@@ -32,7 +32,8 @@ if side == "reference_gpu":
 from qiskit_aer_b200 import aer_backend
 ops = circuits.qft(n) if workload == "qft" else circuits.quantum_volume(n, 10, 1234)
 kw = dict(device="GPU", shots=1024, seed=1234, fusion=fusion, fusion_max_qubit=fmax, expvals=[([0, 1, n - 1], "ZXY")])
-aer_backend.run_circuit(min(n, 24), circuits.quantum_volume(min(n, 24), 2, 1), **kw)  # warm-up (context, modules)
+aer_backend.run_circuit(20, circuits.quantum_volume(20, 2, 1), device="GPU", shots=16, seed=1, fusion=fusion,
+                        fusion_max_qubit=fmax)  # warm-up (context, modules)
 best = None
 for _ in range(2):
     t0 = time.perf_counter()

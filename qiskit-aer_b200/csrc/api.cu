@@ -463,7 +463,7 @@ int b200sv_apply_gate_sequence(b200sv_handle h, int ngates, const int *nq, const
   return guard([&] {
     select(H);
     if (ngates < 0 || (ngates > 0 && (!nq || !qubits || !mats))) throw Error("apply_gate_sequence: bad arguments");
-    const int passes = ngates ? apply_gate_sequence(*H, ngates, nq, qubits, mats, 2) : 0;
+    const int passes = ngates ? apply_gate_sequence(*H, ngates, nq, qubits, mats, 3) : 0;
     if (passes_out) *passes_out = passes;
   });
 }
@@ -473,7 +473,7 @@ int b200sv_apply_op_sequence(b200sv_handle h, int nops, const int *kind, const u
   return guard([&] {
     select(H);
     if (nops < 0 || (nops > 0 && (!kind || !qubits || !mats))) throw Error("apply_op_sequence: bad arguments");
-    const int passes = nops ? apply_gate_sequence(*H, nops, kind, qubits, mats, 2, slot, codes, nslots) : 0;
+    const int passes = nops ? apply_gate_sequence(*H, nops, kind, qubits, mats, 3, slot, codes, nslots) : 0;
     if (passes_out) *passes_out = passes;
   });
 }

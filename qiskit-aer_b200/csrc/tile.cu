@@ -54,6 +54,9 @@ struct TileRound {
   uint16_t eoff[16];            // phys(sum_i bit_i(e) << pos[i]) for the 16 elements of a sub-block
   uint16_t gbit[8];             // phys(1 << tpos[i]): contribution of group-id bit i
   uint8_t ngates;
+  uint8_t sync;                 // 1: CTA barrier after this round; 0: the next round stays inside each warp's sub-tile
+  uint8_t fast;                 // 2 / 1: exactly two / one dense 2-qubit gate(s), on round bits (0,1) [and (2,3)]:
+                                // straight-line code (LDS, DFMA and STS interleave, no form dispatch); 0: generic
   uint8_t form[kMaxRoundGates];  // 0..5: 2-qubit on round-bit pair; 6..9: 1-qubit on round bit (form-6);
                                  // 10..13: per-state Pauli on round bit (form-10), code table slot in gate[]
   uint16_t gate[kMaxRoundGates]; // index into mats (dense) or error-code slot (Pauli)
@@ -69,12 +72,21 @@ struct TilePassParams {
   uint64_t nstates;
   int state_shift;                  // tile index >> state_shift = state (tile bits are all < num_qubits)
   int nrounds;
+  int prefetch;                     // 1: pull the CTA's NEXT tile into L2 while this one is being computed on
   TileRound rounds[kMaxRounds];
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+// same, ordered against the surrounding shared-memory accesses of the issuing thread (buffer refill right after read-out)
+__device__ __forceinline__ void cp_async16_ordered(void *smem, const void *gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *gmem) {
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
@@ -139,51 +151,50 @@ __device__ __forceinline__ void apply_pauli_reg(double2 (&a)[16], int code) {
   }
 }
 
-#ifdef B200SV_TILE_PROFILE
-__device__ unsigned long long g_tile_prof[4];  // load-wait, rounds, store, tiles (thread 0 of every CTA)
-#define PROF_T(var) const long long var = clock64()
-#define PROF_ADD(i, v) if (threadIdx.x == 0) atomicAdd(&g_tile_prof[i], (unsigned long long)(v))
-#else
-#define PROF_T(var)
-#define PROF_ADD(i, v)
-#endif
-
-template <int TB>
-__global__ void __launch_bounds__(1 << (TB - 4), TB == 12 ? 2 : 4)
-tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassParams p) {
-  constexpr int kLoBits = TB - 4;  // tile-local bits covered by the thread id (= group id bits)
-  extern __shared__ __align__(16) double2 tile[];
-  const int tid = threadIdx.x;
-  uint64_t glo = 0;
+// all rounds of one tile, in place in shared memory.  GROUPED = 0: the CTA is one 2^(TB-4)-thread group
+// (__syncthreads); GROUPED = 1: 256-thread groups of a bigger CTA, named barrier 1 + grp.
+// MODE 0: fast and generic rounds; 1: every round of the pass is fast; 2: generic code only (fast rounds carry
+// generic forms too).  The pipelined kernel is instantiated per mode: with both code paths in one kernel ptxas
+// runs out of uniform registers and demotes the generic path's matrix operands to vector registers.
+template <int GROUPED, int kLoBits, int MODE>
+__device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int tid, const uint64_t t,
+                                           const TilePassParams &p, const int grp, const bool valid) {
+  for (int r = 0; r < p.nrounds; r++) {
+    const TileRound &R = p.rounds[r];
+    {
+      const int g = tid;
+      uint32_t base = 0;
 #pragma unroll
-  for (int u = 0; u < kLoBits; u++)
-    if ((tid >> u) & 1) glo |= p.goff_lo[u];
-  const uint32_t slo = phys_slot((uint32_t)tid);
-
-  for (uint64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-    double2 *gt = psi + (insert_zeros(t, p.ins) | glo);
-    PROF_T(c0);
+      for (int i = 0; i < kLoBits; i++)
+        if ((g >> i) & 1) base ^= R.gbit[i];
+      const int fast = MODE == 2 ? 0 : R.fast;
+      if (fast == 2) {
+        double2 a[16];
 #pragma unroll
-    for (int m = 0; m < kHiCount; m++) cp_async16(&tile[slo ^ p.soff_hi[m]], gt + p.goff_hi[m]);
-    cp_async_wait_all();
-    __syncthreads();
-    PROF_T(c1);
-
-    for (int r = 0; r < p.nrounds; r++) {
-      const TileRound &R = p.rounds[r];
-      {
-        const int g = tid;
-        uint32_t base = 0;
+        for (int e = 0; e < 16; e++) a[e] = tile[base ^ R.eoff[e]];
+        apply2<0, 1>(a, p.mats[R.gate[0]]);
+        apply2<2, 3>(a, p.mats[R.gate[1]]);
 #pragma unroll
-        for (int i = 0; i < kLoBits; i++)
-          if ((g >> i) & 1) base ^= R.gbit[i];
+        for (int e = 0; e < 16; e++)
+          if (valid) tile[base ^ R.eoff[e]] = a[e];
+      } else if (MODE == 1 || fast == 1) {
+        double2 a[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) a[e] = tile[base ^ R.eoff[e]];
+        apply2<0, 1>(a, p.mats[R.gate[0]]);
+#pragma unroll
+        for (int e = 0; e < 16; e++)
+          if (valid) tile[base ^ R.eoff[e]] = a[e];
+      } else {
         double2 a[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) a[e] = tile[base ^ R.eoff[e]];
         for (int k = 0; k < R.ngates; k++) {
           const int form = R.form[k];
           if (form >= 10) {  // sampled noise: Pauli chosen per state (shot)
-            const int code = p.codes[(size_t)R.gate[k] * p.nstates + (t >> p.state_shift)];
+            // uniform over the CTA; the lane-0 broadcast lets the compiler see that (keeps the dense gates below in
+            // convergent control flow, i.e. their matrices on the uniform datapath)
+            const int code = __shfl_sync(0xffffffffu, (int)p.codes[(size_t)R.gate[k] * p.nstates + (t >> p.state_shift)], 0);
             if (code) {
               switch (form) {
               case 10: apply_pauli_reg<0>(a, code); break;
@@ -209,10 +220,63 @@ tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
           }
         }
 #pragma unroll
-        for (int e = 0; e < 16; e++) tile[base ^ R.eoff[e]] = a[e];
+        for (int e = 0; e < 16; e++)
+          if (valid) tile[base ^ R.eoff[e]] = a[e];
       }
-      __syncthreads();
     }
+    if (R.sync) {
+      if (GROUPED) {
+        if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
+        else asm volatile("bar.sync 1, 256;" ::: "memory");
+      } else __syncthreads();
+    }
+    else __syncwarp();
+  }
+}
+
+#ifdef B200SV_TILE_PROFILE
+__device__ unsigned long long g_tile_prof[4];  // load-wait, rounds, store, tiles (thread 0 of every CTA)
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(i, v) if (threadIdx.x == 0) atomicAdd(&g_tile_prof[i], (unsigned long long)(v))
+#else
+#define PROF_T(var)
+#define PROF_ADD(i, v)
+#endif
+
+template <int TB>
+__global__ void __launch_bounds__(1 << (TB - 4), TB == 12 ? 2 : 4)
+tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassParams p) {
+  constexpr int kLoBits = TB - 4;  // tile-local bits covered by the thread id (= group id bits)
+  extern __shared__ __align__(16) double2 tile[];
+  const int tid = threadIdx.x;
+  uint64_t glo = 0;
+#pragma unroll
+  for (int u = 0; u < kLoBits; u++)
+    if ((tid >> u) & 1) glo |= p.goff_lo[u];
+  const uint32_t slo = phys_slot((uint32_t)tid);
+  // L2 prefetch of the next tile: 2^(TB-3) lines of 128 B, 2 per thread; line L = tid + nthreads * i covers
+  // tile-local j = L << 3 (the three lowest tile bits are the three lowest global bits whenever low_bits >= 3)
+  uint64_t plo = 0;
+#pragma unroll
+  for (int u = 3; u < kLoBits; u++)
+    if ((tid >> (u - 3)) & 1) plo |= p.goff_lo[u];
+  const int pm = tid >> (kLoBits - 3);
+
+  for (uint64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+    double2 *gt = psi + (insert_zeros(t, p.ins) | glo);
+    PROF_T(c0);
+#pragma unroll
+    for (int m = 0; m < kHiCount; m++) cp_async16(&tile[slo ^ p.soff_hi[m]], gt + p.goff_hi[m]);
+    if (p.prefetch && t + gridDim.x < p.ntiles) {
+      const double2 *gn = psi + (insert_zeros(t + gridDim.x, p.ins) | plo);
+      prefetch_l2(gn + p.goff_hi[pm]);
+      prefetch_l2(gn + p.goff_hi[pm + 8]);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    PROF_T(c1);
+
+    run_rounds<0, kLoBits, 0>(tile, tid, t, p, 0, true);
 
     PROF_T(c2);
 #pragma unroll
@@ -221,6 +285,92 @@ tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
     PROF_T(c3);
     PROF_ADD(0, c1 - c0); PROF_ADD(1, c2 - c1); PROF_ADD(2, c3 - c2); PROF_ADD(3, 1);
   }
+}
+
+// ------------------------------------------------------------------------------------------ pipelined variant
+// One 512-thread CTA per SM = two 256-thread groups that each run the load-wait / rounds / store sequence of
+// tile_pass_kernel<12> on their own tile, plus a THIRD 64 KiB tile buffer: the buffer a group has just streamed
+// out is refilled at once (same thread, same slots: LDS -> STG -> LDGSTS) with the tile the OTHER group will need
+// two tiles later, so a tile's HBM latency runs behind the other group's rounds instead of stalling its consumer.
+// Tile k of the CTA lives in buffer k % 3 and belongs to group k % 2; "full" mbarriers (256 cp.async arrivals)
+// hand a loaded buffer across groups.  (Queueing view: 2 compute customers + 3 memory customers per SM instead of
+// 2 + 2 -- profiles/r01_tile_phase_breakdown.md.)
+constexpr int kPipeBufs = 3;
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_cp_async(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n.reg .pred P1;\nWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\nbra WAIT_LOOP;\nDONE:\n}" ::"r"(a), "r"(parity) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(512, 1)
+tile_pipe_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassParams p) {
+  constexpr int kLoBits = 8;
+  extern __shared__ __align__(16) double2 tiles[];  // kPipeBufs tiles, then the barriers and progress counters
+  uint64_t *full = reinterpret_cast<uint64_t *>(tiles + kPipeBufs * 4096);
+  volatile int *progress = reinterpret_cast<volatile int *>(full + kPipeBufs);  // [grp]: tiles whose rounds are done
+  // broadcast from lane 0: tells the compiler the group id is warp-uniform (keeps the gate matrices on the uniform datapath)
+  const int grp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 8), 0), tid = threadIdx.x & 255;
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < kPipeBufs; b++) mbar_init(&full[b], 256);
+    progress[0] = 0;
+    progress[1] = 0;
+  }
+  __syncthreads();
+  uint64_t glo = 0;
+#pragma unroll
+  for (int u = 0; u < kLoBits; u++)
+    if ((tid >> u) & 1) glo |= p.goff_lo[u];
+  const uint32_t slo = phys_slot((uint32_t)tid);
+  auto issue_load = [&](uint64_t k) {  // all 256 threads of one group; arrives on full[k % 3] when the copies land
+    const uint64_t t = blockIdx.x + k * gridDim.x;
+    double2 *buf = tiles + (k % kPipeBufs) * 4096;
+    if (t < p.ntiles) {
+      const double2 *gt = psi + (insert_zeros(t, p.ins) | glo);
+#pragma unroll
+      for (int m = 0; m < kHiCount; m++) cp_async16_ordered(&buf[slo ^ p.soff_hi[m]], gt + p.goff_hi[m]);
+    }
+    mbar_arrive_cp_async(&full[k % kPipeBufs]);
+  };
+  if (grp == 0) { issue_load(0); issue_load(2); }
+  else issue_load(1);
+  // Both groups run the same (uniform) number of iterations so that the rounds stay in convergent control flow
+  // (gate matrices on the uniform datapath); a group without a tile in its last iteration computes on stale shared
+  // memory with its stores predicated off.
+  const int K = (int)((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // tiles of this CTA
+  for (int kk = 0; 2 * kk < K; kk++) {
+    const int k = 2 * kk + grp;
+    const bool valid = k < K;
+    const uint64_t t = blockIdx.x + (uint64_t)k * gridDim.x;
+    double2 *tile = tiles + (k % kPipeBufs) * 4096;
+    if (valid) {
+      // tile k >= 3 was requested by the other group after ITS tile k - 3: make sure that group is past its own wait
+      // on this buffer before testing the barrier's phase parity (a waiter two phases ahead would read a stale parity)
+      if (k >= 3) {
+        const int need = ((k - 3) >> 1) + 1;
+        while (progress[grp ^ 1] < need) { }
+      }
+      mbar_wait(&full[k % kPipeBufs], (uint32_t)((k / kPipeBufs) & 1));
+    }
+    run_rounds<1, kLoBits, MODE>(tile, tid, t, p, grp, valid);
+    if (valid) {
+      if (tid == 0) progress[grp] = kk + 1;
+      double2 *gt = psi + (insert_zeros(t, p.ins) | glo);
+#pragma unroll
+      for (int m = 0; m < kHiCount; m++) gt[p.goff_hi[m]] = tile[slo ^ p.soff_hi[m]];
+      issue_load(k + 3);
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------ host scheduler
@@ -248,12 +398,18 @@ static bool pick_lane_positions(const std::vector<int> &free_pos, int out[3]) {
   return false;
 }
 
-static void build_round(TileRound &R, const std::vector<int> &round_pos /*tile-local, <=4*/, int kTB) {
+// Thread-id bits 0..4 (lane) and 5.. (warp) of a round map to the tile positions that are not round positions.
+// `wpos` (kTB - 9 positions, or empty) pins the warp-id bits: consecutive rounds that share wpos keep every warp
+// inside its own 2^9-amplitude sub-tile (round positions + lane positions = all positions outside wpos), so only
+// __syncwarp() is needed between them.  Returns the padded, sorted round positions.
+static std::vector<int> build_round(TileRound &R, const std::vector<int> &round_pos /*tile-local, <=4*/,
+                                    const std::vector<int> &wpos, int kTB, bool keep_order = false) {
+  auto has = [](const std::vector<int> &v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); };
   // pad the round to 4 positions with unused tile positions (highest first)
   std::vector<int> pos = round_pos;
   for (int u = kTB - 1; (int)pos.size() < kRoundBits && u >= 0; u--)
-    if (std::find(pos.begin(), pos.end(), u) == pos.end()) pos.push_back(u);
-  std::sort(pos.begin(), pos.end());
+    if (!has(pos, u) && !has(wpos, u)) pos.push_back(u);
+  if (!keep_order) std::sort(pos.begin(), pos.end());  // fast rounds fix round bit i <-> round_pos[i]
   for (int e = 0; e < 16; e++) {
     uint32_t j = 0;
     for (int i = 0; i < 4; i++)
@@ -262,16 +418,18 @@ static void build_round(TileRound &R, const std::vector<int> &round_pos /*tile-l
   }
   std::vector<int> free_pos;
   for (int u = 0; u < kTB; u++)
-    if (std::find(pos.begin(), pos.end(), u) == pos.end()) free_pos.push_back(u);
+    if (!has(pos, u) && !has(wpos, u)) free_pos.push_back(u);
   int lane[3];
   if (!pick_lane_positions(free_pos, lane)) { lane[0] = free_pos[0]; lane[1] = free_pos[1]; lane[2] = free_pos[2]; }
   std::vector<int> tpos(lane, lane + 3);
   for (int u : free_pos)
     if (u != lane[0] && u != lane[1] && u != lane[2]) tpos.push_back(u);
+  for (int u : wpos) tpos.push_back(u);
   for (int i = 0; i < kTB - 4; i++) R.gbit[i] = (uint16_t)phys_slot(1u << tpos[i]);
   R.ngates = 0;
-  // stash sorted positions in eoff order: callers need pos -> round-bit index
-  (void)pos;
+  R.sync = 1;
+  R.fast = 0;
+  return pos;
 }
 
 static int round_bit_of(const std::vector<int> &sorted_pos, int tile_pos) {
@@ -289,6 +447,8 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
   p.codes = dev_codes;
   p.nstates = (uint64_t)s.nstates;
   p.state_shift = s.nq - kTB;
+  static const int env_prefetch = [] { const char *e = getenv("B200SV_TILE_PREFETCH"); return e ? atoi(e) : 0; }();
+  p.prefetch = env_prefetch;
   p.ins.n = kTB;
   for (int u = 0; u < kTB; u++) p.ins.pos[u] = (uint8_t)tile_bits[u];
   for (int u = 0; u < kLoBits; u++) p.goff_lo[u] = 1ull << tile_bits[u];
@@ -308,9 +468,9 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
   // rounds: scan in order, capacity 4 tile positions, respect dependencies
   std::vector<int> rem(sel.size());
   for (size_t i = 0; i < sel.size(); i++) rem[i] = (int)i;  // indices into sel
-  p.nrounds = 0;
+  std::vector<std::vector<int>> round_take, round_pos;
   while (!rem.empty()) {
-    if (p.nrounds >= kMaxRounds) throw Error("tile pass: too many rounds");
+    if ((int)round_take.size() >= kMaxRounds) throw Error("tile pass: too many rounds");
     uint64_t rq = 0, blocked = 0;
     std::vector<int> take, rest;
     for (int li : rem) {
@@ -323,49 +483,128 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
     std::vector<int> rpos;
     for (int q = 0; q < 64; q++)
       if ((rq >> q) & 1) rpos.push_back(tile_pos(q));
-    TileRound &R = p.rounds[p.nrounds++];
-    build_round(R, rpos, kTB);
-    // recompute the padded+sorted position list exactly as build_round did
-    std::vector<int> pos = rpos;
-    for (int u = kTB - 1; (int)pos.size() < kRoundBits && u >= 0; u--)
-      if (std::find(pos.begin(), pos.end(), u) == pos.end()) pos.push_back(u);
-    std::sort(pos.begin(), pos.end());
-    for (int li : take) {
-      const QGate &g = gates[sel[li]];
-      if (!g.mat) {  // per-state Pauli
-        R.form[R.ngates] = (uint8_t)(10 + round_bit_of(pos, tile_pos(g.q[0])));
-        R.gate[R.ngates++] = (uint16_t)g.slot;
-        continue;
-      }
-      if (ndense >= kMaxTileGates) throw Error("tile pass: too many dense gates");
-      const int mi = ndense++;
-      double2 *M = p.mats[mi];
-      if (g.nq == 1) {
-        const int b = round_bit_of(pos, tile_pos(g.q[0]));
-        for (int i = 0; i < 2; i++)
-          for (int j = 0; j < 2; j++) M[i * 2 + j] = mk<double>(g.mat[2 * (i + 2 * j)], g.mat[2 * (i + 2 * j) + 1]);
-        R.form[R.ngates] = (uint8_t)(6 + b);
-      } else {
-        int b0 = round_bit_of(pos, tile_pos(g.q[0])), b1 = round_bit_of(pos, tile_pos(g.q[1]));
-        const bool flip = b0 > b1;  // canonical: matrix bit0 <-> lower round bit
-        for (int i = 0; i < 4; i++)
-          for (int j = 0; j < 4; j++) {
-            const int si = flip ? ((i >> 1) | ((i & 1) << 1)) : i, sj = flip ? ((j >> 1) | ((j & 1) << 1)) : j;
-            M[i * 4 + j] = mk<double>(g.mat[2 * (si + 4 * sj)], g.mat[2 * (si + 4 * sj) + 1]);
-          }
-        if (flip) std::swap(b0, b1);
-        static const int form_of[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
-        R.form[R.ngates] = (uint8_t)form_of[b0][b1];
-      }
-      R.gate[R.ngates++] = (uint16_t)mi;
-    }
+    round_take.push_back(take);
+    round_pos.push_back(rpos);
     rem.swap(rest);
+  }
+  // segments: maximal runs of rounds that leave >= nW tile positions untouched; those become the warp-id positions
+  // of the whole run, which makes the run warp-local (no CTA barrier inside).  B200SV_TILE_WARP_LOCAL=0 disables.
+  static const int env_wl = [] { const char *e = getenv("B200SV_TILE_WARP_LOCAL"); return e ? atoi(e) : 1; }();
+  const int nW = kTB - 9, nr = (int)round_take.size();
+  p.nrounds = nr;
+  for (int r0 = 0; r0 < nr;) {
+    uint32_t touched = 0;
+    int r1 = r0;
+    while (r1 < nr) {
+      uint32_t t2 = touched;
+      for (int u : round_pos[r1]) t2 |= 1u << u;
+      if (r1 > r0 && (!env_wl || kTB - __builtin_popcount(t2) < nW)) break;
+      touched = t2;
+      r1++;
+    }
+    std::vector<int> cand;
+    for (int u = 0; u < kTB; u++)
+      if (!((touched >> u) & 1)) cand.push_back(u);
+    // choose the warp positions that leave conflict-free lane triples in the most rounds (prefer high positions)
+    std::vector<int> best;
+    int best_ok = -1;
+    const int nc = (int)cand.size();
+    for (int a = nc - 1; a >= nW - 1; a--)
+      for (int b = (nW >= 2 ? a - 1 : -1); b >= (nW >= 2 ? nW - 2 : -1); b--)
+        for (int c = (nW >= 3 ? b - 1 : -1); c >= (nW >= 3 ? 0 : -1); c--) {
+          std::vector<int> w;
+          w.push_back(cand[a]);
+          if (nW >= 2) w.push_back(cand[b]);
+          if (nW >= 3) w.push_back(cand[c]);
+          int ok = 0;
+          for (int r = r0; r < r1; r++) {
+            std::vector<int> pos = round_pos[r];
+            for (int u = kTB - 1; (int)pos.size() < kRoundBits && u >= 0; u--)
+              if (std::find(pos.begin(), pos.end(), u) == pos.end() && std::find(w.begin(), w.end(), u) == w.end())
+                pos.push_back(u);
+            std::vector<int> fp;
+            for (int u = 0; u < kTB; u++)
+              if (std::find(pos.begin(), pos.end(), u) == pos.end() && std::find(w.begin(), w.end(), u) == w.end())
+                fp.push_back(u);
+            int lane[3];
+            ok += pick_lane_positions(fp, lane);
+          }
+          if (ok > best_ok) { best_ok = ok; best = w; }
+          if (nW < 3) break;
+        }
+    std::sort(best.begin(), best.end());
+    for (int r = r0; r < r1; r++) {
+      TileRound &R = p.rounds[r];
+      // fast round: one or two disjoint dense 2-qubit gates -> round bits (0,1) and (2,3) in gate-qubit order
+      static const int env_fast = [] { const char *e = getenv("B200SV_TILE_FAST"); return e ? atoi(e) : 1; }();
+      int fast = 0;
+      std::vector<int> ordered;
+      if (env_fast && round_take[r].size() <= 2) {
+        fast = (int)round_take[r].size();
+        for (int li : round_take[r]) {
+          const QGate &g = gates[sel[li]];
+          if (!g.mat || g.nq != 2) { fast = 0; break; }
+          ordered.push_back(tile_pos(g.q[0]));
+          ordered.push_back(tile_pos(g.q[1]));
+        }
+        if (fast == 2 && (ordered[0] == ordered[2] || ordered[0] == ordered[3] || ordered[1] == ordered[2] ||
+                          ordered[1] == ordered[3]))
+          fast = 0;
+      }
+      const std::vector<int> pos = build_round(R, fast ? ordered : round_pos[r], best, kTB, fast != 0);
+      R.sync = (r == r1 - 1);
+      R.fast = (uint8_t)fast;
+      for (int li : round_take[r]) {
+        const QGate &g = gates[sel[li]];
+        if (!g.mat) {  // per-state Pauli
+          R.form[R.ngates] = (uint8_t)(10 + round_bit_of(pos, tile_pos(g.q[0])));
+          R.gate[R.ngates++] = (uint16_t)g.slot;
+          continue;
+        }
+        if (ndense >= kMaxTileGates) throw Error("tile pass: too many dense gates");
+        const int mi = ndense++;
+        double2 *M = p.mats[mi];
+        if (g.nq == 1) {
+          const int b = round_bit_of(pos, tile_pos(g.q[0]));
+          for (int i = 0; i < 2; i++)
+            for (int j = 0; j < 2; j++) M[i * 2 + j] = mk<double>(g.mat[2 * (i + 2 * j)], g.mat[2 * (i + 2 * j) + 1]);
+          R.form[R.ngates] = (uint8_t)(6 + b);
+        } else {
+          int b0 = round_bit_of(pos, tile_pos(g.q[0])), b1 = round_bit_of(pos, tile_pos(g.q[1]));
+          const bool flip = b0 > b1;  // canonical: matrix bit0 <-> lower round bit
+          for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) {
+              const int si = flip ? ((i >> 1) | ((i & 1) << 1)) : i, sj = flip ? ((j >> 1) | ((j & 1) << 1)) : j;
+              M[i * 4 + j] = mk<double>(g.mat[2 * (si + 4 * sj)], g.mat[2 * (si + 4 * sj) + 1]);
+            }
+          if (flip) std::swap(b0, b1);
+          static const int form_of[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
+          R.form[R.ngates] = (uint8_t)form_of[b0][b1];
+        }
+        R.gate[R.ngates++] = (uint16_t)mi;
+      }
+    }
+    r0 = r1;
   }
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 12)));
     B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 11)));
+    B200_CUDA(cudaFuncSetAttribute(tile_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kPipeBufs * (16 << 12) + 64));
+    B200_CUDA(cudaFuncSetAttribute(tile_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kPipeBufs * (16 << 12) + 64));
     attr_set = true;
+  }
+  static const int env_pipe = [] { const char *e = getenv("B200SV_TILE_PIPE"); return e ? atoi(e) : 1; }();
+  if (kTB == 12 && env_pipe) {
+    const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms);
+    bool all_fast = true;
+    for (int r = 0; r < p.nrounds; r++) all_fast = all_fast && p.rounds[r].fast;
+    if (all_fast) tile_pipe_kernel<1><<<grid, 512, kPipeBufs * (16 << 12) + 64, s.stream>>>((double2 *)s.data, p);
+    else tile_pipe_kernel<2><<<grid, 512, kPipeBufs * (16 << 12) + 64, s.stream>>>((double2 *)s.data, p);
+    B200_CUDA(cudaGetLastError());
+    return;
   }
   const int per_sm = kTB == 12 ? 2 : 4;
   const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms * per_sm);
@@ -422,7 +661,8 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
   if (any_pauli) {
     const size_t bytes = (size_t)nslots * s.nstates;
     void *hm = s.ensure_pinned(bytes);
-    dev_codes = (uint8_t *)s.ensure_scratch(bytes);
+    // + slack: the pipelined kernel's idle group reads (and discards) codes of up to 2 * grid tiles past the end
+    dev_codes = (uint8_t *)s.ensure_scratch(bytes + 1024);
     B200_CUDA(cudaStreamSynchronize(s.stream));
     memcpy(hm, codes_host, bytes);
     B200_CUDA(cudaMemcpyAsync(dev_codes, hm, bytes, cudaMemcpyHostToDevice, s.stream));

@@ -332,7 +332,7 @@ public:
   }
   void apply_diagonal_matrix(const reg_t &qubits, const cvector_t<double> &mat) {
     if (idle()) return;
-    if (batch_queueing() && qubits.size() <= 2 && mat.size() == (1ull << qubits.size())) {  // ride on the tile passes
+    if (ride_queue(qubits) && mat.size() == (1ull << qubits.size())) {  // ride on the tile passes
       const size_t dim = mat.size();
       std::vector<std::complex<double>> full(dim * dim, 0.0);
       for (size_t i = 0; i < dim; i++) full[i + dim * i] = mat[i];
@@ -347,17 +347,27 @@ public:
   }
   void apply_mcx(const reg_t &qubits) {
     if (idle()) return;
-    if (batch_queueing() && qubits.size() <= 2) {  // noisy batches: x / cx as dense gates share passes with the noise
+    if (ride_queue(qubits)) {  // x / cx as dense gates share HBM passes with their neighbours (and the sampled noise)
       static const std::complex<double> X[4] = {0, 1, 1, 0};
       static const std::complex<double> CX[16] = {1, 0, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 0};  // control = qubits[0]
       if (enqueue(qubits, qubits.size() == 1 ? X : CX, qubits.size() == 1 ? 4 : 16)) return;
     }
     for_target([&](b200sv_handle h) { ck(b200sv_apply_mcx(h, qubits.data(), (int)qubits.size())); });
   }
-  void apply_mcy(const reg_t &qubits) { for_target([&](b200sv_handle h) { ck(b200sv_apply_mcy(h, qubits.data(), (int)qubits.size())); }); }
+  void apply_mcy(const reg_t &qubits) {
+    if (idle()) return;
+    if (ride_queue(qubits)) {
+      const std::complex<double> I(0, 1);
+      const std::complex<double> Y[4] = {0, I, -I, 0};
+      std::complex<double> CY[16] = {};  // control = qubits[0], target = qubits[1]; column-major, index = q0 + 2 q1
+      CY[0] = 1; CY[2 + 4 * 2] = 1; CY[3 + 4 * 1] = I; CY[1 + 4 * 3] = -I;
+      if (enqueue(qubits, qubits.size() == 1 ? Y : CY, qubits.size() == 1 ? 4 : 16)) return;
+    }
+    for_target([&](b200sv_handle h) { ck(b200sv_apply_mcy(h, qubits.data(), (int)qubits.size())); });
+  }
   void apply_mcphase(const reg_t &qubits, const std::complex<double> phase) {
     if (idle()) return;
-    if (batch_queueing() && qubits.size() <= 2) {
+    if (ride_queue(qubits)) {
       std::complex<double> d[16] = {};
       const size_t dim = 1ull << qubits.size();
       for (size_t i = 0; i < dim; i++) d[i + dim * i] = 1.0;
@@ -368,11 +378,26 @@ public:
   }
   void apply_mcu(const reg_t &qubits, const cvector_t<double> &mat) {
     if (idle()) return;
-    // an uncontrolled, non-diagonal 2x2 is a plain 1-qubit matrix (qubitvector.hpp:1676-1680): queue it
-    if (qubits.size() == 1 && (batch_queueing() || !(mat[1] == 0.0 && mat[2] == 0.0)) && enqueue(qubits, mat.data(), mat.size())) return;
+    // an uncontrolled 2x2 is a plain 1-qubit matrix (qubitvector.hpp:1676-1680), a singly-controlled one a 4x4 with
+    // U in the control = 1 block: both ride on the gate queue
+    if (qubits.size() == 1 && (ride_queue(qubits) || !(mat[1] == 0.0 && mat[2] == 0.0)) && enqueue(qubits, mat.data(), mat.size())) return;
+    if (qubits.size() == 2 && mat.size() == 4 && ride_queue(qubits)) {
+      std::complex<double> CU[16] = {};  // control = qubits[0], target = qubits[1]; column-major, index = q0 + 2 q1
+      CU[0] = 1; CU[2 + 4 * 2] = 1;
+      for (int tr = 0; tr < 2; tr++)
+        for (int tc = 0; tc < 2; tc++) CU[(1 + 2 * tr) + 4 * (1 + 2 * tc)] = mat[tr + 2 * tc];
+      if (enqueue(qubits, CU, 16)) return;
+    }
     for_target([&](b200sv_handle h) { ck(b200sv_apply_mcu(h, qubits.data(), (int)qubits.size(), (const double *)mat.data())); });
   }
-  void apply_mcswap(const reg_t &qubits) { for_target([&](b200sv_handle h) { ck(b200sv_apply_mcswap(h, qubits.data(), (int)qubits.size())); }); }
+  void apply_mcswap(const reg_t &qubits) {
+    if (idle()) return;
+    if (qubits.size() == 2 && ride_queue(qubits)) {
+      static const std::complex<double> SWAP[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
+      if (enqueue(qubits, SWAP, 16)) return;
+    }
+    for_target([&](b200sv_handle h) { ck(b200sv_apply_mcswap(h, qubits.data(), (int)qubits.size())); });
+  }
   void apply_multi_swaps(const reg_t &qubits) {  // pairs of qubits, qubitvector.hpp:1843-1876
     for (size_t i = 0; i + 1 < qubits.size(); i += 2) apply_mcswap({qubits[i], qubits[i + 1]});
   }
@@ -591,6 +616,16 @@ protected:
   b200sv_handle Hs() const { return batch_ ? state_view(batch_pos_) : h_; }
   bool idle() const { return batch_ && batch_->on && batch_pos_ != 0; }
   bool batch_queueing() const { return batch_ && batch_->on && batch_->cond_reg < 0 && queue_enabled(); }
+  // may a <= 2-qubit special gate (x, cx, cy, cz/cp, swap, cu, small diagonal) be rewritten as a dense matrix and
+  // queued?  Yes when the flush runs tile passes (double precision, >= 12 qubits, all qubits local): the gate then
+  // shares an HBM pass with its neighbours instead of costing one of its own.
+  bool ride_queue(const reg_t &qubits) const {
+    if (!queue_enabled() || qubits.empty() || qubits.size() > 2) return false;
+    for (const auto q : qubits)
+      if (q >= num_qubits_) return false;
+    if (batch_) return batch_queueing();
+    return sizeof(data_t) == 8 && num_qubits_ >= 12;
+  }
   b200sv_handle state_view(size_t s) const {
     if (s == batch_pos_) {
       if (!view_) ck(b200sv_create_view(&view_, batch_->h, (int64_t)s, 1));

@@ -58,7 +58,8 @@ struct TileRound {
   uint8_t fast;                 // 2 / 1: exactly two / one dense 2-qubit gate(s), on round bits (0,1) [and (2,3)]:
                                 // straight-line code (LDS, DFMA and STS interleave, no form dispatch); 0: generic
   uint8_t form[kMaxRoundGates];  // 0..5: 2-qubit on round-bit pair; 6..9: 1-qubit on round bit (form-6);
-                                 // 10..13: per-state Pauli on round bit (form-10), code table slot in gate[]
+                                 // 10..13: per-state Pauli on round bit (form-10), code table slot in gate[];
+                                 // 14..19: DIAGONAL 2-qubit on round-bit pair (form-14 as 0..5); 20..23: diagonal 1-qubit
   uint16_t gate[kMaxRoundGates]; // index into mats (dense) or error-code slot (Pauli)
 };
 struct TilePassParams {
@@ -136,6 +137,30 @@ __device__ __forceinline__ void apply1(double2 (&a)[16], const double2 *__restri
   }
 }
 
+// diagonal gates (cz / cp / rzz / phase ...): one complex multiply per amplitude instead of 4 (2-qubit) or 2 (1-qubit)
+// complex FMAs.  m[0..3] (m[0..1]) = the diagonal, index = bit(P0) + 2 bit(P1).
+template <int P0, int P1>
+__device__ __forceinline__ void apply_diag2(double2 (&a)[16], const double2 *__restrict__ m) {
+  const double2 d0 = m[0], d1 = m[1], d2 = m[2], d3 = m[3];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int idx = ((i >> P0) & 1) | (((i >> P1) & 1) << 1);
+    const double2 d = idx == 0 ? d0 : idx == 1 ? d1 : idx == 2 ? d2 : d3;
+    const double2 x = a[i];
+    a[i] = mk<double>(d.x * x.x - d.y * x.y, d.x * x.y + d.y * x.x);
+  }
+}
+template <int P>
+__device__ __forceinline__ void apply_diag1(double2 (&a)[16], const double2 *__restrict__ m) {
+  const double2 d0 = m[0], d1 = m[1];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const double2 d = ((i >> P) & 1) ? d1 : d0;
+    const double2 x = a[i];
+    a[i] = mk<double>(d.x * x.x - d.y * x.y, d.x * x.y + d.y * x.x);
+  }
+}
+
 // per-state Pauli on round bit P (apply_pauli semantics, qubitvector.hpp:2393-2437: swap, Z sign, (-i)^num_y):
 // pure moves and sign flips.  `code` is uniform over the CTA (a tile never straddles two states).
 template <int P>
@@ -191,7 +216,7 @@ __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int
         for (int e = 0; e < 16; e++) a[e] = tile[base ^ R.eoff[e]];
         for (int k = 0; k < R.ngates; k++) {
           const int form = R.form[k];
-          if (form >= 10) {  // sampled noise: Pauli chosen per state (shot)
+          if (form >= 10 && form < 14) {  // sampled noise: Pauli chosen per state (shot)
             // uniform over the CTA; the lane-0 broadcast lets the compiler see that (keeps the dense gates below in
             // convergent control flow, i.e. their matrices on the uniform datapath)
             const int code = __shfl_sync(0xffffffffu, (int)p.codes[(size_t)R.gate[k] * p.nstates + (t >> p.state_shift)], 0);
@@ -216,7 +241,17 @@ __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int
           case 6: apply1<0>(a, m); break;
           case 7: apply1<1>(a, m); break;
           case 8: apply1<2>(a, m); break;
-          default: apply1<3>(a, m); break;
+          case 9: apply1<3>(a, m); break;
+          case 14: apply_diag2<0, 1>(a, m); break;
+          case 15: apply_diag2<0, 2>(a, m); break;
+          case 16: apply_diag2<0, 3>(a, m); break;
+          case 17: apply_diag2<1, 2>(a, m); break;
+          case 18: apply_diag2<1, 3>(a, m); break;
+          case 19: apply_diag2<2, 3>(a, m); break;
+          case 20: apply_diag1<0>(a, m); break;
+          case 21: apply_diag1<1>(a, m); break;
+          case 22: apply_diag1<2>(a, m); break;
+          default: apply_diag1<3>(a, m); break;
           }
         }
 #pragma unroll
@@ -381,6 +416,14 @@ struct QGate {
   int slot;           // error-code table slot for a per-state Pauli (kind 3)
 };
 
+static bool is_diag(const QGate &g) {
+  if (!g.mat) return false;
+  const int dim = 1 << g.nq;
+  for (int i = 0; i < dim; i++)
+    for (int j = 0; j < dim; j++)
+      if (i != j && (g.mat[2 * (i + dim * j)] != 0.0 || g.mat[2 * (i + dim * j) + 1] != 0.0)) return false;
+  return true;
+}
 static uint64_t qmask(const QGate &g) { return (1ull << g.q[0]) | (g.nq == 2 ? (1ull << g.q[1]) : 0); }
 
 // choose 3 group-id "lane" positions with independent swizzle vectors among the non-round positions
@@ -543,7 +586,7 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
         fast = (int)round_take[r].size();
         for (int li : round_take[r]) {
           const QGate &g = gates[sel[li]];
-          if (!g.mat || g.nq != 2) { fast = 0; break; }
+          if (!g.mat || g.nq != 2 || is_diag(g)) { fast = 0; break; }
           ordered.push_back(tile_pos(g.q[0]));
           ordered.push_back(tile_pos(g.q[1]));
         }
@@ -564,7 +607,22 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
         if (ndense >= kMaxTileGates) throw Error("tile pass: too many dense gates");
         const int mi = ndense++;
         double2 *M = p.mats[mi];
-        if (g.nq == 1) {
+        const bool diag = is_diag(g);
+        if (diag && g.nq == 1) {
+          const int b = round_bit_of(pos, tile_pos(g.q[0]));
+          for (int i = 0; i < 2; i++) M[i] = mk<double>(g.mat[2 * (i + 2 * i)], g.mat[2 * (i + 2 * i) + 1]);
+          R.form[R.ngates] = (uint8_t)(20 + b);
+        } else if (diag) {
+          int b0 = round_bit_of(pos, tile_pos(g.q[0])), b1 = round_bit_of(pos, tile_pos(g.q[1]));
+          const bool flip = b0 > b1;  // canonical: diagonal index bit0 <-> lower round bit
+          for (int i = 0; i < 4; i++) {
+            const int si = flip ? ((i >> 1) | ((i & 1) << 1)) : i;
+            M[i] = mk<double>(g.mat[2 * (si + 4 * si)], g.mat[2 * (si + 4 * si) + 1]);
+          }
+          if (flip) std::swap(b0, b1);
+          static const int form_of[4][4] = {{-1, 0, 1, 2}, {-1, -1, 3, 4}, {-1, -1, -1, 5}, {-1, -1, -1, -1}};
+          R.form[R.ngates] = (uint8_t)(14 + form_of[b0][b1]);
+        } else if (g.nq == 1) {
           const int b = round_bit_of(pos, tile_pos(g.q[0]));
           for (int i = 0; i < 2; i++)
             for (int j = 0; j < 2; j++) M[i * 2 + j] = mk<double>(g.mat[2 * (i + 2 * j)], g.mat[2 * (i + 2 * j) + 1]);

@@ -42,19 +42,24 @@ def test_qv_circuit_gpu_equals_cpu_through_the_reference_controller(n, fusion, f
     assert np.array_equal(_counts(gpu, n), _counts(cpu, n))  # same seed -> identical sampled counts
 
 
-def test_named_gates_qft_and_measure_reset():
+@pytest.mark.parametrize("n", [9, 13])
+def test_named_gates_qft_and_measure_reset(n):
     """Gate table of Statevector::State (statevector_state.hpp:314-384) on the B200 vector, plus
-    mid-circuit measure / reset (apply_measure :936-1014 -> probabilities + diagonal/permutation)."""
+    mid-circuit measure / reset (apply_measure :936-1014 -> probabilities + diagonal/permutation).
+    n = 13 reaches the tile engine: x / cx / cy / cz / cp / swap / cu are rewritten as (diagonal) 4x4 gates
+    and ride on the adapter's gate queue."""
     from qiskit_aer_b200 import circuits
     be = _backend()
-    n = 9
     ops = circuits.qft(n)
     extra = [("gate", "ccx", [0, 1, 2], []), ("gate", "cswap", [3, 4, 5], []), ("gate", "y", [6], []),
              ("gate", "cy", [6, 7], []), ("gate", "cz", [1, 8], []), ("gate", "t", [2], []),
              ("gate", "rx", [3], [0.3]), ("gate", "ry", [4], [1.1]), ("gate", "rz", [5], [0.7]),
              ("gate", "rxx", [0, 8], [0.4]), ("gate", "rzz", [1, 7], [0.9]), ("gate", "u", [2], [0.1, 0.2, 0.3]),
              ("gate", "sdg", [3], []), ("gate", "sx", [4], []), ("gate", "ecr", [5, 6], []),
-             ("gate", "mcp", [0, 3, 6], [0.5]), ("gate", "cu", [7, 8], [0.3, 0.2, 0.1, 0.4])]
+             ("gate", "mcp", [0, 3, 6], [0.5]), ("gate", "cu", [7, 8], [0.3, 0.2, 0.1, 0.4]),
+             ("gate", "cx", [n - 1, 0], []), ("gate", "swap", [n - 2, 1], []), ("gate", "cy", [2, n - 1], []),
+             ("gate", "x", [n - 1], []), ("gate", "cp", [n - 1, 3], [0.8]), ("gate", "cu", [n - 2, n - 1], [0.7, 0.1, 0.9, 0.2]),
+             ("gate", "p", [n - 1], [0.33]), ("gate", "z", [n - 2], []), ("gate", "s", [0], [])]
     ops = [("gate", "h", [q], []) for q in range(n)] + ops + extra
     kw = dict(shots=500, seed=5, fusion=False, save_statevector=True)
     gpu = be.run_circuit(n, ops, device="GPU", **kw)

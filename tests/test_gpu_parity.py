@@ -389,7 +389,10 @@ def test_gate_sequence_tile_passes(n):
                 qs = [int(q) for q in rng.choice(4, size=k, replace=False) + (n - 4)]
             else:
                 qs = opgen.pick(rng, n, k)
-            gates.append((qs, opgen.colmajor(opgen.haar_unitary(rng, 1 << k))))
+            if rng.random() < 0.3:  # diagonal gates (cz / cp / rzz / phase) take the one-multiply tile forms
+                gates.append((qs, opgen.colmajor(np.diag(np.exp(1j * rng.uniform(0, 2 * np.pi, 1 << k))))))
+            else:
+                gates.append((qs, opgen.colmajor(opgen.haar_unitary(rng, 1 << k))))
         ora, gpu = OracleQV(n), gpu_qv(n)
         ora.set_state(psi0)
         gpu.set_state(psi0)

@@ -408,6 +408,73 @@ tile_pipe_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
+// ------------------------------------------------------------------------------------------ pipelined variant 2
+// Same three-buffer rotation, but the tile traffic is taken off the compute groups altogether: four extra warps
+// (threads 512..639; registers are handed out to warps four at a time, so 20 warps x 96 registers is the fit) stream every finished tile out and the tile three positions later in, so the 16 compute warps
+// only ever wait on barriers, read/write shared memory and issue DFMA.  Hand-offs: full[b] (128 cp.async arrivals)
+// memory -> compute, done[b] (256 arrivals) compute -> memory.
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int MODE>
+__global__ void __maxnreg__(96) tile_pipe2_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassParams p) {
+  constexpr int kLoBits = 8;
+  extern __shared__ __align__(16) double2 tiles[];
+  uint64_t *full = reinterpret_cast<uint64_t *>(tiles + kPipeBufs * 4096);
+  uint64_t *done = full + kPipeBufs;
+  // lane-0 broadcasts: warp-uniform role / group ids the compiler can see (uniform branches, uniform datapath)
+  const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  if (threadIdx.x == 0)
+    for (int b = 0; b < kPipeBufs; b++) { mbar_init(&full[b], 128); mbar_init(&done[b], 256); }
+  __syncthreads();
+  const int K = (int)((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // tiles of this CTA
+  if (wid >= 16) {
+    // ---- memory warps: thread mt moves tile-local amplitudes j = mt + 128 i
+    const int mt = threadIdx.x - 512;
+    uint64_t glo = 0;
+#pragma unroll
+    for (int u = 0; u < 7; u++)
+      if ((mt >> u) & 1) glo |= p.goff_lo[u];
+    const uint32_t slo = phys_slot((uint32_t)mt);
+    auto goff = [&](int i) { return ((i & 1) ? p.goff_lo[7] : 0) | p.goff_hi[i >> 1]; };
+    auto soff = [&](int i) { return phys_slot((uint32_t)(i & 1) << 7) ^ (uint32_t)p.soff_hi[i >> 1]; };
+    auto load = [&](int k) {
+      double2 *buf = tiles + (k % kPipeBufs) * 4096;
+      const double2 *gt = psi + (insert_zeros(blockIdx.x + (uint64_t)k * gridDim.x, p.ins) | glo);
+#pragma unroll 16
+      for (int i = 0; i < 32; i++) cp_async16_ordered(&buf[slo ^ soff(i)], gt + goff(i));
+      mbar_arrive_cp_async(&full[k % kPipeBufs]);
+    };
+    for (int k = 0; k < kPipeBufs && k < K; k++) load(k);
+    for (int k = 0; k < K; k++) {
+      mbar_wait(&done[k % kPipeBufs], (uint32_t)((k / kPipeBufs) & 1));
+      double2 *buf = tiles + (k % kPipeBufs) * 4096;
+      double2 *gt = psi + (insert_zeros(blockIdx.x + (uint64_t)k * gridDim.x, p.ins) | glo);
+#pragma unroll 16
+      for (int i = 0; i < 32; i++) gt[goff(i)] = buf[slo ^ soff(i)];
+      if (k + kPipeBufs < K) load(k + kPipeBufs);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    return;
+  }
+  // ---- compute groups
+  const int grp = wid >> 3, tid = threadIdx.x & 255;
+  for (int kk = 0; 2 * kk < K; kk++) {
+    const int k = 2 * kk + grp;
+    const bool valid = k < K;
+    const uint64_t t = blockIdx.x + (uint64_t)k * gridDim.x;
+    double2 *tile = tiles + (k % kPipeBufs) * 4096;
+    if (valid) {
+      // order the parity tests: tile k - 3 (other group) left this buffer => full[] is in tile k's phase or past it
+      if (k >= kPipeBufs) mbar_wait(&done[k % kPipeBufs], (uint32_t)(((k - kPipeBufs) / kPipeBufs) & 1));
+      mbar_wait(&full[k % kPipeBufs], (uint32_t)((k / kPipeBufs) & 1));
+    }
+    run_rounds<1, kLoBits, MODE>(tile, tid, t, p, grp, valid);
+    if (valid) mbar_arrive(&done[k % kPipeBufs]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host scheduler
 struct QGate {
   int nq;
@@ -482,7 +549,8 @@ static int round_bit_of(const std::vector<int> &sorted_pos, int tile_pos) {
 }
 
 // One pass: gates[sel] all fit the tile; tile_bits sorted global positions (kTB of them).
-static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::vector<int> &sel,
+// Returns the entries of `sel` that did not fit (round or matrix-slot budget): the caller re-queues them.
+static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates, const std::vector<int> &sel,
                           const std::vector<int> &tile_bits, const uint8_t *dev_codes, int kTB) {
   const int kLoBits = kTB - 4;
   static thread_local TilePassParams p;
@@ -512,14 +580,27 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
   std::vector<int> rem(sel.size());
   for (size_t i = 0; i < sel.size(); i++) rem[i] = (int)i;  // indices into sel
   std::vector<std::vector<int>> round_take, round_pos;
+  // A round that starts with a dense (non-diagonal) 2-qubit gate stays "fast": at most one more such gate on two
+  // other qubits joins it (straight-line code, no form dispatch, no register shuffling at the dispatch joins);
+  // further gates on the same qubits go to the next round, which costs one warp-local shared-memory round trip --
+  // cheaper than the generic dispatch.  Rounds that start with a 1-qubit / diagonal / Pauli op are generic.
+  static const int env_prefer_fast = [] { const char *e = getenv("B200SV_TILE_PREFER_FAST"); return e ? atoi(e) : 1; }();
+  auto fast_eligible = [&](const QGate &g) { return g.mat && g.nq == 2 && !is_diag(g); };
+  std::vector<int> leftover;
   while (!rem.empty()) {
-    if ((int)round_take.size() >= kMaxRounds) throw Error("tile pass: too many rounds");
+    if ((int)round_take.size() >= kMaxRounds) {  // out of rounds: hand the rest back
+      for (int li : rem) leftover.push_back(sel[li]);
+      break;
+    }
     uint64_t rq = 0, blocked = 0;
     std::vector<int> take, rest;
+    bool fast_round = false;
     for (int li : rem) {
       const QGate &g = gates[sel[li]];
       const uint64_t m = qmask(g);
       if ((m & blocked) || (int)take.size() >= kMaxRoundGates) { blocked |= m; rest.push_back(li); continue; }
+      if (take.empty()) fast_round = env_prefer_fast && fast_eligible(g);
+      else if (fast_round && (!fast_eligible(g) || (m & rq) || take.size() >= 2)) { blocked |= m; rest.push_back(li); continue; }
       if (__builtin_popcountll(rq | m) <= kRoundBits) { rq |= m; take.push_back(li); }
       else { blocked |= m; rest.push_back(li); }
     }
@@ -654,21 +735,34 @@ static void run_tile_pass(State &s, const std::vector<QGate> &gates, const std::
                                    kPipeBufs * (16 << 12) + 64));
     attr_set = true;
   }
-  static const int env_pipe = [] { const char *e = getenv("B200SV_TILE_PIPE"); return e ? atoi(e) : 1; }();
+  static const int env_pipe = [] { const char *e = getenv("B200SV_TILE_PIPE"); return e ? atoi(e) : 2; }();
+  bool all_fast = true;
+  for (int r = 0; r < p.nrounds; r++) all_fast = all_fast && p.rounds[r].fast;
+  if (kTB == 12 && env_pipe == 2 && all_fast) {  // memory-warp variant: fast-only code fits its 112-register budget
+    static bool attr2 = false;
+    const int smem2 = kPipeBufs * (16 << 12) + 64;
+    if (!attr2) {
+      B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      attr2 = true;
+    }
+    const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms);
+    tile_pipe2_kernel<1><<<grid, 640, smem2, s.stream>>>((double2 *)s.data, p);
+    B200_CUDA(cudaGetLastError());
+    return leftover;
+  }
   if (kTB == 12 && env_pipe) {
     const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms);
-    bool all_fast = true;
-    for (int r = 0; r < p.nrounds; r++) all_fast = all_fast && p.rounds[r].fast;
     if (all_fast) tile_pipe_kernel<1><<<grid, 512, kPipeBufs * (16 << 12) + 64, s.stream>>>((double2 *)s.data, p);
     else tile_pipe_kernel<2><<<grid, 512, kPipeBufs * (16 << 12) + 64, s.stream>>>((double2 *)s.data, p);
     B200_CUDA(cudaGetLastError());
-    return;
+    return leftover;
   }
   const int per_sm = kTB == 12 ? 2 : 4;
   const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms * per_sm);
   if (kTB == 12) tile_pass_kernel<12><<<grid, 256, 16 << 12, s.stream>>>((double2 *)s.data, p);
   else tile_pass_kernel<11><<<grid, 128, 16 << 11, s.stream>>>((double2 *)s.data, p);
   B200_CUDA(cudaGetLastError());
+  return leftover;
 }
 
 // Partition an op sequence into tile passes (in-order greedy with dependency blocking) and run them.
@@ -753,8 +847,12 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
     std::vector<int> tile_bits;
     for (int q = 0; q < 64; q++)
       if ((Q >> q) & 1) tile_bits.push_back(q);
-    run_tile_pass(s, gates, sel, tile_bits, dev_codes, kTB);
+    const std::vector<int> back = run_tile_pass(s, gates, sel, tile_bits, dev_codes, kTB);
     passes++;
+    if (!back.empty()) {  // deferred ops commute with everything earlier that is still queued: program order is safe
+      rest.insert(rest.end(), back.begin(), back.end());
+      std::sort(rest.begin(), rest.end());
+    }
     rem.swap(rest);
   }
   return passes;

@@ -181,7 +181,9 @@ __device__ __forceinline__ void apply_pauli_reg(double2 (&a)[16], int code) {
 // MODE 0: fast and generic rounds; 1: every round of the pass is fast; 2: generic code only (fast rounds carry
 // generic forms too).  The pipelined kernel is instantiated per mode: with both code paths in one kernel ptxas
 // runs out of uniform registers and demotes the generic path's matrix operands to vector registers.
-template <int GROUPED, int kLoBits, int MODE>
+// LASTSYNC = false: no barrier after the final round (the caller hands the tile over through an mbarrier that every
+// thread arrives on, so the warps of a group may drift apart across tiles).
+template <int GROUPED, int kLoBits, int MODE, bool LASTSYNC = true>
 __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int tid, const uint64_t t,
                                            const TilePassParams &p, const int grp, const bool valid) {
   for (int r = 0; r < p.nrounds; r++) {
@@ -259,7 +261,7 @@ __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int
           if (valid) tile[base ^ R.eoff[e]] = a[e];
       }
     }
-    if (R.sync) {
+    if (R.sync && (LASTSYNC || r + 1 < p.nrounds)) {
       if (GROUPED) {
         if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
         else asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -408,6 +410,90 @@ tile_pipe_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
   asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
+// ------------------------------------------------------------------------------------------ single precision
+// float2 amplitudes are 8 bytes: a 16-byte swizzle slot holds the two amplitudes that differ in global qubit 0, so
+// the whole staging / buffer-rotation machinery above is reused unchanged on the state seen as 2^(n-1) 16-byte
+// elements (tile = 2^12 slots = 2^13 amplitudes).  A thread's 16 slots are a 5-bit block: bit 0 = global qubit 0,
+// bits 1..4 = the round's slot positions.  Rounds are straight-line only: gate A on bits (1,2) -- or (0,1) when it
+// involves qubit 0 -- and optionally gate B on bits (3,4); the host promotes 1-qubit gates to 4x4.
+template <int P0, int P1>
+__device__ __forceinline__ void apply2f(float2 (&a)[32], const float2 *__restrict__ m) {
+  float2 mm[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) mm[i] = m[i];
+#pragma unroll
+  for (int o = 0; o < 8; o++) {
+    int base = 0, ob = 0;
+#pragma unroll
+    for (int b = 0; b < 5; b++)
+      if (b != P0 && b != P1) {
+        if ((o >> ob) & 1) base |= 1 << b;
+        ob++;
+      }
+    const int i0 = base, i1 = base | (1 << P0), i2 = base | (1 << P1), i3 = base | (1 << P0) | (1 << P1);
+    const float2 x0 = a[i0], x1 = a[i1], x2 = a[i2], x3 = a[i3];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      float2 acc = mk<float>(0, 0);
+      cfma(acc, mm[r * 4 + 0], x0);
+      cfma(acc, mm[r * 4 + 1], x1);
+      cfma(acc, mm[r * 4 + 2], x2);
+      cfma(acc, mm[r * 4 + 3], x3);
+      a[r == 0 ? i0 : r == 1 ? i1 : r == 2 ? i2 : i3] = acc;
+    }
+  }
+}
+
+// R.fast: 1 = A on bits (1,2); 2 = A on (1,2) + B on (3,4); 3 = A on (0,1); 4 = A on (0,1) + B on (3,4)
+__device__ __forceinline__ void run_rounds_f32(double2 *__restrict__ tile, const int tid, const TilePassParams &p,
+                                               const int grp, const bool valid) {
+  for (int r = 0; r < p.nrounds; r++) {
+    const TileRound &R = p.rounds[r];
+    uint32_t base = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if ((tid >> i) & 1) base ^= R.gbit[i];
+    const float2 *mA = reinterpret_cast<const float2 *>(p.mats[R.gate[0]]);
+    const float2 *mB = reinterpret_cast<const float2 *>(p.mats[R.gate[1]]);
+    const int kind = R.fast;
+    float2 a[32];
+#define B200_F32_LOAD                                                                  \
+  _Pragma("unroll") for (int e = 0; e < 16; e++) {                                     \
+    const float4 v = *reinterpret_cast<const float4 *>(&tile[base ^ R.eoff[e]]);       \
+    a[2 * e] = make_float2(v.x, v.y);                                                  \
+    a[2 * e + 1] = make_float2(v.z, v.w);                                              \
+  }
+#define B200_F32_STORE                                                                                           \
+  _Pragma("unroll") for (int e = 0; e < 16; e++) if (valid)                                                      \
+      *reinterpret_cast<float4 *>(&tile[base ^ R.eoff[e]]) = make_float4(a[2 * e].x, a[2 * e].y, a[2 * e + 1].x, a[2 * e + 1].y);
+    if (kind == 2) {
+      B200_F32_LOAD
+      apply2f<1, 2>(a, mA);
+      apply2f<3, 4>(a, mB);
+      B200_F32_STORE
+    } else if (kind == 1) {
+      B200_F32_LOAD
+      apply2f<1, 2>(a, mA);
+      B200_F32_STORE
+    } else if (kind == 4) {
+      B200_F32_LOAD
+      apply2f<0, 1>(a, mA);
+      apply2f<3, 4>(a, mB);
+      B200_F32_STORE
+    } else {
+      B200_F32_LOAD
+      apply2f<0, 1>(a, mA);
+      B200_F32_STORE
+    }
+#undef B200_F32_LOAD
+#undef B200_F32_STORE
+    if (R.sync && r + 1 < p.nrounds) {
+      if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
+      else asm volatile("bar.sync 1, 256;" ::: "memory");
+    } else __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ pipelined variant 2
 // Same three-buffer rotation, but the tile traffic is taken off the compute groups altogether: four extra warps
 // (threads 512..639; registers are handed out to warps four at a time, so 20 warps x 96 registers is the fit) stream every finished tile out and the tile three positions later in, so the 16 compute warps
@@ -417,6 +503,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+// MODE 1: double precision, fast rounds; MODE 3: single precision (psi = the state as 16-byte slots)
 template <int MODE>
 __global__ void __maxnreg__(96) tile_pipe2_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassParams p) {
   constexpr int kLoBits = 8;
@@ -470,8 +557,9 @@ __global__ void __maxnreg__(96) tile_pipe2_kernel(double2 *__restrict__ psi, con
       if (k >= kPipeBufs) mbar_wait(&done[k % kPipeBufs], (uint32_t)(((k - kPipeBufs) / kPipeBufs) & 1));
       mbar_wait(&full[k % kPipeBufs], (uint32_t)((k / kPipeBufs) & 1));
     }
-    run_rounds<1, kLoBits, MODE>(tile, tid, t, p, grp, valid);
-    if (valid) mbar_arrive(&done[k % kPipeBufs]);
+    if (MODE == 3) run_rounds_f32(tile, tid, p, grp, valid);
+    else run_rounds<1, kLoBits, MODE == 3 ? 1 : MODE, false>(tile, tid, t, p, grp, valid);
+    if (valid) mbar_arrive(&done[k % kPipeBufs]);  // release: this thread's shared-memory writes are visible to the waiter
   }
 }
 
@@ -548,6 +636,61 @@ static int round_bit_of(const std::vector<int> &sorted_pos, int tile_pos) {
   return -1;
 }
 
+// Segments: maximal runs of rounds that leave >= nW = kTB - 9 tile positions untouched; those become the warp-id
+// positions of the whole run, which makes the run warp-local (no CTA barrier inside).  round_w[r] = warp positions
+// of round r (sorted), seg_end[r] = one past the last round of r's segment.  B200SV_TILE_WARP_LOCAL=0 disables.
+static void plan_segments(const std::vector<std::vector<int>> &round_pos, int kTB, std::vector<std::vector<int>> &round_w,
+                          std::vector<int> &seg_end) {
+  static const int env_wl = [] { const char *e = getenv("B200SV_TILE_WARP_LOCAL"); return e ? atoi(e) : 1; }();
+  const int nW = kTB - 9, nr = (int)round_pos.size();
+  round_w.assign(nr, {});
+  seg_end.assign(nr, 0);
+  for (int r0 = 0; r0 < nr;) {
+    uint32_t touched = 0;
+    int r1 = r0;
+    while (r1 < nr) {
+      uint32_t t2 = touched;
+      for (int u : round_pos[r1]) t2 |= 1u << u;
+      if (r1 > r0 && (!env_wl || kTB - __builtin_popcount(t2) < nW)) break;
+      touched = t2;
+      r1++;
+    }
+    std::vector<int> cand;
+    for (int u = 0; u < kTB; u++)
+      if (!((touched >> u) & 1)) cand.push_back(u);
+    // choose the warp positions that leave conflict-free lane triples in the most rounds (prefer high positions)
+    std::vector<int> best;
+    int best_ok = -1;
+    const int nc = (int)cand.size();
+    for (int a = nc - 1; a >= nW - 1; a--)
+      for (int b = (nW >= 2 ? a - 1 : -1); b >= (nW >= 2 ? nW - 2 : -1); b--)
+        for (int c = (nW >= 3 ? b - 1 : -1); c >= (nW >= 3 ? 0 : -1); c--) {
+          std::vector<int> w;
+          w.push_back(cand[a]);
+          if (nW >= 2) w.push_back(cand[b]);
+          if (nW >= 3) w.push_back(cand[c]);
+          int ok = 0;
+          for (int r = r0; r < r1; r++) {
+            std::vector<int> pos = round_pos[r];
+            for (int u = kTB - 1; (int)pos.size() < kRoundBits && u >= 0; u--)
+              if (std::find(pos.begin(), pos.end(), u) == pos.end() && std::find(w.begin(), w.end(), u) == w.end())
+                pos.push_back(u);
+            std::vector<int> fp;
+            for (int u = 0; u < kTB; u++)
+              if (std::find(pos.begin(), pos.end(), u) == pos.end() && std::find(w.begin(), w.end(), u) == w.end())
+                fp.push_back(u);
+            int lane[3];
+            ok += pick_lane_positions(fp, lane);
+          }
+          if (ok > best_ok) { best_ok = ok; best = w; }
+          if (nW < 3) break;
+        }
+    std::sort(best.begin(), best.end());
+    for (int r = r0; r < r1; r++) { round_w[r] = best; seg_end[r] = r1; }
+    r0 = r1;
+  }
+}
+
 // One pass: gates[sel] all fit the tile; tile_bits sorted global positions (kTB of them).
 // Returns the entries of `sel` that did not fit (round or matrix-slot budget): the caller re-queues them.
 static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates, const std::vector<int> &sel,
@@ -611,52 +754,15 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
     round_pos.push_back(rpos);
     rem.swap(rest);
   }
-  // segments: maximal runs of rounds that leave >= nW tile positions untouched; those become the warp-id positions
-  // of the whole run, which makes the run warp-local (no CTA barrier inside).  B200SV_TILE_WARP_LOCAL=0 disables.
-  static const int env_wl = [] { const char *e = getenv("B200SV_TILE_WARP_LOCAL"); return e ? atoi(e) : 1; }();
-  const int nW = kTB - 9, nr = (int)round_take.size();
+  // segments of warp-local rounds and their warp-id positions
+  const int nr = (int)round_take.size();
   p.nrounds = nr;
+  std::vector<std::vector<int>> round_w;
+  std::vector<int> seg_end;
+  plan_segments(round_pos, kTB, round_w, seg_end);
   for (int r0 = 0; r0 < nr;) {
-    uint32_t touched = 0;
-    int r1 = r0;
-    while (r1 < nr) {
-      uint32_t t2 = touched;
-      for (int u : round_pos[r1]) t2 |= 1u << u;
-      if (r1 > r0 && (!env_wl || kTB - __builtin_popcount(t2) < nW)) break;
-      touched = t2;
-      r1++;
-    }
-    std::vector<int> cand;
-    for (int u = 0; u < kTB; u++)
-      if (!((touched >> u) & 1)) cand.push_back(u);
-    // choose the warp positions that leave conflict-free lane triples in the most rounds (prefer high positions)
-    std::vector<int> best;
-    int best_ok = -1;
-    const int nc = (int)cand.size();
-    for (int a = nc - 1; a >= nW - 1; a--)
-      for (int b = (nW >= 2 ? a - 1 : -1); b >= (nW >= 2 ? nW - 2 : -1); b--)
-        for (int c = (nW >= 3 ? b - 1 : -1); c >= (nW >= 3 ? 0 : -1); c--) {
-          std::vector<int> w;
-          w.push_back(cand[a]);
-          if (nW >= 2) w.push_back(cand[b]);
-          if (nW >= 3) w.push_back(cand[c]);
-          int ok = 0;
-          for (int r = r0; r < r1; r++) {
-            std::vector<int> pos = round_pos[r];
-            for (int u = kTB - 1; (int)pos.size() < kRoundBits && u >= 0; u--)
-              if (std::find(pos.begin(), pos.end(), u) == pos.end() && std::find(w.begin(), w.end(), u) == w.end())
-                pos.push_back(u);
-            std::vector<int> fp;
-            for (int u = 0; u < kTB; u++)
-              if (std::find(pos.begin(), pos.end(), u) == pos.end() && std::find(w.begin(), w.end(), u) == w.end())
-                fp.push_back(u);
-            int lane[3];
-            ok += pick_lane_positions(fp, lane);
-          }
-          if (ok > best_ok) { best_ok = ok; best = w; }
-          if (nW < 3) break;
-        }
-    std::sort(best.begin(), best.end());
+    const int r1 = seg_end[r0];
+    const std::vector<int> &best = round_w[r0];
     for (int r = r0; r < r1; r++) {
       TileRound &R = p.rounds[r];
       // fast round: one or two disjoint dense 2-qubit gates -> round bits (0,1) and (2,3) in gate-qubit order
@@ -765,6 +871,165 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
   return leftover;
 }
 
+// ------------------------------------------------------------------------------------------ single-precision passes
+// One pass over a float state: tile_bits = 13 sorted global positions, tile_bits[0] == 0 (global qubit 0 lives inside
+// the 16-byte slot).  Slot space: slot bit u <-> tile_bits[u + 1].  Returns the gates that did not fit.
+static std::vector<int> run_tile_pass_f32(State &s, const std::vector<QGate> &gates, const std::vector<int> &sel,
+                                          const std::vector<int> &tile_bits) {
+  constexpr int kSB = 12;  // slot bits
+  static thread_local TilePassParams p;
+  p.ntiles = s.total_amps() >> (kSB + 1);
+  p.codes = nullptr;
+  p.nstates = (uint64_t)s.nstates;
+  p.state_shift = s.nq - (kSB + 1);
+  p.prefetch = 0;
+  p.ins.n = kSB;
+  for (int u = 0; u < kSB; u++) p.ins.pos[u] = (uint8_t)(tile_bits[u + 1] - 1);
+  for (int u = 0; u < 8; u++) p.goff_lo[u] = 1ull << (tile_bits[u + 1] - 1);
+  for (int m = 0; m < kHiCount; m++) {
+    uint64_t go = 0;
+    for (int b = 0; b < 4; b++)
+      if ((m >> b) & 1) go |= 1ull << (tile_bits[8 + b + 1] - 1);
+    p.goff_hi[m] = go;
+    p.soff_hi[m] = (uint16_t)phys_slot((uint32_t)m << 8);
+  }
+  auto slot_pos = [&](int q) {  // -1: global qubit 0 (inside the slot)
+    for (int u = 0; u <= kSB; u++)
+      if (tile_bits[u] == q) return u - 1;
+    throw Error("tile pass: qubit not in tile");
+  };
+  // rounds: gate A (any), optionally gate B on two other slot positions (B never involves qubit 0)
+  struct FRound { int a = -1, b = -1; };
+  std::vector<FRound> frounds;
+  std::vector<std::vector<int>> round_pos;
+  std::vector<int> rem(sel.begin(), sel.end()), leftover;
+  int ndense = 0;
+  while (!rem.empty()) {
+    if ((int)frounds.size() >= kMaxRounds || ndense + 2 > kMaxTileGates) { leftover = rem; break; }
+    FRound fr;
+    uint64_t rq = 0, blocked = 0;
+    std::vector<int> rest;
+    for (int gi : rem) {
+      const QGate &g = gates[gi];
+      const uint64_t m = qmask(g);
+      if (m & blocked) { blocked |= m; rest.push_back(gi); continue; }
+      if (fr.a < 0) { fr.a = gi; rq |= m; }
+      else if (fr.b < 0 && !(m & 1ull) && !(m & rq)) { fr.b = gi; rq |= m; }
+      else { blocked |= m; rest.push_back(gi); }
+    }
+    std::vector<int> rp;
+    for (int q = 1; q < 64; q++)
+      if ((rq >> q) & 1) rp.push_back(slot_pos(q));
+    frounds.push_back(fr);
+    round_pos.push_back(rp);
+    ndense += 1 + (fr.b >= 0);
+    rem.swap(rest);
+  }
+  const int nr = (int)frounds.size();
+  p.nrounds = nr;
+  std::vector<std::vector<int>> round_w;
+  std::vector<int> seg_end;
+  plan_segments(round_pos, kSB, round_w, seg_end);
+  int nm = 0;
+  auto put_matrix = [&](const QGate &g, bool q0_is_low_round_bit) {
+    // 4x4 row-major float2, matrix bit 0 <-> lower round bit; 1-qubit gates become (identity on the pad bit) x U
+    float2 *M = reinterpret_cast<float2 *>(p.mats[nm]);
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) {
+        double re, im;
+        if (g.nq == 1) {
+          const bool same_hi = (i >> 1) == (j >> 1);
+          re = same_hi ? g.mat[2 * ((i & 1) + 2 * (j & 1))] : 0.0;
+          im = same_hi ? g.mat[2 * ((i & 1) + 2 * (j & 1)) + 1] : 0.0;
+        } else {
+          const int si = q0_is_low_round_bit ? i : ((i >> 1) | ((i & 1) << 1));
+          const int sj = q0_is_low_round_bit ? j : ((j >> 1) | ((j & 1) << 1));
+          re = g.mat[2 * (si + 4 * sj)];
+          im = g.mat[2 * (si + 4 * sj) + 1];
+        }
+        M[i * 4 + j] = make_float2((float)re, (float)im);
+      }
+    return nm++;
+  };
+  for (int r = 0; r < nr; r++) {
+    const FRound &fr = frounds[r];
+    const QGate &A = gates[fr.a];
+    const std::vector<int> &w = round_w[r];
+    auto has = [](const std::vector<int> &v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+    std::vector<int> pads;  // unused slot positions outside the warp positions, highest first
+    for (int u = kSB - 1; u >= 0; u--)
+      if (!has(round_pos[r], u) && !has(w, u)) pads.push_back(u);
+    size_t np = 0;
+    std::vector<int> ordered(4);
+    TileRound &R = p.rounds[r];
+    const bool a_has0 = (qmask(A) & 1ull) != 0;
+    bool a_q0_low;
+    if (a_has0) {  // bits (0,1): qubit 0 and the other qubit (or a pad for a 1-qubit gate on qubit 0)
+      if (A.nq == 1) { ordered[0] = pads[np++]; a_q0_low = true; }
+      else { ordered[0] = slot_pos(A.q[0] == 0 ? A.q[1] : A.q[0]); a_q0_low = A.q[0] == 0; }
+      ordered[1] = pads[np++];
+    } else {       // bits (1,2)
+      ordered[0] = slot_pos(A.q[0]);
+      ordered[1] = A.nq == 2 ? slot_pos(A.q[1]) : pads[np++];
+      a_q0_low = true;
+    }
+    if (fr.b >= 0) {
+      const QGate &B = gates[fr.b];
+      ordered[2] = slot_pos(B.q[0]);
+      ordered[3] = B.nq == 2 ? slot_pos(B.q[1]) : pads[np++];
+    } else {
+      ordered[2] = pads[np++];
+      ordered[3] = pads[np++];
+    }
+    build_round(R, ordered, w, kSB, true);
+    R.sync = (r == seg_end[r] - 1);
+    R.fast = (uint8_t)((a_has0 ? 3 : 1) + (fr.b >= 0 ? 1 : 0));
+    R.gate[0] = (uint16_t)put_matrix(A, a_q0_low);
+    R.gate[1] = fr.b >= 0 ? (uint16_t)put_matrix(gates[fr.b], true) : R.gate[0];
+    R.ngates = (uint8_t)(1 + (fr.b >= 0));
+  }
+  static bool attr = false;
+  const int smem = kPipeBufs * (16 << 12) + 64;
+  if (!attr) {
+    B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms);
+  tile_pipe2_kernel<3><<<grid, 640, smem, s.stream>>>((double2 *)s.data, p);
+  B200_CUDA(cudaGetLastError());
+  return leftover;
+}
+
+// float states: partition into passes over 13-bit tiles (the 4 lowest global bits are always in the tile: 128-byte runs)
+static int apply_gate_sequence_f32(State &s, const std::vector<QGate> &gates) {
+  constexpr int kTBf = 13;
+  std::vector<int> rem(gates.size());
+  for (size_t i = 0; i < gates.size(); i++) rem[i] = (int)i;
+  int passes = 0;
+  while (!rem.empty()) {
+    uint64_t Q = 0xF, blocked = 0;
+    std::vector<int> sel, rest;
+    for (int i : rem) {
+      const uint64_t m = qmask(gates[i]);
+      if ((m & blocked) || (int)sel.size() >= kMaxTileGates) { blocked |= m; rest.push_back(i); continue; }
+      if (__builtin_popcountll(Q | m) <= kTBf) { Q |= m; sel.push_back(i); }
+      else { blocked |= m; rest.push_back(i); }
+    }
+    for (int q = 0; q < s.nq && __builtin_popcountll(Q) < kTBf; q++) Q |= 1ull << q;
+    std::vector<int> tile_bits;
+    for (int q = 0; q < 64; q++)
+      if ((Q >> q) & 1) tile_bits.push_back(q);
+    const std::vector<int> back = run_tile_pass_f32(s, gates, sel, tile_bits);
+    passes++;
+    if (!back.empty()) {
+      rest.insert(rest.end(), back.begin(), back.end());
+      std::sort(rest.begin(), rest.end());
+    }
+    rem.swap(rest);
+  }
+  return passes;
+}
+
 // Partition an op sequence into tile passes (in-order greedy with dependency blocking) and run them.
 // kind[i]: 1 = dense 1-qubit, 2 = dense 2-qubit, 3 = per-state Pauli on one qubit (code table slot[i]).
 // Returns the number of HBM passes used.
@@ -792,6 +1057,8 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
   // B200SV_TILE_BITS = 11 | 12 selects the tile size (default 12)
   static const int env_tb = [] { const char *e = getenv("B200SV_TILE_BITS"); return e ? atoi(e) : 0; }();
   const int kTB = env_tb == 11 ? 11 : 12;
+  static const int env_f32 = [] { const char *e = getenv("B200SV_TILE_F32"); return e ? atoi(e) : 1; }();
+  if (s.precision == B200SV_F32 && s.nq >= 13 && !any_pauli && env_f32) return apply_gate_sequence_f32(s, gates);
   const bool tiled = s.precision == B200SV_F64 && s.nq >= kTB;
   if (!tiled) {  // small or single-precision states: one streaming pass per op
     for (auto &g : gates) {

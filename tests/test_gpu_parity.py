@@ -433,6 +433,66 @@ def test_gate_sequence_small_and_batched_states():
             assert np.max(np.abs(got[i] - o.vector())) < 1e-12
 
 
+@pytest.mark.parametrize("n", [13, 14, 17, 20])
+def test_gate_sequence_single_precision_tile_passes(n):
+    """complex64 states >= 13 qubits flush the gate queue through the float tile passes (16-byte slots = amplitude
+    pairs over qubit 0, rounds A(1,2)|A(0,1) [+ B(3,4)], 1-qubit gates promoted to 4x4): same result as the gates
+    applied one by one by the double-precision oracle, to single-precision tolerance."""
+    rng = np.random.default_rng(300 + n)
+    psi0 = opgen.random_state(rng, n)
+    for trial in range(4):
+        gates = []
+        for _ in range(int(rng.integers(1, 48))):
+            k = int(rng.integers(1, 3))
+            if trial == 1:    # stress qubit 0 (inside the slot) and the low coalescing bits
+                qs = [int(q) for q in rng.choice(min(n, 5), size=k, replace=False)]
+            elif trial == 2:  # chains on a few high qubits
+                qs = [int(q) for q in rng.choice(4, size=k, replace=False) + (n - 4)]
+            else:
+                qs = opgen.pick(rng, n, k)
+            if rng.random() < 0.25:
+                gates.append((qs, opgen.colmajor(np.diag(np.exp(1j * rng.uniform(0, 2 * np.pi, 1 << k))))))
+            else:
+                gates.append((qs, opgen.colmajor(opgen.haar_unitary(rng, 1 << k))))
+        ora, gpu = OracleQV(n), gpu_qv(n, np.complex64)
+        ora.set_state(psi0)
+        gpu.set_state(psi0.astype(np.complex64))
+        for qs, m in gates:
+            ora.apply_matrix(qs, m)
+        passes = gpu.apply_gate_sequence(gates)
+        assert 1 <= passes <= len(gates)
+        got = gpu.vector().astype(np.complex128)
+        assert np.max(np.abs(ora.vector() - got)) < 1e-3 / np.sqrt(1 << n), (trial, len(gates))  # amplitudes ~ 2^(-n/2)
+        assert opgen.fidelity_gap(ora.vector(), got) < 1e-5
+
+
+def test_gate_sequence_single_precision_quantum_volume_and_batch():
+    from qiskit_aer_b200 import circuits, executor
+    n = 18
+    ops = circuits.quantum_volume(n, 8, seed=5)
+    ora, gpu = OracleQV(n), gpu_qv(n, np.complex64)
+    executor.apply_ops(ora, ops)
+    stats = {}
+    executor.apply_ops_queued(gpu, ops, stats)
+    assert opgen.fidelity_gap(ora.vector(), gpu.vector().astype(np.complex128)) < 1e-5
+    assert stats["passes"] < len(ops) // 3, stats
+    # several states in one container: tiles never straddle two states
+    rng = np.random.default_rng(11)
+    S, n = 3, 13
+    states = [opgen.random_state(rng, n) for _ in range(S)]
+    gpu = gpu_qv(n, np.complex64, num_states=S)
+    gpu.set_state(np.concatenate(states).astype(np.complex64))
+    gates = [(opgen.pick(rng, n, 2), opgen.colmajor(opgen.haar_unitary(rng, 4))) for _ in range(12)]
+    gpu.apply_gate_sequence(gates)
+    got = gpu.vector().reshape(S, -1).astype(np.complex128)
+    for i, st in enumerate(states):
+        o = OracleQV(n)
+        o.set_state(st)
+        for qs, m in gates:
+            o.apply_matrix(qs, m)
+        assert opgen.fidelity_gap(o.vector(), got[i]) < 1e-5
+
+
 def test_concurrent_host_threads_on_different_handles():
     """Aer calls the vector from OpenMP threads (one State per shot / chunk group,
     circuit_executor.hpp:958, parallel_state_executor.hpp:831-840): the ABI must be re-entrant."""

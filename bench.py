@@ -28,6 +28,7 @@ import numpy as np  # noqa: E402
 DEPTH = 10
 SHOTS = 1024
 AMP_BYTES = 16
+CDTYPE = None  # numpy complex dtype of the amplitudes, set from --precision
 
 
 def log(*a):
@@ -136,7 +137,7 @@ def reference_arm(args):
     print(json.dumps({
         "impl": "reference", "metric": "amplitude_updates_per_s", "value": value, "unit": "amp-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if AMP_BYTES == 16 else "f32", "data": "synthetic",
         "config": {"workload": name, "sample_qubits": n, "depth": args.depth, "fusion_max_qubit": 5,
                    "device": "CPU", "threads": cores},
         "cpu_baseline": {"value": value, "unit": "amp-updates/s", "cores": cores, "kind": "reference",
@@ -203,6 +204,8 @@ def b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n, name, ops, amps_written = workload(args, world)
+    if args.precision == "single":
+        name += "_f32"
     n_local = n - int(np.log2(world))
     fused = fusion.fuse(ops, max_qubit=args.fusion_max_qubit, max_diag_qubit=args.max_diag_qubit)
     if rank == 0:
@@ -212,13 +215,13 @@ def b200_arm(args):
     stream = torch.cuda.Stream(device=dev)
     if world > 1 and args.exchange == "p2p":
         # library-owned allocation (exportable over CUDA IPC), kernels ordered on the torch stream NCCL uses
-        qv = q.QubitVectorB200(n_local, np.complex128, device=local_rank)
+        qv = q.QubitVectorB200(n_local, CDTYPE, device=local_rank)
         qv.set_stream(stream.cuda_stream)
         buf = qv.torch_view()
     else:
         with torch.cuda.stream(stream):
-            buf = torch.empty((1 << n_local) * 2, dtype=torch.float64, device=dev)
-        qv = q.QubitVectorB200(n_local, np.complex128, device=local_rank, external_ptr=buf.data_ptr(),
+            buf = torch.empty((1 << n_local) * 2, dtype=torch.float64 if AMP_BYTES == 16 else torch.float32, device=dev)
+        qv = q.QubitVectorB200(n_local, CDTYPE, device=local_rank, external_ptr=buf.data_ptr(),
                                stream=stream.cuda_stream)
     if world > 1:
         from qiskit_aer_b200 import sharded
@@ -391,7 +394,7 @@ def b200_arm(args):
                 qv.close()
                 del buf
                 torch.cuda.empty_cache()
-                kw = dict(device="GPU", shots=SHOTS, seed=1234, fusion=False, expvals=paulis)
+                kw = dict(device="GPU", shots=SHOTS, seed=1234, fusion=False, expvals=paulis, precision=args.precision)
                 aer_backend.run_circuit(n, ops, **kw)
                 t0 = time.perf_counter()
                 for _ in range(args.steps):
@@ -418,7 +421,7 @@ def b200_arm(args):
             if ent:  # per-amplitude DRAM bytes from the committed ncu --set full capture, scaled to this launch
                 traffic = ent["bytes_per_amp"] * 2.0 ** n_local
         fp64 = None
-        if dom == "tile_pass":
+        if dom == "tile_pass" and AMP_BYTES == 16:
             # the tile pass carries several gates per HBM pass and is FP64-pipe bound: report that roofline too
             flops = sum(8.0 * 2 ** len(op[1] if op[0] == "unitary" else op[2]) for op in ops) * 2.0 ** n_local
             tf = flops * args.steps / (tot / 1e3) / 1e12
@@ -428,7 +431,7 @@ def b200_arm(args):
         out = {
             "metric": "amplitude_updates_per_s", "value": value, "unit": "amp-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if AMP_BYTES == 16 else "f32", "data": "synthetic",
             "config": {"workload": name, "qubits": n, "qubits_per_gpu": n_local, "depth": args.depth,
                        "circuit_gates": len(ops), "engine": args.engine,
                        "hbm_passes": (per_class["tile_pass"][0] // args.steps) if tile else len(fused),
@@ -477,9 +480,14 @@ def main():
                     help="tile: multi-gate shared-memory passes (default); dense: one fused dense block per pass")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="global-qubit exchange: in-place NVLink peer swap kernel over CUDA IPC, or ncclSend/Recv slices")
+    ap.add_argument("--precision", default="double", choices=["double", "single"],
+                    help="amplitude type; BASELINE's metric is quoted in double precision (the default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-aer-e2e", action="store_true", help="skip the run through the reference Controller")
     args = ap.parse_args()
+    global AMP_BYTES, CDTYPE
+    AMP_BYTES = 16 if args.precision == "double" else 8
+    CDTYPE = np.complex128 if args.precision == "double" else np.complex64
     if args.workload == "qft":
         args.engine = "dense"  # QFT is mostly controlled phases: commutation-aware fusion + wide diagonal passes
     if args.impl == "reference":

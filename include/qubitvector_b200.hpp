@@ -617,14 +617,14 @@ protected:
   bool idle() const { return batch_ && batch_->on && batch_pos_ != 0; }
   bool batch_queueing() const { return batch_ && batch_->on && batch_->cond_reg < 0 && queue_enabled(); }
   // may a <= 2-qubit special gate (x, cx, cy, cz/cp, swap, cu, small diagonal) be rewritten as a dense matrix and
-  // queued?  Yes when the flush runs tile passes (double precision, >= 12 qubits, all qubits local): the gate then
+  // queued?  Yes when the flush runs tile passes (>= 12 qubits in double, >= 13 in single precision, all qubits local): the gate then
   // shares an HBM pass with its neighbours instead of costing one of its own.
   bool ride_queue(const reg_t &qubits) const {
     if (!queue_enabled() || qubits.empty() || qubits.size() > 2) return false;
     for (const auto q : qubits)
       if (q >= num_qubits_) return false;
     if (batch_) return batch_queueing();
-    return sizeof(data_t) == 8 && num_qubits_ >= 12;
+    return sizeof(data_t) == 8 ? num_qubits_ >= 12 : num_qubits_ >= 13;  // the sizes the tile passes take
   }
   b200sv_handle state_view(size_t s) const {
     if (s == batch_pos_) {

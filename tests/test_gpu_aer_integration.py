@@ -105,6 +105,17 @@ def test_single_precision_through_controller():
     gpu = be.run_circuit(n, ops, device="GPU", **kw)
     cpu = be.run_circuit(n, ops, device="CPU", **kw)
     assert opgen.fidelity_gap(np.asarray(cpu["data"]["sv"]), np.asarray(gpu["data"]["sv"])) < 1e-5
+    # >= 13 qubits, fusion off: 1-/2-qubit gates (named gates included) ride the adapter's queue into the float tile passes.
+    # No diagonal gates here: the reference's float AVX2 diagonal kernel writes past its buffer (qv_avx2.cpp:1197-1203),
+    # which would corrupt the heap of the CPU leg of this comparison.
+    n = 14
+    ops = circuits.quantum_volume(n, 4, seed=9) + [("gate", "h", [0], []), ("gate", "cx", [0, n - 1], []),
+                                                   ("gate", "ry", [n - 1], [0.4]), ("gate", "swap", [2, n - 2], []),
+                                                   ("gate", "x", [0], []), ("gate", "cy", [n - 1, 0], [])]
+    kw = dict(shots=0, seed=3, fusion=False, save_statevector=True, precision="single", measure=False)
+    gpu = be.run_circuit(n, ops, device="GPU", **kw)
+    cpu = be.run_circuit(n, ops, device="CPU", **kw)
+    assert opgen.fidelity_gap(np.asarray(cpu["data"]["sv"]), np.asarray(gpu["data"]["sv"])) < 1e-5
 
 
 def _freq(res, n, shots):

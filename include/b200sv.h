@@ -139,6 +139,16 @@ int b200sv_apply_gate_sequence(b200sv_handle h, int ngates, const int *nq, const
 int b200sv_apply_op_sequence(b200sv_handle h, int nops, const int *kind, const uint64_t *qubits, const double *mats,
                              const int *slot, const uint8_t *codes, int nslots, int *passes_out);
 
+/* Self-test of the pass / round scheduler behind the two calls above -- TEST INFRASTRUCTURE, not a compute path: no
+ * handle and no device are involved.  The op list is partitioned exactly as b200sv_apply_op_sequence does, but each
+ * tile-pass parameter block is INTERPRETED on `host_state` (num_states << num_qubits complex<double> or
+ * complex<float> amplitudes, 12 <= num_qubits <= 24) with the kernels' addressing (staging maps, swizzled slots,
+ * per-thread round blocks, gate forms), and the warp-local-segment invariant is checked.  Lets the CPU-only
+ * test-suite cover host logic that otherwise runs only in front of a GPU.  No reference counterpart. */
+int b200sv_selftest_op_sequence(int num_qubits, int64_t num_states, int precision, void *host_state, int nops,
+                                const int *kind, const uint64_t *qubits, const double *mats, const int *slot,
+                                const uint8_t *codes, int nslots, int *passes_out);
+
 /* Per-state measurement collapse for batched containers (apply_batched_measure / apply_batched_reset,
  * qubitvector_thrust.hpp:2251-2460: check_measure_probability_func + reset_after_measure_func): for every
  * state s with active[s] != 0, amplitudes whose `qubits` bits differ from outcomes[s] are zeroed and the

@@ -478,6 +478,22 @@ int b200sv_apply_op_sequence(b200sv_handle h, int nops, const int *kind, const u
   });
 }
 
+int b200sv_selftest_op_sequence(int num_qubits, int64_t num_states, int precision, void *host_state, int nops,
+                                const int *kind, const uint64_t *qubits, const double *mats, const int *slot,
+                                const uint8_t *codes, int nslots, int *passes_out) {
+  return guard([&] {
+    if (!host_state || nops < 1 || !kind || !qubits || !mats || num_qubits < 12 || num_qubits > 24 || num_states < 1)
+      throw Error("selftest_op_sequence: bad arguments");
+    State st;  // no device, no stream: the tile passes are interpreted on the host array
+    st.nq = num_qubits;
+    st.nstates = num_states;
+    st.precision = precision;
+    st.selftest_host = host_state;
+    const int passes = apply_gate_sequence(st, nops, kind, qubits, mats, 3, slot, codes, nslots);
+    if (passes_out) *passes_out = passes;
+  });
+}
+
 int b200sv_apply_batched_pauli(b200sv_handle h, const uint64_t *masks4) {
   return guard([&] { select(H); launch_batched_pauli(*H, masks4); });
 }

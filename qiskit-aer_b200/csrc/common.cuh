@@ -84,6 +84,10 @@ struct State {
   size_t pinned_bytes = 0;
   void *checkpoint = nullptr;
   int num_sms = 148;
+  // scheduler self-test only (b200sv_selftest_op_sequence): a HOST array the tile-pass parameter blocks are
+  // interpreted on instead of being launched; never set on a handle
+  void *selftest_host = nullptr;
+  const uint8_t *selftest_codes = nullptr;
 
   uint64_t amps_per_state() const { return 1ull << nq; }
   uint64_t total_amps() const { return (uint64_t)nstates << nq; }

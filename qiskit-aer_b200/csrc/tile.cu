@@ -29,6 +29,7 @@
 // staging accesses (consecutive j) conflict free as well.  Because the swizzle
 // is linear, addresses are  phys(base) ^ phys(offset): one XOR per access.
 #include "common.cuh"
+#include <complex>
 
 namespace b200sv {
 
@@ -596,6 +597,124 @@ static bool pick_lane_positions(const std::vector<int> &free_pos, int out[3]) {
   return false;
 }
 
+// ------------------------------------------------------------------------------------------ scheduler self-test
+// Host interpreter of a TilePassParams block: follows the kernels' addressing step by step (staging through
+// insert_zeros / goff_* into swizzled slots, per-thread round blocks through gbit / eoff, fast kinds and generic
+// forms, store back) on a HOST array.  It exists so that the pass / round / segment scheduler -- host code that
+// otherwise only runs in front of a GPU -- is covered by the CPU test-suite (tests/test_tile_scheduler.py); it also
+// checks the invariant the warp-local segments rely on: between two rounds that are separated by __syncwarp() only,
+// no slot changes hands between warps.  Never reachable from a handle.
+template <typename T>
+static void emulate_tile_pass(const TilePassParams &p, void *host, const uint8_t *codes, bool f32_layout) {
+  typedef std::complex<T> C;
+  const int kSlots = 4096, kPer = f32_layout ? 2 : 1;  // amplitudes per 16-byte slot
+  C *psi = reinterpret_cast<C *>(host);
+  std::vector<C> tile((size_t)kSlots * kPer);
+  std::vector<int> owner(kSlots);
+  for (uint64_t t = 0; t < p.ntiles; t++) {
+    const uint64_t tbase = insert_zeros(t, p.ins);
+    // stage in with the memory-warp mapping (thread mt moves tile-local slots mt + 128 i) ...
+    for (int mt = 0; mt < 128; mt++) {
+      uint64_t glo = 0;
+      for (int u = 0; u < 7; u++)
+        if ((mt >> u) & 1) glo |= p.goff_lo[u];
+      const uint32_t slo = phys_slot((uint32_t)mt);
+      for (int i = 0; i < 32; i++) {
+        const uint64_t g = (tbase | glo) + (((i & 1) ? p.goff_lo[7] : 0) | p.goff_hi[i >> 1]);
+        const uint32_t sl = slo ^ phys_slot((uint32_t)(i & 1) << 7) ^ (uint32_t)p.soff_hi[i >> 1];
+        for (int c = 0; c < kPer; c++) tile[(size_t)sl * kPer + c] = psi[g * kPer + c];
+      }
+    }
+    std::fill(owner.begin(), owner.end(), -1);
+    for (int r = 0; r < p.nrounds; r++) {
+      const TileRound &R = p.rounds[r];
+      for (int tid = 0; tid < 256; tid++) {
+        uint32_t base = 0;
+        for (int i = 0; i < 8; i++)
+          if ((tid >> i) & 1) base ^= R.gbit[i];
+        const int nb = f32_layout ? 5 : 4, na = 1 << nb;
+        C a[32];
+        for (int e = 0; e < 16; e++) {
+          const uint32_t sl = base ^ R.eoff[e];
+          if (sl >= (uint32_t)kSlots) throw Error("selftest: slot out of range");
+          if (owner[sl] >= 0 && owner[sl] != (tid >> 5)) throw Error("selftest: a slot changes warps inside a warp-local segment");
+          owner[sl] = tid >> 5;
+          for (int c = 0; c < kPer; c++) a[e * kPer + c] = tile[(size_t)sl * kPer + c];
+        }
+        auto dense2 = [&](int P0, int P1, const C *M) {  // M row-major 4x4, index bit 0 <-> P0
+          for (int i = 0; i < na; i++) {
+            if (i & ((1 << P0) | (1 << P1))) continue;
+            const int idx[4] = {i, i | (1 << P0), i | (1 << P1), i | (1 << P0) | (1 << P1)};
+            C x[4], y[4];
+            for (int c = 0; c < 4; c++) x[c] = a[idx[c]];
+            for (int rr = 0; rr < 4; rr++) {
+              y[rr] = 0;
+              for (int c = 0; c < 4; c++) y[rr] += M[rr * 4 + c] * x[c];
+            }
+            for (int c = 0; c < 4; c++) a[idx[c]] = y[c];
+          }
+        };
+        if (f32_layout) {
+          std::complex<float> MA[16], MB[16];
+          const float2 *mA = reinterpret_cast<const float2 *>(p.mats[R.gate[0]]);
+          const float2 *mB = reinterpret_cast<const float2 *>(p.mats[R.gate[1]]);
+          for (int i = 0; i < 16; i++) { MA[i] = {mA[i].x, mA[i].y}; MB[i] = {mB[i].x, mB[i].y}; }
+          const C *A = reinterpret_cast<const C *>(MA), *B = reinterpret_cast<const C *>(MB);
+          if (R.fast == 1 || R.fast == 2) dense2(1, 2, A); else dense2(0, 1, A);
+          if (R.fast == 2 || R.fast == 4) dense2(3, 4, B);
+        } else {
+          static const int pair_of[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+          for (int k = 0; k < R.ngates; k++) {
+            const int form = R.fast ? (k == 0 ? 0 : 5) : R.form[k];
+            C M[16];
+            const double2 *m = p.mats[R.gate[k]];
+            for (int i = 0; i < 16; i++) M[i] = C((T)m[i].x, (T)m[i].y);
+            if (form >= 10 && form < 14) {
+              const int code = codes[(size_t)R.gate[k] * p.nstates + (t >> p.state_shift)], P = form - 10;
+              for (int i = 0; i < na && code; i++) {
+                if (i & (1 << P)) continue;
+                const int j = i | (1 << P);
+                const C x0 = a[i], x1 = a[j];
+                if (code == 1) { a[i] = x1; a[j] = x0; }
+                else if (code == 2) { a[i] = C(x1.imag(), -x1.real()); a[j] = C(-x0.imag(), x0.real()); }
+                else a[j] = -x1;
+              }
+            } else if (form < 6) dense2(pair_of[form][0], pair_of[form][1], M);
+            else if (form < 10) {
+              const int P = form - 6;
+              for (int i = 0; i < na; i++) {
+                if (i & (1 << P)) continue;
+                const C x0 = a[i], x1 = a[i | (1 << P)];
+                a[i] = M[0] * x0 + M[1] * x1;
+                a[i | (1 << P)] = M[2] * x0 + M[3] * x1;
+              }
+            } else if (form < 20) {
+              const int P0 = pair_of[form - 14][0], P1 = pair_of[form - 14][1];
+              for (int i = 0; i < na; i++) a[i] *= M[((i >> P0) & 1) | (((i >> P1) & 1) << 1)];
+            } else {
+              const int P = form - 20;
+              for (int i = 0; i < na; i++) a[i] *= M[(i >> P) & 1];
+            }
+          }
+        }
+        for (int e = 0; e < 16; e++)
+          for (int c = 0; c < kPer; c++) tile[(size_t)(base ^ R.eoff[e]) * kPer + c] = a[e * kPer + c];
+      }
+      if (R.sync) std::fill(owner.begin(), owner.end(), -1);  // CTA barrier: slots may change warps
+    }
+    // ... and out with the compute-group mapping (thread tid moves slots tid + 256 m): both must be the same bijection
+    for (int tid = 0; tid < 256; tid++) {
+      uint64_t glo = 0;
+      for (int u = 0; u < 8; u++)
+        if ((tid >> u) & 1) glo |= p.goff_lo[u];
+      const uint32_t slo = phys_slot((uint32_t)tid);
+      for (int m = 0; m < kHiCount; m++)
+        for (int c = 0; c < kPer; c++)
+          psi[((tbase | glo) + p.goff_hi[m]) * kPer + c] = tile[(size_t)(slo ^ p.soff_hi[m]) * kPer + c];
+    }
+  }
+}
+
 // Thread-id bits 0..4 (lane) and 5.. (warp) of a round map to the tile positions that are not round positions.
 // `wpos` (kTB - 9 positions, or empty) pins the warp-id bits: consecutive rounds that share wpos keep every warp
 // inside its own 2^9-amplitude sub-tile (round positions + lane positions = all positions outside wpos), so only
@@ -831,6 +950,10 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
     }
     r0 = r1;
   }
+  if (s.selftest_host) {  // scheduler self-test: interpret the parameter block on the host array
+    emulate_tile_pass<double>(p, s.selftest_host, s.selftest_codes, false);
+    return leftover;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 12)));
@@ -988,6 +1111,10 @@ static std::vector<int> run_tile_pass_f32(State &s, const std::vector<QGate> &ga
     R.gate[1] = fr.b >= 0 ? (uint16_t)put_matrix(gates[fr.b], true) : R.gate[0];
     R.ngates = (uint8_t)(1 + (fr.b >= 0));
   }
+  if (s.selftest_host) {
+    emulate_tile_pass<float>(p, s.selftest_host, nullptr, true);
+    return leftover;
+  }
   static bool attr = false;
   const int smem = kPipeBufs * (16 << 12) + 64;
   if (!attr) {
@@ -1056,10 +1183,11 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
   }
   // B200SV_TILE_BITS = 11 | 12 selects the tile size (default 12)
   static const int env_tb = [] { const char *e = getenv("B200SV_TILE_BITS"); return e ? atoi(e) : 0; }();
-  const int kTB = env_tb == 11 ? 11 : 12;
+  const int kTB = (env_tb == 11 && !s.selftest_host) ? 11 : 12;
   static const int env_f32 = [] { const char *e = getenv("B200SV_TILE_F32"); return e ? atoi(e) : 1; }();
   if (s.precision == B200SV_F32 && s.nq >= 13 && !any_pauli && env_f32) return apply_gate_sequence_f32(s, gates);
   const bool tiled = s.precision == B200SV_F64 && s.nq >= kTB;
+  if (!tiled && s.selftest_host) throw Error("selftest: this state size / precision / op mix does not take the tile passes");
   if (!tiled) {  // small or single-precision states: one streaming pass per op
     for (auto &g : gates) {
       if (g.mat) { launch_dense(s, g.q, g.nq, nullptr, 0, g.mat); continue; }
@@ -1077,7 +1205,8 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
     return ngates;
   }
   uint8_t *dev_codes = nullptr;
-  if (any_pauli) {
+  if (any_pauli && s.selftest_host) s.selftest_codes = codes_host;
+  if (any_pauli && !s.selftest_host) {
     const size_t bytes = (size_t)nslots * s.nstates;
     void *hm = s.ensure_pinned(bytes);
     // + slack: the pipelined kernel's idle group reads (and discards) codes of up to 2 * grid tiles past the end

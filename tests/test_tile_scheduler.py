@@ -1,0 +1,131 @@
+"""CPU coverage of the tile-pass scheduler (csrc/tile.cu host code): b200sv_selftest_op_sequence partitions an op
+list into passes / rounds / warp-local segments exactly as the product path does and INTERPRETS every parameter
+block on a host array with the kernels' addressing.  The result must equal the ops applied one by one by the
+oracle.  No GPU, no handle: this tests host logic (and the staging / swizzle / round-block address algebra the
+kernels share with the interpreter), not the kernels -- those are covered by tests/test_gpu_parity.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import opgen
+from oracle.oracle import OracleQV
+
+import qiskit_aer_b200  # noqa: F401
+from qiskit_aer_b200 import capi, circuits
+
+
+def selftest(n, state, ops, num_states=1, codes=None):
+    """ops: (kind, qubits, matrix-or-slot); kind 1/2 dense column-major, 3 per-state Pauli (slot)."""
+    lib = capi.lib()
+    nops = len(ops)
+    kind = np.zeros(nops, dtype=np.int32)
+    slot = np.zeros(nops, dtype=np.int32)
+    qs = np.zeros(2 * nops, dtype=np.uint64)
+    mats = np.zeros((nops, 16), dtype=np.complex128)
+    for i, (k, q, m) in enumerate(ops):
+        kind[i] = k
+        qs[2 * i:2 * i + len(q)] = q
+        if k == 3:
+            slot[i] = m
+        else:
+            m = np.asarray(m, dtype=np.complex128).reshape(-1)
+            mats[i, :m.size] = m
+    passes = C.c_int(0)
+    prec = 64 if state.dtype == np.complex128 else 32  # B200SV_F64 / B200SV_F32
+    nslots = 0 if codes is None else codes.shape[0]
+    capi.check(lib.b200sv_selftest_op_sequence(
+        n, num_states, prec, C.c_void_p(state.ctypes.data), nops, kind.ctypes.data_as(C.POINTER(C.c_int)),
+        qs.ctypes.data_as(C.POINTER(C.c_uint64)), mats.ctypes.data_as(C.POINTER(C.c_double)),
+        slot.ctypes.data_as(C.POINTER(C.c_int)),
+        None if codes is None else codes.ctypes.data_as(C.POINTER(C.c_uint8)), nslots, C.byref(passes)))
+    return passes.value
+
+
+def random_ops(rng, n, count, mode):
+    ops = []
+    for _ in range(count):
+        k = int(rng.integers(1, 3))
+        if mode == "low":
+            qs = [int(q) for q in rng.choice(min(n, 6), size=k, replace=False)]
+        elif mode == "chain":
+            qs = [int(q) for q in rng.choice(4, size=k, replace=False) + (n - 4)]
+        else:
+            qs = opgen.pick(rng, n, k)
+        if rng.random() < 0.3:
+            m = np.diag(np.exp(1j * rng.uniform(0, 2 * np.pi, 1 << k)))
+        else:
+            m = opgen.haar_unitary(rng, 1 << k)
+        ops.append((k, qs, opgen.colmajor(m)))
+    return ops
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+@pytest.mark.parametrize("n", [13, 15])
+def test_scheduler_random_gate_lists(n, dtype):
+    rng = np.random.default_rng(400 + n)
+    psi0 = opgen.random_state(rng, n)
+    tol = 1e-12 if dtype == np.complex128 else 1e-5
+    for mode in ("any", "low", "chain", "any"):
+        ops = random_ops(rng, n, int(rng.integers(1, 40)), mode)
+        ora = OracleQV(n)
+        ora.set_state(psi0)
+        for _, qs, m in ops:
+            ora.apply_matrix(qs, m)
+        state = psi0.astype(dtype)
+        passes = selftest(n, state, ops)
+        assert 1 <= passes <= len(ops)
+        assert opgen.fidelity_gap(ora.vector(), state.astype(np.complex128)) < tol, (mode, len(ops))
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_scheduler_quantum_volume_fast_rounds(dtype):
+    """QV layers are all dense 2-qubit gates: every round is a fast round, passes carry several gates."""
+    n = 14
+    gate_ops = circuits.quantum_volume(n, 6, seed=4)
+    ops = [(2, list(op[1]), opgen.colmajor(np.asarray(op[2]))) for op in gate_ops]
+    rng = np.random.default_rng(1)
+    psi0 = opgen.random_state(rng, n)
+    ora = OracleQV(n)
+    ora.set_state(psi0)
+    for _, qs, m in ops:
+        ora.apply_matrix(qs, m)
+    state = psi0.astype(dtype)
+    passes = selftest(n, state, ops)
+    assert passes < len(ops) // 3
+    assert opgen.fidelity_gap(ora.vector(), state.astype(np.complex128)) < (1e-12 if dtype == np.complex128 else 1e-5)
+
+
+def test_scheduler_batched_states_with_per_state_paulis():
+    """kind 3 ops (sampled Pauli noise, one code per state and slot) ride on the passes of a multi-state container."""
+    n, S = 12, 3
+    rng = np.random.default_rng(7)
+    states = [opgen.random_state(rng, n) for _ in range(S)]
+    ops, nslots = [], 0
+    for i in range(24):
+        if i % 3 == 2:
+            ops.append((3, [int(rng.integers(0, n))], nslots))
+            nslots += 1
+        else:
+            k = int(rng.integers(1, 3))
+            ops.append((k, opgen.pick(rng, n, k), opgen.colmajor(opgen.haar_unitary(rng, 1 << k))))
+    codes = rng.integers(0, 4, size=(nslots, S)).astype(np.uint8)
+    state = np.concatenate(states).astype(np.complex128)
+    selftest(n, state, ops, num_states=S, codes=codes)
+    got = state.reshape(S, -1)
+    P = [np.eye(2), np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1, -1])]
+    for s_i, st in enumerate(states):
+        o = OracleQV(n)
+        o.set_state(st)
+        for k, qs, m in ops:
+            if k == 3:
+                o.apply_matrix(qs, opgen.colmajor(P[int(codes[m, s_i])].astype(np.complex128)))
+            else:
+                o.apply_matrix(qs, m)
+        assert np.max(np.abs(got[s_i] - o.vector())) < 1e-12
+
+
+def test_selftest_rejects_sizes_outside_the_tile_path():
+    state = np.zeros(1 << 10, dtype=np.complex128)
+    with pytest.raises(capi.B200Error):
+        selftest(10, state, [(1, [0], opgen.colmajor(np.eye(2)))])

@@ -445,7 +445,12 @@ def b200_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": dom, "launches": cnt, "avg_ms": avg_ms,
                          "bytes_per_launch": bytes_per_launch, "peak_source": peak_src,
-                         "frac_of_nominal_8000": achieved / 8000.0, "fp64": fp64},
+                         "frac_of_nominal_8000": achieved / 8000.0, "fp64": fp64,
+                         # the north star's "per-gate GB/s": what one streaming pass PER GATE would have to sustain to
+                         # finish the circuit in the same time (several gates share one HBM pass in the tile engine)
+                         "per_gate_equivalent": {
+                             "GBps": AMP_BYTES * 2.0 * amps_written / world / (ms_per_step / 1e3) / 1e9,
+                             "x_hbm_peak": AMP_BYTES * 2.0 * amps_written / world / (ms_per_step / 1e3) / 1e9 / peak}},
             "per_kernel": {c: {"launches": v[0], "avg_ms": v[1] / v[0],
                                "GBps": (bytes_per_launch / (v[1] / v[0] / 1e3) / 1e9) if c.startswith(("dense", "diagonal", "tile")) else None}
                            for c, v in sorted(per_class.items())},

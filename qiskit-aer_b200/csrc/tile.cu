@@ -29,6 +29,7 @@
 // staging accesses (consecutive j) conflict free as well.  Because the swizzle
 // is linear, addresses are  phys(base) ^ phys(offset): one XOR per access.
 #include "common.cuh"
+#include <array>
 #include <complex>
 
 namespace b200sv {
@@ -954,7 +955,9 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
     emulate_tile_pass<double>(p, s.selftest_host, s.selftest_codes, false);
     return leftover;
   }
-  static bool attr_set = false;
+  // function attributes are per device: one flag per device ordinal (a process may drive several GPUs)
+  static bool attr_set_dev[64] = {};
+  bool &attr_set = attr_set_dev[s.device & 63];
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 12)));
     B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 11)));
@@ -968,7 +971,8 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
   bool all_fast = true;
   for (int r = 0; r < p.nrounds; r++) all_fast = all_fast && p.rounds[r].fast;
   if (kTB == 12 && env_pipe == 2 && all_fast) {  // memory-warp variant: fast-only code fits its 112-register budget
-    static bool attr2 = false;
+    static bool attr2_dev[64] = {};
+    bool &attr2 = attr2_dev[s.device & 63];
     const int smem2 = kPipeBufs * (16 << 12) + 64;
     if (!attr2) {
       B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
@@ -1115,7 +1119,8 @@ static std::vector<int> run_tile_pass_f32(State &s, const std::vector<QGate> &ga
     emulate_tile_pass<float>(p, s.selftest_host, nullptr, true);
     return leftover;
   }
-  static bool attr = false;
+  static bool attr_dev[64] = {};
+  bool &attr = attr_dev[s.device & 63];
   const int smem = kPipeBufs * (16 << 12) + 64;
   if (!attr) {
     B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1157,6 +1162,93 @@ static int apply_gate_sequence_f32(State &s, const std::vector<QGate> &gates) {
   return passes;
 }
 
+// ------------------------------------------------------------------------------------------ queue-level absorption
+// A dense 1-qubit gate whose neighbour in time on that qubit is a dense (non-diagonal) 2-qubit gate is multiplied
+// into it on the host: u(a) directly after G(a,b) becomes (u x 1) G, directly before it G (u x 1); consecutive 1-qubit
+// gates on one qubit collapse the same way.  "Directly" = no other op (gate or per-state Pauli) on that qubit in
+// between, so the reordering is exact.  Typical transpiled circuits (rz / sx / u around every cx) lose 2/3 of their ops
+// and turn their generic rounds into fast ones.  This is the engine's counterpart of what Fusion::optimize_circuit
+// does for 1-qubit gates when Aer's fusion is switched off in favour of the gate queue.  B200SV_QUEUE_ABSORB=0 disables.
+typedef std::complex<double> cd_t;
+static void mat4_mul(const cd_t *A, const cd_t *B, cd_t *C) {  // column-major 4x4, C = A B
+  cd_t out[16];
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++) {
+      cd_t acc = 0;
+      for (int k = 0; k < 4; k++) acc += A[r + 4 * k] * B[k + 4 * c];
+      out[r + 4 * c] = acc;
+    }
+  std::copy(out, out + 16, C);
+}
+static void embed_1q(const cd_t *u /*column-major 2x2*/, bool on_bit0, cd_t *E) {
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++) {
+      const int rl = r & 1, rh = r >> 1, cl = c & 1, ch = c >> 1;
+      E[r + 4 * c] = on_bit0 ? (rh == ch ? u[rl + 2 * cl] : cd_t(0)) : (rl == cl ? u[rh + 2 * ch] : cd_t(0));
+    }
+}
+static void absorb_one_qubit_gates(std::vector<QGate> &gates, int nq, std::vector<std::array<double, 32>> &store) {
+  static const int env_on = [] { const char *e = getenv("B200SV_QUEUE_ABSORB"); return e ? atoi(e) : 1; }();
+  if (!env_on) return;
+  store.reserve(gates.size());  // pointers into `store` must stay valid
+  auto own = [&](QGate &g) {    // give g a private, writable matrix
+    cd_t *cur = reinterpret_cast<cd_t *>(const_cast<double *>(g.mat));
+    for (auto &st : store)
+      if (reinterpret_cast<cd_t *>(st.data()) == cur) return cur;
+    store.emplace_back();
+    std::copy(g.mat, g.mat + 32, store.back().data());
+    g.mat = store.back().data();
+    return reinterpret_cast<cd_t *>(store.back().data());
+  };
+  std::vector<int> last(nq, -1);  // index (in gates) of the last kept op on each qubit
+  std::vector<char> dead(gates.size(), 0);
+  auto dense2 = [&](int i) { return i >= 0 && gates[i].mat && gates[i].nq == 2 && !is_diag(gates[i]); };
+  auto dense1 = [&](int i) { return i >= 0 && gates[i].mat && gates[i].nq == 1; };
+  for (int i = 0; i < (int)gates.size(); i++) {
+    QGate &g = gates[i];
+    if (dense1(i)) {
+      const int a = g.q[0], j = last[a];
+      const cd_t *u = reinterpret_cast<const cd_t *>(g.mat);
+      if (dense2(j)) {            // (u on a) after G: G <- E G
+        cd_t E[16];
+        embed_1q(u, gates[j].q[0] == a, E);
+        cd_t *G = own(gates[j]);
+        mat4_mul(E, G, G);
+        dead[i] = 1;
+        continue;
+      }
+      if (dense1(j)) {            // u after v on the same qubit: v <- u v
+        cd_t *v = own(gates[j]);
+        cd_t out[4];
+        for (int c = 0; c < 2; c++)
+          for (int r = 0; r < 2; r++) out[r + 2 * c] = u[r] * v[2 * c] + u[r + 2] * v[1 + 2 * c];
+        std::copy(out, out + 4, v);
+        dead[i] = 1;
+        continue;
+      }
+      last[a] = i;
+      continue;
+    }
+    if (dense2(i)) {
+      for (int x = 0; x < 2; x++) {
+        const int j = last[g.q[x]];
+        if (dense1(j)) {          // u directly before G on this qubit: G <- G E
+          cd_t E[16];
+          embed_1q(reinterpret_cast<const cd_t *>(gates[j].mat), x == 0, E);
+          cd_t *G = own(g);
+          mat4_mul(G, E, G);
+          dead[j] = 1;
+        }
+      }
+    }
+    for (int x = 0; x < g.nq; x++) last[g.q[x]] = i;
+  }
+  size_t w = 0;
+  for (size_t i = 0; i < gates.size(); i++)
+    if (!dead[i]) gates[w++] = gates[i];
+  gates.resize(w);
+}
+
 // Partition an op sequence into tile passes (in-order greedy with dependency blocking) and run them.
 // kind[i]: 1 = dense 1-qubit, 2 = dense 2-qubit, 3 = per-state Pauli on one qubit (code table slot[i]).
 // Returns the number of HBM passes used.
@@ -1180,6 +1272,11 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
       gates[i].slot = slot[i];
       any_pauli = true;
     }
+  }
+  std::vector<std::array<double, 32>> merged;
+  if ((s.precision == B200SV_F64 && s.nq >= 12) || (s.precision == B200SV_F32 && s.nq >= 13)) {
+    absorb_one_qubit_gates(gates, s.nq, merged);
+    ngates = (int)gates.size();
   }
   // B200SV_TILE_BITS = 11 | 12 selects the tile size (default 12)
   static const int env_tb = [] { const char *e = getenv("B200SV_TILE_BITS"); return e ? atoi(e) : 0; }();

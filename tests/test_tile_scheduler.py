@@ -129,3 +129,32 @@ def test_selftest_rejects_sizes_outside_the_tile_path():
     state = np.zeros(1 << 10, dtype=np.complex128)
     with pytest.raises(capi.B200Error):
         selftest(10, state, [(1, [0], opgen.colmajor(np.eye(2)))])
+
+
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_scheduler_absorbs_one_qubit_gates_into_their_two_qubit_neighbours(dtype):
+    """rz / sx / u around every cx (a transpiled circuit): the 1-qubit gates are multiplied into the neighbouring dense
+    2-qubit gate before the passes are planned; consecutive 1-qubit gates collapse; diagonal 2-qubit gates and
+    per-state Paulis are left alone / act as barriers.  Result unchanged."""
+    n = 13
+    rng = np.random.default_rng(21)
+    CX = opgen.colmajor(np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=np.complex128))
+    CZ = opgen.colmajor(np.diag([1, 1, 1, -1]).astype(np.complex128))
+    ops = []
+    for layer in range(6):
+        perm = rng.permutation(n)
+        for i in range(n // 2):
+            a, b = int(perm[2 * i]), int(perm[2 * i + 1])
+            for q in (a, b, a):
+                ops.append((1, [q], opgen.colmajor(opgen.haar_unitary(rng, 2))))
+            ops.append((2, [a, b], CZ if (layer + i) % 3 == 0 else CX))
+            ops.append((1, [b], opgen.colmajor(np.diag(np.exp(1j * rng.uniform(0, 6.28, 2))))))
+    psi0 = opgen.random_state(rng, n)
+    ora = OracleQV(n)
+    ora.set_state(psi0)
+    for _, qs, m in ops:
+        ora.apply_matrix(qs, m)
+    state = psi0.astype(dtype)
+    passes = selftest(n, state, ops)
+    assert passes <= len(ops) // 8, (passes, len(ops))
+    assert opgen.fidelity_gap(ora.vector(), state.astype(np.complex128)) < (1e-12 if dtype == np.complex128 else 1e-5)

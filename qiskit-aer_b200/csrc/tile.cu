@@ -1202,14 +1202,16 @@ static void absorb_one_qubit_gates(std::vector<QGate> &gates, int nq, std::vecto
   };
   std::vector<int> last(nq, -1);  // index (in gates) of the last kept op on each qubit
   std::vector<char> dead(gates.size(), 0);
-  auto dense2 = [&](int i) { return i >= 0 && gates[i].mat && gates[i].nq == 2 && !is_diag(gates[i]); };
+  auto two = [&](int i) { return i >= 0 && gates[i].mat && gates[i].nq == 2; };
   auto dense1 = [&](int i) { return i >= 0 && gates[i].mat && gates[i].nq == 1; };
+  // a 1-qubit gate may join a 2-qubit one when that does not make a cheap diagonal gate dense
+  auto joins = [&](int one, int twoq) { return two(twoq) && (!is_diag(gates[twoq]) || is_diag(gates[one])); };
   for (int i = 0; i < (int)gates.size(); i++) {
     QGate &g = gates[i];
     if (dense1(i)) {
       const int a = g.q[0], j = last[a];
       const cd_t *u = reinterpret_cast<const cd_t *>(g.mat);
-      if (dense2(j)) {            // (u on a) after G: G <- E G
+      if (joins(i, j)) {          // (u on a) after G: G <- E G
         cd_t E[16];
         embed_1q(u, gates[j].q[0] == a, E);
         cd_t *G = own(gates[j]);
@@ -1229,10 +1231,27 @@ static void absorb_one_qubit_gates(std::vector<QGate> &gates, int nq, std::vecto
       last[a] = i;
       continue;
     }
-    if (dense2(i)) {
+    if (two(i)) {
+      const int j0 = last[g.q[0]], j1 = last[g.q[1]];
+      if (j0 == j1 && two(j0)) {
+        // the previous op on BOTH qubits is a 2-qubit gate on the same pair: H <- G H (cx rz cx -> one gate)
+        QGate &h = gates[j0];
+        cd_t P[16];
+        const cd_t *G = reinterpret_cast<const cd_t *>(g.mat);
+        const bool same_order = h.q[0] == g.q[0];
+        for (int c = 0; c < 4; c++)
+          for (int r = 0; r < 4; r++) {
+            const int rs = same_order ? r : ((r >> 1) | ((r & 1) << 1)), cs = same_order ? c : ((c >> 1) | ((c & 1) << 1));
+            P[r + 4 * c] = G[rs + 4 * cs];
+          }
+        cd_t *H = own(h);
+        mat4_mul(P, H, H);
+        dead[i] = 1;
+        continue;
+      }
       for (int x = 0; x < 2; x++) {
         const int j = last[g.q[x]];
-        if (dense1(j)) {          // u directly before G on this qubit: G <- G E
+        if (dense1(j) && joins(j, i)) {  // u directly before G on this qubit: G <- G E
           cd_t E[16];
           embed_1q(reinterpret_cast<const cd_t *>(gates[j].mat), x == 0, E);
           cd_t *G = own(g);

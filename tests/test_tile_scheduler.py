@@ -149,6 +149,9 @@ def test_scheduler_absorbs_one_qubit_gates_into_their_two_qubit_neighbours(dtype
                 ops.append((1, [q], opgen.colmajor(opgen.haar_unitary(rng, 2))))
             ops.append((2, [a, b], CZ if (layer + i) % 3 == 0 else CX))
             ops.append((1, [b], opgen.colmajor(np.diag(np.exp(1j * rng.uniform(0, 6.28, 2))))))
+            if i % 2 == 0:  # cx rz cx (a zz rotation) and a gate on the same pair in the other qubit order: one gate each
+                ops.append((2, [a, b], CX))
+                ops.append((2, [b, a], opgen.colmajor(opgen.haar_unitary(rng, 4))))
     psi0 = opgen.random_state(rng, n)
     ora = OracleQV(n)
     ora.set_state(psi0)

@@ -54,6 +54,66 @@ dense_kernel(cx<T> *__restrict__ psi, const __grid_constant__ DenseParams<T, K> 
   }
 }
 
+// ------------------------------------------------------------------ dense k = 5 on the FP64 tensor path (DMMA)
+// A 5-qubit block is 128 DFMA per amplitude: FP64 bound, and in the register kernel above also issue bound (every
+// complex matrix entry feeds one complex FMA per thread: one LDCU per two DFMA).  Here the block is a real 64x64
+// matrix [[Re M, -Im M], [Im M, Re M]] applied to columns of 64 reals (re 0..31, im 0..31 of a group) with
+// mma.sync.m8n8k4.f64: 256 FMA per instruction, the matrix fragment comes from shared memory with ONE LDS.64 per MMA.
+// A warp takes 8 groups per step.  Input mapping: lane l holds the amplitudes 4i + (l & 3), i = 0..7, of group l >> 2
+// -- re/im of one amplitude are exactly the B-fragment values of k-steps i and i + 8, so amplitudes are loaded as
+// whole double2.  Output mapping (the m8n8 accumulator layout): lane l ends up with re (row blocks 0..3) and im (row
+// blocks 4..7) of the amplitudes (l >> 2) + 8j of groups 2(l & 3) + {0,1}: again whole double2, stored straight from
+// registers.  No shared-memory transposition of amplitudes at all.  (North star: "only large-k fused blocks ... on
+// FP64 DMMA"; tools/micro/fp64_pipes.cu: DMMA and DFMA share one 37 TFLOP/s datapath, DMMA needs 8x fewer issue slots.)
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256, 3)
+dense5_dmma_kernel(double2 *__restrict__ psi, const __grid_constant__ DenseParams<double, 5> p) {
+  __shared__ double afrag[128 * 32];  // fragment f = rb * 16 + ks, lane l: R[8 rb + (l >> 2)][4 ks + (l & 3)]
+  for (int e = threadIdx.x; e < 128 * 32; e += blockDim.x) {
+    const int f = e >> 5, l = e & 31, o = 8 * (f >> 4) + (l >> 2), i = 4 * (f & 15) + (l & 3);
+    const double2 m = p.m[(o & 31) * 32 + (i & 31)];
+    afrag[e] = (o < 32) == (i < 32) ? m.x : (o < 32 ? -m.y : m.y);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  uint64_t in_off[8], out_off[4];
+#pragma unroll
+  for (int i = 0; i < 8; i++) in_off[i] = p.off[4 * i + (lane & 3)];
+#pragma unroll
+  for (int j = 0; j < 4; j++) out_off[j] = p.off[(lane >> 2) + 8 * j];
+  const uint64_t nbatch = p.ngroups >> 3;
+  const uint64_t wstride = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  for (uint64_t gb = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); gb < nbatch; gb += wstride) {
+    const uint64_t base_in = insert_zeros(gb * 8 + (lane >> 2), p.ins);
+    double xr[8], xi[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const double2 v = psi[base_in + in_off[i]];
+      xr[i] = v.x;
+      xi[i] = v.y;
+    }
+    double acc[8][2];
+#pragma unroll
+    for (int rb = 0; rb < 8; rb++) acc[rb][0] = acc[rb][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < 16; ks++) {
+      const double b = ks < 8 ? xr[ks] : xi[ks - 8];
+#pragma unroll
+      for (int rb = 0; rb < 8; rb++) dmma_m8n8k4(acc[rb][0], acc[rb][1], afrag[(rb * 16 + ks) * 32 + lane], b);
+    }
+    // all lanes of the warp have consumed their inputs (mma.sync is warp-collective): safe to overwrite in place
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+      const uint64_t base_out = insert_zeros(gb * 8 + 2 * (lane & 3) + g, p.ins);
+#pragma unroll
+      for (int j = 0; j < 4; j++) psi[base_out + out_off[j]] = make_double2(acc[j][g], acc[j + 4][g]);
+    }
+  }
+}
+
 template <typename T, int K>
 static void launch_dense_t(State &s, const int *targets, const int *controls, int nc, const double *mat) {
   constexpr int DIM = 1 << K;
@@ -77,6 +137,15 @@ static void launch_dense_t(State &s, const int *targets, const int *controls, in
   p.ins.n = (int)all.size();
   for (size_t i = 0; i < all.size(); i++) p.ins.pos[i] = (uint8_t)all[i];
   p.ngroups = s.total_amps() >> (K + nc);
+  if constexpr (K == 5 && std::is_same<T, double>::value) {
+    static const int env_dmma = [] { const char *e = getenv("B200SV_DENSE5_DMMA"); return e ? atoi(e) : 1; }();
+    if (env_dmma && nc == 0 && p.ngroups >= 8) {
+      const int grid5 = (int)std::min<uint64_t>((p.ngroups / 8 + 7) / 8, (uint64_t)s.num_sms * 3);
+      dense5_dmma_kernel<<<grid5, 256, 0, s.stream>>>((double2 *)s.data, p);
+      B200_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   const int threads = K >= 5 ? 128 : 256;
   const int grid = grid_for(s, p.ngroups, threads, K >= 5 ? 12 : 16);
   dense_kernel<T, K><<<grid, threads, 0, s.stream>>>((cx<T> *)s.data, p);

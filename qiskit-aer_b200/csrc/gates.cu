@@ -69,6 +69,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+// PAIR: global qubit 0 is not a target, so the two groups a lane holds results for (2c, 2c + 1) are neighbours in
+// memory: one 256-bit store per amplitude instead of two 16-byte pieces in separate instructions (full 32-byte sectors).
+template <bool PAIR>
 __global__ void __launch_bounds__(256, 3)
 dense5_dmma_kernel(double2 *__restrict__ psi, const __grid_constant__ DenseParams<double, 5> p) {
   __shared__ double afrag[128 * 32];  // fragment f = rb * 16 + ks, lane l: R[8 rb + (l >> 2)][4 ks + (l & 3)]
@@ -105,11 +108,20 @@ dense5_dmma_kernel(double2 *__restrict__ psi, const __grid_constant__ DenseParam
       for (int rb = 0; rb < 8; rb++) dmma_m8n8k4(acc[rb][0], acc[rb][1], afrag[(rb * 16 + ks) * 32 + lane], b);
     }
     // all lanes of the warp have consumed their inputs (mma.sync is warp-collective): safe to overwrite in place
+    if (PAIR) {
+      const uint64_t base_out = insert_zeros(gb * 8 + 2 * (lane & 3), p.ins);
 #pragma unroll
-    for (int g = 0; g < 2; g++) {
-      const uint64_t base_out = insert_zeros(gb * 8 + 2 * (lane & 3) + g, p.ins);
+      for (int j = 0; j < 4; j++)
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(psi + base_out + out_off[j]), "d"(acc[j][0]),
+                     "d"(acc[j + 4][0]), "d"(acc[j][1]), "d"(acc[j + 4][1])
+                     : "memory");
+    } else {
 #pragma unroll
-      for (int j = 0; j < 4; j++) psi[base_out + out_off[j]] = make_double2(acc[j][g], acc[j + 4][g]);
+      for (int g = 0; g < 2; g++) {
+        const uint64_t base_out = insert_zeros(gb * 8 + 2 * (lane & 3) + g, p.ins);
+#pragma unroll
+        for (int j = 0; j < 4; j++) psi[base_out + out_off[j]] = make_double2(acc[j][g], acc[j + 4][g]);
+      }
     }
   }
 }
@@ -141,7 +153,8 @@ static void launch_dense_t(State &s, const int *targets, const int *controls, in
     static const int env_dmma = [] { const char *e = getenv("B200SV_DENSE5_DMMA"); return e ? atoi(e) : 1; }();
     if (env_dmma && nc == 0 && p.ngroups >= 8) {
       const int grid5 = (int)std::min<uint64_t>((p.ngroups / 8 + 7) / 8, (uint64_t)s.num_sms * 3);
-      dense5_dmma_kernel<<<grid5, 256, 0, s.stream>>>((double2 *)s.data, p);
+      if (p.ins.pos[0] > 0) dense5_dmma_kernel<true><<<grid5, 256, 0, s.stream>>>((double2 *)s.data, p);
+      else dense5_dmma_kernel<false><<<grid5, 256, 0, s.stream>>>((double2 *)s.data, p);
       B200_CUDA(cudaGetLastError());
       return;
     }

@@ -37,8 +37,8 @@ namespace b200sv {
 constexpr int kMaxTB = 12;            // tile bits: 12 (64 KiB, 256 threads, 2 CTAs/SM) or 11 (32 KiB, 128 threads, 4 CTAs/SM)
 constexpr int kHiCount = 16;          // staging iterations per thread = 2^TB / threads (one 16-amp group per thread)
 constexpr int kRoundBits = 4;
-constexpr int kMaxRounds = 24;
-constexpr int kMaxTileGates = 16;   // == kMaxRounds: worst case one gate per round
+constexpr int kMaxRounds = 64;     // gate rounds + one round per sampled-noise Pauli op
+constexpr int kMaxTileGates = 16;   // 4x4 matrices per pass (kernel-parameter space)
 constexpr int kMaxRoundGates = 12;  // dense gates + per-state Pauli ops in one round
 
 __host__ __device__ constexpr int swz_vec(int u) {
@@ -57,8 +57,9 @@ struct TileRound {
   uint16_t gbit[8];             // phys(1 << tpos[i]): contribution of group-id bit i
   uint8_t ngates;
   uint8_t sync;                 // 1: CTA barrier after this round; 0: the next round stays inside each warp's sub-tile
-  uint8_t fast;                 // 2 / 1: exactly two / one dense 2-qubit gate(s), on round bits (0,1) [and (2,3)]:
-                                // straight-line code (LDS, DFMA and STS interleave, no form dispatch); 0: generic
+  uint8_t fast;                 // 2 / 1: exactly two / one dense 4x4 block(s), on round bits (0,1) [and (2,3)]:
+                                // straight-line code (LDS, DFMA and STS interleave, no form dispatch); 5: one per-state
+                                // Pauli on round bit 0 (gate[0] = code slot); 0: generic
   uint8_t form[kMaxRoundGates];  // 0..5: 2-qubit on round-bit pair; 6..9: 1-qubit on round bit (form-6);
                                  // 10..13: per-state Pauli on round bit (form-10), code table slot in gate[];
                                  // 14..19: DIAGONAL 2-qubit on round-bit pair (form-14 as 0..5); 20..23: diagonal 1-qubit
@@ -75,6 +76,8 @@ struct TilePassParams {
   uint64_t nstates;
   int state_shift;                  // tile index >> state_shift = state (tile bits are all < num_qubits)
   int nrounds;
+  int npauli;                       // Pauli rounds of a slot-round pass read their codes from a per-tile shared copy:
+  uint16_t pauli_slot[kMaxRounds];  //   entry i = code-table slot of the pass's i-th Pauli op
   int prefetch;                     // 1: pull the CTA's NEXT tile into L2 while this one is being computed on
   TileRound rounds[kMaxRounds];
 };
@@ -187,7 +190,8 @@ __device__ __forceinline__ void apply_pauli_reg(double2 (&a)[16], int code) {
 // thread arrives on, so the warps of a group may drift apart across tiles).
 template <int GROUPED, int kLoBits, int MODE, bool LASTSYNC = true>
 __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int tid, const uint64_t t,
-                                           const TilePassParams &p, const int grp, const bool valid) {
+                                           const TilePassParams &p, const int grp, const bool valid,
+                                           const uint8_t *scodes = nullptr) {
   for (int r = 0; r < p.nrounds; r++) {
     const TileRound &R = p.rounds[r];
     {
@@ -196,7 +200,7 @@ __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int
 #pragma unroll
       for (int i = 0; i < kLoBits; i++)
         if ((g >> i) & 1) base ^= R.gbit[i];
-      const int fast = MODE == 2 ? 0 : R.fast;
+      const int fast = MODE == 2 ? 0 : R.fast;  // MODE 4 = MODE 1 + Pauli rounds
       if (fast == 2) {
         double2 a[16];
 #pragma unroll
@@ -206,7 +210,27 @@ __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int
 #pragma unroll
         for (int e = 0; e < 16; e++)
           if (valid) tile[base ^ R.eoff[e]] = a[e];
-      } else if (MODE == 1 || fast == 1) {
+      } else if ((MODE == 0 || MODE == 4) && fast == 5) {
+        // one per-state Pauli (sampled noise between gate rounds) on round bit 0, R.gate[0] = code-table slot.  Most
+        // draws are the identity: the round then costs one byte load and a broadcast, no shared-memory traffic.
+        int raw;
+        if (MODE == 4) {
+          const uint32_t sa = (uint32_t)__cvta_generic_to_shared(scodes) + R.gate[0];
+          asm volatile("ld.shared.u8 %0, [%1];" : "=r"(raw) : "r"(sa));
+        } else {
+          raw = (int)p.codes[(size_t)p.pauli_slot[R.gate[0]] * p.nstates + (t >> p.state_shift)];
+        }
+        const int code = __shfl_sync(0xffffffffu, raw, 0);
+        if (code) {
+          double2 a[16];
+#pragma unroll
+          for (int e = 0; e < 16; e++) a[e] = tile[base ^ R.eoff[e]];
+          apply_pauli_reg<0>(a, code);
+#pragma unroll
+          for (int e = 0; e < 16; e++)
+            if (valid) tile[base ^ R.eoff[e]] = a[e];
+        }
+      } else if (MODE == 1 || MODE == 4 || fast == 1) {
         double2 a[16];
 #pragma unroll
         for (int e = 0; e < 16; e++) a[e] = tile[base ^ R.eoff[e]];
@@ -357,6 +381,7 @@ tile_pipe_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
   extern __shared__ __align__(16) double2 tiles[];  // kPipeBufs tiles, then the barriers and progress counters
   uint64_t *full = reinterpret_cast<uint64_t *>(tiles + kPipeBufs * 4096);
   volatile int *progress = reinterpret_cast<volatile int *>(full + kPipeBufs);  // [grp]: tiles whose rounds are done
+  uint8_t *scodes = reinterpret_cast<uint8_t *>(full + kPipeBufs + 1);           // [grp][kMaxRounds] Pauli codes of the tile's state
   // broadcast from lane 0: tells the compiler the group id is warp-uniform (keeps the gate matrices on the uniform datapath)
   const int grp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 8), 0), tid = threadIdx.x & 255;
   if (threadIdx.x == 0) {
@@ -400,7 +425,16 @@ tile_pipe_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
       }
       mbar_wait(&full[k % kPipeBufs], (uint32_t)((k / kPipeBufs) & 1));
     }
-    run_rounds<1, kLoBits, MODE>(tile, tid, t, p, grp, valid);
+    if (MODE == 4) {  // this tile's state: one code per Pauli op of the pass, fetched once (not once per round)
+      // the group's first warp fetches them (uniform branch, uniform parameter index: anything thread-indexed here makes
+      // the compiler move the parameter block to local memory and the gate matrices off the uniform datapath)
+      if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0)
+        for (int i = 0; i < p.npauli; i++)
+          scodes[grp * kMaxRounds + i] = p.codes[(size_t)p.pauli_slot[i] * p.nstates + (t >> p.state_shift)];
+      if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
+      else asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    run_rounds<1, kLoBits, MODE>(tile, tid, t, p, grp, valid, scodes + grp * kMaxRounds);
     if (valid) {
       if (tid == 0) progress[grp] = kk + 1;
       double2 *gt = psi + (insert_zeros(t, p.ins) | glo);
@@ -560,12 +594,13 @@ __global__ void __maxnreg__(96) tile_pipe2_kernel(double2 *__restrict__ psi, con
       mbar_wait(&full[k % kPipeBufs], (uint32_t)((k / kPipeBufs) & 1));
     }
     if (MODE == 3) run_rounds_f32(tile, tid, p, grp, valid);
-    else run_rounds<1, kLoBits, MODE == 3 ? 1 : MODE, false>(tile, tid, t, p, grp, valid);
+    else run_rounds<1, kLoBits, MODE == 3 ? 1 : MODE, false>(tile, tid, t, p, grp, valid);  // MODE 1 or 4
     if (valid) mbar_arrive(&done[k % kPipeBufs]);  // release: this thread's shared-memory writes are visible to the waiter
   }
 }
 
 // ------------------------------------------------------------------------------------------ host scheduler
+typedef std::complex<double> cd_t;
 struct QGate {
   int nq;
   int q[2];
@@ -665,7 +700,18 @@ static void emulate_tile_pass(const TilePassParams &p, void *host, const uint8_t
           if (R.fast == 2 || R.fast == 4) dense2(3, 4, B);
         } else {
           static const int pair_of[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
-          for (int k = 0; k < R.ngates; k++) {
+          if (R.fast == 5) {
+            const int code = codes[(size_t)p.pauli_slot[R.gate[0]] * p.nstates + (t >> p.state_shift)];
+            for (int i = 0; i < na && code; i++) {
+              if (i & 1) continue;
+              const int j = i | 1;
+              const C x0 = a[i], x1 = a[j];
+              if (code == 1) { a[i] = x1; a[j] = x0; }
+              else if (code == 2) { a[i] = C(x1.imag(), -x1.real()); a[j] = C(-x0.imag(), x0.real()); }
+              else a[j] = -x1;
+            }
+          }
+          for (int k = 0; k < (R.fast == 5 ? 0 : R.ngates); k++) {
             const int form = R.fast ? (k == 0 ? 0 : 5) : R.form[k];
             C M[16];
             const double2 *m = p.mats[R.gate[k]];
@@ -811,6 +857,120 @@ static void plan_segments(const std::vector<std::vector<int>> &round_pos, int kT
   }
 }
 
+// ------------------------------------------------------------------------------------------ slot rounds
+// Round formation for passes without diagonal 2-qubit gates: every gate round is "fast" by construction.  A round has
+// two slots, round bits (0,1) and (2,3); a slot holds one dense 2-qubit gate or up to two 1-qubit gates on different
+// qubits, which the host multiplies into one 4x4 (v x u: the same 16 DFMA per amplitude as the two gates apart, but no
+// form dispatch).  Per-state Pauli ops (sampled noise) get rounds of their own, which cost a byte load unless the state
+// drew a non-identity Pauli.  Fills p.rounds / p.mats / p.nrounds; returns true when the pass contains Pauli rounds.
+static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates, const std::vector<int> &sel,
+                              const std::vector<int> &tile_bits, std::vector<int> &leftover) {
+  constexpr int kTB = 12;
+  auto tile_pos = [&](int q) {
+    for (int u = 0; u < kTB; u++)
+      if (tile_bits[u] == q) return u;
+    throw Error("tile pass: qubit not in tile");
+  };
+  struct SRound { int kind = 0; std::vector<int> slot[2]; int pauli = -1; };
+  std::vector<SRound> rounds;
+  std::vector<std::vector<int>> round_pos;
+  std::vector<int> rem(sel.begin(), sel.end());
+  int nmat = 0;
+  while (!rem.empty()) {
+    if ((int)rounds.size() >= kMaxRounds || nmat + 2 > kMaxTileGates) { leftover = rem; break; }
+    SRound sr;
+    uint64_t rq = 0, blocked = 0;
+    std::vector<int> rest;
+    for (int gi : rem) {
+      const QGate &g = gates[gi];
+      const uint64_t m = qmask(g);
+      bool taken = false;
+      if (!(m & blocked)) {
+        if (!g.mat) {  // per-state Pauli: only as the sole op of a round
+          if (sr.kind == 0) { sr.kind = 5; sr.pauli = gi; rq |= m; taken = true; }
+        } else if (sr.kind != 5 && !(m & rq)) {
+          for (int k = 0; k < 2 && !taken; k++) {
+            std::vector<int> &sl = sr.slot[k];
+            const bool fits = g.nq == 2 ? sl.empty() : (sl.size() < 2 && (sl.empty() || gates[sl[0]].nq == 1));
+            if (fits) { sl.push_back(gi); sr.kind = 1; rq |= m; taken = true; }
+          }
+        }
+      }
+      if (!taken) { blocked |= m; rest.push_back(gi); }
+    }
+    if (sr.kind == 1 && sr.slot[0].empty()) std::swap(sr.slot[0], sr.slot[1]);
+    if (sr.kind == 1 && !sr.slot[1].empty()) sr.kind = 2;
+    std::vector<int> rp;
+    for (int q = 0; q < 64; q++)
+      if ((rq >> q) & 1) rp.push_back(tile_pos(q));
+    nmat += sr.kind == 5 ? 0 : sr.kind;
+    rounds.push_back(sr);
+    round_pos.push_back(rp);
+    rem.swap(rest);
+  }
+  const int nr = (int)rounds.size();
+  p.nrounds = nr;
+  std::vector<std::vector<int>> round_w;
+  std::vector<int> seg_end;
+  plan_segments(round_pos, kTB, round_w, seg_end);
+  auto has = [](const std::vector<int> &v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); };
+  int nm = 0;
+  bool any_pauli = false;
+  p.npauli = 0;
+  std::fill(p.pauli_slot, p.pauli_slot + kMaxRounds, (uint16_t)0);
+  for (int r = 0; r < nr; r++) {
+    const SRound &sr = rounds[r];
+    std::vector<int> pads;  // unused positions outside the warp positions, highest first
+    for (int u = kTB - 1; u >= 0; u--)
+      if (!has(round_pos[r], u) && !has(round_w[r], u)) pads.push_back(u);
+    size_t np = 0;
+    std::vector<int> ordered;
+    TileRound &R = p.rounds[r];
+    if (sr.kind == 5) {
+      ordered.push_back(tile_pos(gates[sr.pauli].q[0]));
+      while (ordered.size() < 4) ordered.push_back(pads[np++]);
+      build_round(R, ordered, round_w[r], kTB, true);
+      R.fast = 5;
+      p.pauli_slot[p.npauli] = (uint16_t)gates[sr.pauli].slot;
+      R.gate[0] = (uint16_t)p.npauli++;
+      R.ngates = 0;
+      any_pauli = true;
+    } else {
+      cd_t M4[2][16];
+      for (int k = 0; k < sr.kind; k++) {
+        const std::vector<int> &sl = sr.slot[k];
+        const QGate &g0 = gates[sl[0]];
+        if (g0.nq == 2) {
+          ordered.push_back(tile_pos(g0.q[0]));
+          ordered.push_back(tile_pos(g0.q[1]));
+          std::copy(reinterpret_cast<const cd_t *>(g0.mat), reinterpret_cast<const cd_t *>(g0.mat) + 16, M4[k]);
+        } else {
+          const cd_t *u = reinterpret_cast<const cd_t *>(g0.mat);
+          static const cd_t I2[4] = {1, 0, 0, 1};
+          const cd_t *v = sl.size() == 2 ? reinterpret_cast<const cd_t *>(gates[sl[1]].mat) : I2;
+          ordered.push_back(tile_pos(g0.q[0]));
+          ordered.push_back(sl.size() == 2 ? tile_pos(gates[sl[1]].q[0]) : pads[np++]);
+          for (int c = 0; c < 4; c++)      // column-major 4x4, index = bit(first qubit) + 2 bit(second): v x u
+            for (int rr = 0; rr < 4; rr++) M4[k][rr + 4 * c] = u[(rr & 1) + 2 * (c & 1)] * v[(rr >> 1) + 2 * (c >> 1)];
+        }
+      }
+      while (ordered.size() < 4) ordered.push_back(pads[np++]);
+      build_round(R, ordered, round_w[r], kTB, true);
+      R.fast = (uint8_t)sr.kind;
+      R.ngates = (uint8_t)sr.kind;
+      for (int k = 0; k < sr.kind; k++) {
+        double2 *M = p.mats[nm];
+        for (int i = 0; i < 4; i++)
+          for (int j = 0; j < 4; j++) M[i * 4 + j] = mk<double>(M4[k][i + 4 * j].real(), M4[k][i + 4 * j].imag());
+        R.form[k] = (uint8_t)(k == 0 ? 0 : 5);
+        R.gate[k] = (uint16_t)nm++;
+      }
+    }
+    R.sync = (r == seg_end[r] - 1);
+  }
+  return any_pauli;
+}
+
 // One pass: gates[sel] all fit the tile; tile_bits sorted global positions (kTB of them).
 // Returns the entries of `sel` that did not fit (round or matrix-slot budget): the caller re-queues them.
 static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates, const std::vector<int> &sel,
@@ -838,10 +998,18 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
       if (tile_bits[u] == q) return u;
     throw Error("tile pass: qubit not in tile");
   };
+  static const int env_pipe = [] { const char *e = getenv("B200SV_TILE_PIPE"); return e ? atoi(e) : 2; }();
+  static const int env_slots = [] { const char *e = getenv("B200SV_TILE_SLOTS"); return e ? atoi(e) : 1; }();
+  bool use_slots = env_slots && kTB == 12 && env_pipe != 0, slot_pauli = false;
+  for (int gi : sel)
+    if (gates[gi].mat && gates[gi].nq == 2 && is_diag(gates[gi])) use_slots = false;  // cz / cp / rzz: one-multiply forms
+  std::vector<int> leftover;
+  if (use_slots) slot_pauli = build_slot_rounds(p, gates, sel, tile_bits, leftover);
   int ndense = 0;
   // rounds: scan in order, capacity 4 tile positions, respect dependencies
   std::vector<int> rem(sel.size());
   for (size_t i = 0; i < sel.size(); i++) rem[i] = (int)i;  // indices into sel
+  if (use_slots) rem.clear();
   std::vector<std::vector<int>> round_take, round_pos;
   // A round that starts with a dense (non-diagonal) 2-qubit gate stays "fast": at most one more such gate on two
   // other qubits joins it (straight-line code, no form dispatch, no register shuffling at the dispatch joins);
@@ -849,7 +1017,6 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
   // cheaper than the generic dispatch.  Rounds that start with a 1-qubit / diagonal / Pauli op are generic.
   static const int env_prefer_fast = [] { const char *e = getenv("B200SV_TILE_PREFER_FAST"); return e ? atoi(e) : 1; }();
   auto fast_eligible = [&](const QGate &g) { return g.mat && g.nq == 2 && !is_diag(g); };
-  std::vector<int> leftover;
   while (!rem.empty()) {
     if ((int)round_take.size() >= kMaxRounds) {  // out of rounds: hand the rest back
       for (int li : rem) leftover.push_back(sel[li]);
@@ -876,7 +1043,7 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
   }
   // segments of warp-local rounds and their warp-id positions
   const int nr = (int)round_take.size();
-  p.nrounds = nr;
+  if (!use_slots) p.nrounds = nr;
   std::vector<std::vector<int>> round_w;
   std::vector<int> seg_end;
   plan_segments(round_pos, kTB, round_w, seg_end);
@@ -967,9 +1134,21 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
                                    kPipeBufs * (16 << 12) + 64));
     attr_set = true;
   }
-  static const int env_pipe = [] { const char *e = getenv("B200SV_TILE_PIPE"); return e ? atoi(e) : 2; }();
   bool all_fast = true;
   for (int r = 0; r < p.nrounds; r++) all_fast = all_fast && p.rounds[r].fast;
+  if (slot_pauli) {  // fast rounds + per-state Pauli rounds: the three-buffer kernel (this mix does not fit the memory-warp one)
+    static bool attr4_dev[64] = {};
+    bool &attr4 = attr4_dev[s.device & 63];
+    const int smem4 = kPipeBufs * (16 << 12) + 64 + 2 * kMaxRounds;
+    if (!attr4) {
+      B200_CUDA(cudaFuncSetAttribute(tile_pipe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+      attr4 = true;
+    }
+    const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms);
+    tile_pipe_kernel<4><<<grid, 512, smem4, s.stream>>>((double2 *)s.data, p);
+    B200_CUDA(cudaGetLastError());
+    return leftover;
+  }
   if (kTB == 12 && env_pipe == 2 && all_fast) {  // memory-warp variant: fast-only code fits its 112-register budget
     static bool attr2_dev[64] = {};
     bool &attr2 = attr2_dev[s.device & 63];
@@ -1169,7 +1348,6 @@ static int apply_gate_sequence_f32(State &s, const std::vector<QGate> &gates) {
 // between, so the reordering is exact.  Typical transpiled circuits (rz / sx / u around every cx) lose 2/3 of their ops
 // and turn their generic rounds into fast ones.  This is the engine's counterpart of what Fusion::optimize_circuit
 // does for 1-qubit gates when Aer's fusion is switched off in favour of the gate queue.  B200SV_QUEUE_ABSORB=0 disables.
-typedef std::complex<double> cd_t;
 static void mat4_mul(const cd_t *A, const cd_t *B, cd_t *C) {  // column-major 4x4, C = A B
   cd_t out[16];
   for (int c = 0; c < 4; c++)

@@ -78,7 +78,6 @@ struct TilePassParams {
   int nrounds;
   int npauli;                       // Pauli rounds of a slot-round pass read their codes from a per-tile shared copy:
   uint16_t pauli_slot[kMaxRounds];  //   entry i = code-table slot of the pass's i-th Pauli op
-  int prefetch;                     // 1: pull the CTA's NEXT tile into L2 while this one is being computed on
   TileRound rounds[kMaxRounds];
 };
 
@@ -90,9 +89,6 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async16_ordered(void *smem, const void *gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void *gmem) {
-  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
@@ -317,24 +313,12 @@ tile_pass_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
   for (int u = 0; u < kLoBits; u++)
     if ((tid >> u) & 1) glo |= p.goff_lo[u];
   const uint32_t slo = phys_slot((uint32_t)tid);
-  // L2 prefetch of the next tile: 2^(TB-3) lines of 128 B, 2 per thread; line L = tid + nthreads * i covers
-  // tile-local j = L << 3 (the three lowest tile bits are the three lowest global bits whenever low_bits >= 3)
-  uint64_t plo = 0;
-#pragma unroll
-  for (int u = 3; u < kLoBits; u++)
-    if ((tid >> (u - 3)) & 1) plo |= p.goff_lo[u];
-  const int pm = tid >> (kLoBits - 3);
 
   for (uint64_t t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
     double2 *gt = psi + (insert_zeros(t, p.ins) | glo);
     PROF_T(c0);
 #pragma unroll
     for (int m = 0; m < kHiCount; m++) cp_async16(&tile[slo ^ p.soff_hi[m]], gt + p.goff_hi[m]);
-    if (p.prefetch && t + gridDim.x < p.ntiles) {
-      const double2 *gn = psi + (insert_zeros(t + gridDim.x, p.ins) | plo);
-      prefetch_l2(gn + p.goff_hi[pm]);
-      prefetch_l2(gn + p.goff_hi[pm + 8]);
-    }
     cp_async_wait_all();
     __syncthreads();
     PROF_T(c1);
@@ -981,8 +965,6 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
   p.codes = dev_codes;
   p.nstates = (uint64_t)s.nstates;
   p.state_shift = s.nq - kTB;
-  static const int env_prefetch = [] { const char *e = getenv("B200SV_TILE_PREFETCH"); return e ? atoi(e) : 0; }();
-  p.prefetch = env_prefetch;
   p.ins.n = kTB;
   for (int u = 0; u < kTB; u++) p.ins.pos[u] = (uint8_t)tile_bits[u];
   for (int u = 0; u < kLoBits; u++) p.goff_lo[u] = 1ull << tile_bits[u];
@@ -1188,7 +1170,6 @@ static std::vector<int> run_tile_pass_f32(State &s, const std::vector<QGate> &ga
   p.codes = nullptr;
   p.nstates = (uint64_t)s.nstates;
   p.state_shift = s.nq - (kSB + 1);
-  p.prefetch = 0;
   p.ins.n = kSB;
   for (int u = 0; u < kSB; u++) p.ins.pos[u] = (uint8_t)(tile_bits[u + 1] - 1);
   for (int u = 0; u < 8; u++) p.goff_lo[u] = 1ull << (tile_bits[u + 1] - 1);

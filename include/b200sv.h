@@ -143,7 +143,8 @@ int b200sv_apply_op_sequence(b200sv_handle h, int nops, const int *kind, const u
  * handle and no device are involved.  The op list is partitioned exactly as b200sv_apply_op_sequence does, but each
  * tile-pass parameter block is INTERPRETED on `host_state` (num_states << num_qubits complex<double> or
  * complex<float> amplitudes, 12 <= num_qubits <= 24) with the kernels' addressing (staging maps, swizzled slots,
- * per-thread round blocks, gate forms), and the warp-local-segment invariant is checked.  Lets the CPU-only
+ * per-thread round blocks, gate forms), and the warp-local-segment invariant is checked.  host_state == NULL plans
+ * only (returns the pass count; num_qubits up to 40).  Lets the CPU-only
  * test-suite cover host logic that otherwise runs only in front of a GPU.  No reference counterpart. */
 int b200sv_selftest_op_sequence(int num_qubits, int64_t num_states, int precision, void *host_state, int nops,
                                 const int *kind, const uint64_t *qubits, const double *mats, const int *slot,

@@ -482,13 +482,15 @@ int b200sv_selftest_op_sequence(int num_qubits, int64_t num_states, int precisio
                                 const int *kind, const uint64_t *qubits, const double *mats, const int *slot,
                                 const uint8_t *codes, int nslots, int *passes_out) {
   return guard([&] {
-    if (!host_state || nops < 1 || !kind || !qubits || !mats || num_qubits < 12 || num_qubits > 24 || num_states < 1)
+    // host_state == NULL: plan only (the pass count for any register size, e.g. a 33-qubit slice)
+    if (nops < 1 || !kind || !qubits || !mats || num_qubits < 12 || num_qubits > (host_state ? 24 : 40) || num_states < 1)
       throw Error("selftest_op_sequence: bad arguments");
     State st;  // no device, no stream: the tile passes are interpreted on the host array
     st.nq = num_qubits;
     st.nstates = num_states;
     st.precision = precision;
-    st.selftest_host = host_state;
+    st.selftest_host = host_state ? host_state : (void *)&st;
+    st.plan_only = host_state == nullptr;
     const int passes = apply_gate_sequence(st, nops, kind, qubits, mats, 3, slot, codes, nslots);
     if (passes_out) *passes_out = passes;
   });

@@ -87,6 +87,7 @@ struct State {
   // scheduler self-test only (b200sv_selftest_op_sequence): a HOST array the tile-pass parameter blocks are
   // interpreted on instead of being launched; never set on a handle
   void *selftest_host = nullptr;
+  bool plan_only = false;  // selftest without a host array: count the passes only
   const uint8_t *selftest_codes = nullptr;
 
   uint64_t amps_per_state() const { return 1ull << nq; }

@@ -56,6 +56,9 @@ struct TileRound {
   uint16_t eoff[16];            // phys(sum_i bit_i(e) << pos[i]) for the 16 elements of a sub-block
   uint16_t gbit[8];             // phys(1 << tpos[i]): contribution of group-id bit i
   uint8_t ngates;
+  uint8_t npre;                 // number of valid entries in pre[]
+  uint8_t pre[4];               // slot rounds: staged-code index of a per-state Pauli applied to round bit i BEFORE the
+                                // round's gates (sampled noise folded into the next gate round on that qubit), or kMaxRounds = none
   uint8_t sync;                 // 1: CTA barrier after this round; 0: the next round stays inside each warp's sub-tile
   uint8_t fast;                 // 2 / 1: exactly two / one dense 4x4 block(s), on round bits (0,1) [and (2,3)]:
                                 // straight-line code (LDS, DFMA and STS interleave, no form dispatch); 5: one per-state
@@ -177,6 +180,37 @@ __device__ __forceinline__ void apply_pauli_reg(double2 (&a)[16], int code) {
   }
 }
 
+// Sampled noise folded into a gate round: the Pauli codes (staged per tile in shared memory) of the ops that precede
+// the round's gates on its four bits.  Identity draws (99 %) cost four shared-memory bytes and a vote; a hit takes the
+// block through registers once more (same thread, same slots: no synchronisation) before the straight-line gate code,
+// which stays untouched.  pre index kMaxRounds ("none") reads a constant 0.
+__device__ __forceinline__ void apply_pre_paulis(double2 *__restrict__ tile, const uint32_t base, const TileRound &R,
+                                                 const uint8_t *scodes, const bool valid) {
+  const int c0 = __shfl_sync(0xffffffffu, (int)scodes[R.pre[0]], 0);
+  const int c1 = __shfl_sync(0xffffffffu, (int)scodes[R.pre[1]], 0);
+  const int c2 = __shfl_sync(0xffffffffu, (int)scodes[R.pre[2]], 0);
+  const int c3 = __shfl_sync(0xffffffffu, (int)scodes[R.pre[3]], 0);
+  if (c0 | c1 | c2 | c3) {
+    // rare path (a few per cent of the rounds): pair by pair in shared memory, runtime bit and code, so that it adds
+    // almost no registers or code next to the straight-line gate blocks
+#pragma unroll 1
+    for (int b = 0; b < 4; b++) {
+      const int code = b == 0 ? c0 : b == 1 ? c1 : b == 2 ? c2 : c3;
+      if (!code) continue;
+#pragma unroll 1
+      for (int j = 0; j < 8; j++) {
+        const int i0 = ((j >> b) << (b + 1)) | (j & ((1 << b) - 1)), i1 = i0 | (1 << b);
+        double2 *s0 = &tile[base ^ R.eoff[i0]], *s1 = &tile[base ^ R.eoff[i1]];
+        const double2 x0 = *s0, x1 = *s1;
+        if (!valid) continue;
+        if (code == 1) { *s0 = x1; *s1 = x0; }
+        else if (code == 2) { *s0 = mk<double>(x1.y, -x1.x); *s1 = mk<double>(-x0.y, x0.x); }
+        else *s1 = mk<double>(-x1.x, -x1.y);
+      }
+    }
+  }
+}
+
 // all rounds of one tile, in place in shared memory.  GROUPED = 0: the CTA is one 2^(TB-4)-thread group
 // (__syncthreads); GROUPED = 1: 256-thread groups of a bigger CTA, named barrier 1 + grp.
 // MODE 0: fast and generic rounds; 1: every round of the pass is fast; 2: generic code only (fast rounds carry
@@ -196,6 +230,7 @@ __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int
 #pragma unroll
       for (int i = 0; i < kLoBits; i++)
         if ((g >> i) & 1) base ^= R.gbit[i];
+      if (MODE == 4 && R.npre) apply_pre_paulis(tile, base, R, scodes, valid);
       const int fast = MODE == 2 ? 0 : R.fast;  // MODE 4 = MODE 1 + Pauli rounds
       if (fast == 2) {
         double2 a[16];
@@ -365,7 +400,7 @@ tile_pipe_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
   extern __shared__ __align__(16) double2 tiles[];  // kPipeBufs tiles, then the barriers and progress counters
   uint64_t *full = reinterpret_cast<uint64_t *>(tiles + kPipeBufs * 4096);
   volatile int *progress = reinterpret_cast<volatile int *>(full + kPipeBufs);  // [grp]: tiles whose rounds are done
-  uint8_t *scodes = reinterpret_cast<uint8_t *>(full + kPipeBufs + 1);           // [grp][kMaxRounds] Pauli codes of the tile's state
+  uint8_t *scodes = reinterpret_cast<uint8_t *>(full + kPipeBufs + 1);           // [grp][kMaxRounds + 16] Pauli codes of the tile's state
   // broadcast from lane 0: tells the compiler the group id is warp-uniform (keeps the gate matrices on the uniform datapath)
   const int grp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 8), 0), tid = threadIdx.x & 255;
   if (threadIdx.x == 0) {
@@ -412,13 +447,15 @@ tile_pipe_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
     if (MODE == 4) {  // this tile's state: one code per Pauli op of the pass, fetched once (not once per round)
       // the group's first warp fetches them (uniform branch, uniform parameter index: anything thread-indexed here makes
       // the compiler move the parameter block to local memory and the gate matrices off the uniform datapath)
-      if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0)
+      if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0) {
         for (int i = 0; i < p.npauli; i++)
-          scodes[grp * kMaxRounds + i] = p.codes[(size_t)p.pauli_slot[i] * p.nstates + (t >> p.state_shift)];
+          scodes[grp * (kMaxRounds + 16) + i] = p.codes[(size_t)p.pauli_slot[i] * p.nstates + (t >> p.state_shift)];
+        scodes[grp * (kMaxRounds + 16) + kMaxRounds] = 0;  // "no Pauli"
+      }
       if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
       else asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    run_rounds<1, kLoBits, MODE>(tile, tid, t, p, grp, valid, scodes + grp * kMaxRounds);
+    run_rounds<1, kLoBits, MODE>(tile, tid, t, p, grp, valid, scodes + grp * (kMaxRounds + 16));
     if (valid) {
       if (tid == 0) progress[grp] = kk + 1;
       double2 *gt = psi + (insert_zeros(t, p.ins) | glo);
@@ -684,6 +721,20 @@ static void emulate_tile_pass(const TilePassParams &p, void *host, const uint8_t
           if (R.fast == 2 || R.fast == 4) dense2(3, 4, B);
         } else {
           static const int pair_of[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+          if (R.fast == 1 || R.fast == 2) {
+            for (int P = 0; P < 4; P++) {
+              if (R.pre[P] == kMaxRounds) continue;
+              const int code = codes[(size_t)p.pauli_slot[R.pre[P]] * p.nstates + (t >> p.state_shift)];
+              for (int i = 0; i < na && code; i++) {
+                if (i & (1 << P)) continue;
+                const int j = i | (1 << P);
+                const C x0 = a[i], x1 = a[j];
+                if (code == 1) { a[i] = x1; a[j] = x0; }
+                else if (code == 2) { a[i] = C(x1.imag(), -x1.real()); a[j] = C(-x0.imag(), x0.real()); }
+                else a[j] = -x1;
+              }
+            }
+          }
           if (R.fast == 5) {
             const int code = codes[(size_t)p.pauli_slot[R.gate[0]] * p.nstates + (t >> p.state_shift)];
             for (int i = 0; i < na && code; i++) {
@@ -777,6 +828,8 @@ static std::vector<int> build_round(TileRound &R, const std::vector<int> &round_
   R.ngates = 0;
   R.sync = 1;
   R.fast = 0;
+  R.pre[0] = R.pre[1] = R.pre[2] = R.pre[3] = (uint8_t)kMaxRounds;
+  R.npre = 0;
   return pos;
 }
 
@@ -855,32 +908,67 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
       if (tile_bits[u] == q) return u;
     throw Error("tile pass: qubit not in tile");
   };
-  struct SRound { int kind = 0; std::vector<int> slot[2]; int pauli = -1; };
+  struct SRound { int kind = 0; std::vector<int> slot[2]; int pauli = -1; std::vector<std::pair<int, int>> pre; };
   std::vector<SRound> rounds;
   std::vector<std::vector<int>> round_pos;
   std::vector<int> rem(sel.begin(), sel.end());
-  int nmat = 0;
+  // a per-state Pauli whose next op on its qubit (inside this pass) is a dense gate is folded into that gate's round
+  // as a "pre-Pauli" instead of getting a round of its own
+  static const int env_fold = [] { const char *e = getenv("B200SV_TILE_FOLD_PAULI"); return e ? atoi(e) : 1; }();
+  std::vector<char> attachable(gates.size(), 0);
+  {
+    int next_dense[64];
+    std::fill(next_dense, next_dense + 64, 0);
+    for (int k = (int)sel.size() - 1; k >= 0; k--) {
+      const QGate &g = gates[sel[k]];
+      if (!g.mat) attachable[sel[k]] = env_fold && next_dense[g.q[0]];
+      for (int x = 0; x < g.nq; x++) next_dense[g.q[x]] = g.mat != nullptr;
+    }
+  }
+  int nmat = 0, npaul = 0;
   while (!rem.empty()) {
-    if ((int)rounds.size() >= kMaxRounds || nmat + 2 > kMaxTileGates) { leftover = rem; break; }
+    if ((int)rounds.size() >= kMaxRounds || nmat + 2 > kMaxTileGates || npaul + 5 > kMaxRounds) { leftover = rem; break; }
     SRound sr;
     uint64_t rq = 0, blocked = 0;
-    std::vector<int> rest;
+    std::vector<std::pair<int, int>> rest;  // (scan position, op): held Paulis that stay unattached re-enter in order
+    int held[64];
+    std::fill(held, held + 64, -1);
+    std::vector<std::pair<int, int>> held_at;  // (scan position, op)
+    int pos = 0;
     for (int gi : rem) {
       const QGate &g = gates[gi];
       const uint64_t m = qmask(g);
       bool taken = false;
       if (!(m & blocked)) {
-        if (!g.mat) {  // per-state Pauli: only as the sole op of a round
-          if (sr.kind == 0) { sr.kind = 5; sr.pauli = gi; rq |= m; taken = true; }
+        if (!g.mat) {
+          const int x = g.q[0];
+          if (attachable[gi] && sr.kind != 5 && held[x] < 0 && !(m & rq)) {  // wait for the gate on x in this round
+            held[x] = gi;
+            held_at.push_back({pos, gi});
+            taken = true;
+          } else if (sr.kind == 0 && held_at.empty()) {  // stand-alone Pauli round
+            sr.kind = 5; sr.pauli = gi; rq |= m; taken = true;
+          }
         } else if (sr.kind != 5 && !(m & rq)) {
           for (int k = 0; k < 2 && !taken; k++) {
             std::vector<int> &sl = sr.slot[k];
             const bool fits = g.nq == 2 ? sl.empty() : (sl.size() < 2 && (sl.empty() || gates[sl[0]].nq == 1));
             if (fits) { sl.push_back(gi); sr.kind = 1; rq |= m; taken = true; }
           }
+          if (taken)
+            for (int x = 0; x < g.nq; x++)
+              if (held[g.q[x]] >= 0) { sr.pre.push_back({g.q[x], held[g.q[x]]}); held[g.q[x]] = -2; }
         }
       }
-      if (!taken) { blocked |= m; rest.push_back(gi); }
+      if (!taken) { blocked |= m; rest.push_back({pos, gi}); }
+      pos++;
+    }
+    for (auto &h : held_at)  // Paulis whose gate did not make it into this round
+      if (held[gates[h.second].q[0]] == h.second) rest.push_back(h);
+    std::sort(rest.begin(), rest.end());
+    if (sr.kind == 0) {  // nothing but held Paulis: give the first one a round of its own (progress)
+      sr.kind = 5; sr.pauli = rest.front().second; rq |= qmask(gates[sr.pauli]);
+      rest.erase(rest.begin());
     }
     if (sr.kind == 1 && sr.slot[0].empty()) std::swap(sr.slot[0], sr.slot[1]);
     if (sr.kind == 1 && !sr.slot[1].empty()) sr.kind = 2;
@@ -888,9 +976,11 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
     for (int q = 0; q < 64; q++)
       if ((rq >> q) & 1) rp.push_back(tile_pos(q));
     nmat += sr.kind == 5 ? 0 : sr.kind;
+    npaul += sr.kind == 5 ? 1 : (int)sr.pre.size();
     rounds.push_back(sr);
     round_pos.push_back(rp);
-    rem.swap(rest);
+    rem.clear();
+    for (auto &e : rest) rem.push_back(e.second);
   }
   const int nr = (int)rounds.size();
   p.nrounds = nr;
@@ -942,6 +1032,13 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
       build_round(R, ordered, round_w[r], kTB, true);
       R.fast = (uint8_t)sr.kind;
       R.ngates = (uint8_t)sr.kind;
+      for (const auto &pr : sr.pre) {  // (qubit, Pauli op): applied to that qubit's round bit before the gates
+        const int bit = (int)(std::find(ordered.begin(), ordered.end(), tile_pos(pr.first)) - ordered.begin());
+        p.pauli_slot[p.npauli] = (uint16_t)gates[pr.second].slot;
+        R.pre[bit] = (uint8_t)p.npauli++;
+        R.npre++;
+        any_pauli = true;
+      }
       for (int k = 0; k < sr.kind; k++) {
         double2 *M = p.mats[nm];
         for (int i = 0; i < 4; i++)
@@ -1121,7 +1218,7 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
   if (slot_pauli) {  // fast rounds + per-state Pauli rounds: the three-buffer kernel (this mix does not fit the memory-warp one)
     static bool attr4_dev[64] = {};
     bool &attr4 = attr4_dev[s.device & 63];
-    const int smem4 = kPipeBufs * (16 << 12) + 64 + 2 * kMaxRounds;
+    const int smem4 = kPipeBufs * (16 << 12) + 64 + 2 * (kMaxRounds + 16);
     if (!attr4) {
       B200_CUDA(cudaFuncSetAttribute(tile_pipe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
       attr4 = true;

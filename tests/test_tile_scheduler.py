@@ -161,3 +161,35 @@ def test_scheduler_absorbs_one_qubit_gates_into_their_two_qubit_neighbours(dtype
     passes = selftest(n, state, ops)
     assert passes <= len(ops) // 8, (passes, len(ops))
     assert opgen.fidelity_gap(ora.vector(), state.astype(np.complex128)) < (1e-12 if dtype == np.complex128 else 1e-5)
+
+
+def test_scheduler_folds_noise_paulis_into_the_next_gate_round():
+    """A noisy-circuit pattern: every gate is followed by a sampled Pauli on each of its qubits.  Paulis whose next op on
+    that qubit is a gate of the same pass are applied as pre-Paulis of that gate's round, the others get rounds of
+    their own; both paths must agree with the oracle, for several states with different draws."""
+    n, S = 13, 4
+    rng = np.random.default_rng(77)
+    states = [opgen.random_state(rng, n) for _ in range(S)]
+    ops, nslots = [], 0
+    for layer in range(5):
+        perm = rng.permutation(n)
+        for i in range(n // 2):
+            a, b = int(perm[2 * i]), int(perm[2 * i + 1])
+            if (layer + i) % 3 == 0:
+                ops.append((1, [a], opgen.colmajor(opgen.haar_unitary(rng, 2))))
+                ops.append((3, [a], nslots)); nslots += 1
+            ops.append((2, [a, b], opgen.colmajor(opgen.haar_unitary(rng, 4))))
+            for q in (a, b):
+                ops.append((3, [q], nslots)); nslots += 1
+    codes = rng.choice(4, size=(nslots, S), p=[0.7, 0.1, 0.1, 0.1]).astype(np.uint8)  # far noisier than real models
+    state = np.concatenate(states).astype(np.complex128)
+    passes = selftest(n, state, ops, num_states=S, codes=codes)
+    assert passes < len(ops) // 6
+    got = state.reshape(S, -1)
+    P = [np.eye(2), np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1, -1])]
+    for s_i, st in enumerate(states):
+        o = OracleQV(n)
+        o.set_state(st)
+        for k, qs, m in ops:
+            o.apply_matrix(qs, opgen.colmajor(P[int(codes[m, s_i])].astype(np.complex128)) if k == 3 else m)
+        assert np.max(np.abs(got[s_i] - o.vector())) < 1e-12

@@ -567,6 +567,7 @@ __global__ void __maxnreg__(96) tile_pipe2_kernel(double2 *__restrict__ psi, con
   extern __shared__ __align__(16) double2 tiles[];
   uint64_t *full = reinterpret_cast<uint64_t *>(tiles + kPipeBufs * 4096);
   uint64_t *done = full + kPipeBufs;
+  uint8_t *scodes = reinterpret_cast<uint8_t *>(done + kPipeBufs);  // MODE 4: [grp][2][kMaxRounds + 16] Pauli codes
   // lane-0 broadcasts: warp-uniform role / group ids the compiler can see (uniform branches, uniform datapath)
   const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (threadIdx.x == 0)
@@ -614,8 +615,20 @@ __global__ void __maxnreg__(96) tile_pipe2_kernel(double2 *__restrict__ psi, con
       if (k >= kPipeBufs) mbar_wait(&done[k % kPipeBufs], (uint32_t)(((k - kPipeBufs) / kPipeBufs) & 1));
       mbar_wait(&full[k % kPipeBufs], (uint32_t)((k / kPipeBufs) & 1));
     }
+    // MODE 4: Pauli codes of this tile's state, staged by the group's first warp (see tile_pipe_kernel).  Two copies per
+    // group, alternating by tile: there is no barrier at the end of a tile here, so the first warp may already be staging
+    // the group's next tile while the others still read this one's codes (the barrier below bounds the lead to one tile).
+    uint8_t *sc = scodes + (grp * 2 + (kk & 1)) * (kMaxRounds + 16);
+    if (MODE == 4) {
+      if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0) {
+        for (int i = 0; i < p.npauli; i++) sc[i] = p.codes[(size_t)p.pauli_slot[i] * p.nstates + (t >> p.state_shift)];
+        sc[kMaxRounds] = 0;
+      }
+      if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
+      else asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     if (MODE == 3) run_rounds_f32(tile, tid, p, grp, valid);
-    else run_rounds<1, kLoBits, MODE == 3 ? 1 : MODE, false>(tile, tid, t, p, grp, valid);  // MODE 1 or 4
+    else run_rounds<1, kLoBits, MODE == 3 ? 1 : MODE, false>(tile, tid, t, p, grp, valid, sc);
     if (valid) mbar_arrive(&done[k % kPipeBufs]);  // release: this thread's shared-memory writes are visible to the waiter
   }
 }
@@ -1215,16 +1228,18 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
   }
   bool all_fast = true;
   for (int r = 0; r < p.nrounds; r++) all_fast = all_fast && p.rounds[r].fast;
-  if (slot_pauli) {  // fast rounds + per-state Pauli rounds: the three-buffer kernel (this mix does not fit the memory-warp one)
+  if (slot_pauli) {  // fast rounds + sampled-noise Paulis
     static bool attr4_dev[64] = {};
     bool &attr4 = attr4_dev[s.device & 63];
-    const int smem4 = kPipeBufs * (16 << 12) + 64 + 2 * (kMaxRounds + 16);
+    const int smem4 = kPipeBufs * (16 << 12) + 64 + 4 * (kMaxRounds + 16);
     if (!attr4) {
       B200_CUDA(cudaFuncSetAttribute(tile_pipe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
+      B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
       attr4 = true;
     }
     const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms);
-    tile_pipe_kernel<4><<<grid, 512, smem4, s.stream>>>((double2 *)s.data, p);
+    if (env_pipe == 2) tile_pipe2_kernel<4><<<grid, 640, smem4, s.stream>>>((double2 *)s.data, p);
+    else tile_pipe_kernel<4><<<grid, 512, smem4, s.stream>>>((double2 *)s.data, p);
     B200_CUDA(cudaGetLastError());
     return leftover;
   }

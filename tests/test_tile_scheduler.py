@@ -193,3 +193,31 @@ def test_scheduler_folds_noise_paulis_into_the_next_gate_round():
         for k, qs, m in ops:
             o.apply_matrix(qs, opgen.colmajor(P[int(codes[m, s_i])].astype(np.complex128)) if k == 3 else m)
         assert np.max(np.abs(got[s_i] - o.vector())) < 1e-12
+
+
+def _plan_only_passes(n, ops):
+    lib = capi.lib()
+    nops = len(ops)
+    kind = np.zeros(nops, dtype=np.int32)
+    slot = np.zeros(nops, dtype=np.int32)
+    qs = np.zeros(2 * nops, dtype=np.uint64)
+    mats = np.zeros((nops, 16), dtype=np.complex128)
+    for i, (q, m) in enumerate(ops):
+        kind[i] = len(q)
+        qs[2 * i:2 * i + len(q)] = q
+        m = np.asarray(m, dtype=np.complex128).reshape(-1)
+        mats[i, :m.size] = m
+    passes = C.c_int(0)
+    capi.check(lib.b200sv_selftest_op_sequence(
+        n, 1, 64, None, nops, kind.ctypes.data_as(C.POINTER(C.c_int)), qs.ctypes.data_as(C.POINTER(C.c_uint64)),
+        mats.ctypes.data_as(C.POINTER(C.c_double)), slot.ctypes.data_as(C.POINTER(C.c_int)), None, 0, C.byref(passes)))
+    return passes.value
+
+
+def test_pass_packing_quality_on_the_headline_circuit():
+    """Plan-only mode (no state): the 33-qubit, depth-10 Quantum Volume circuit of the bench (160 SU(4) gates) must
+    keep fitting in <= 18 HBM passes (first-fit in program order needs 21-24; the ready-set packer 16-18)."""
+    for seed in (1234, 1, 2):
+        ops = circuits.quantum_volume(33, 10, seed)
+        passes = _plan_only_passes(33, [(list(op[1]), opgen.colmajor(np.asarray(op[2]))) for op in ops])
+        assert 14 <= passes <= 18, (seed, passes)

@@ -221,3 +221,47 @@ def test_pass_packing_quality_on_the_headline_circuit():
         ops = circuits.quantum_volume(33, 10, seed)
         passes = _plan_only_passes(33, [(list(op[1]), opgen.colmajor(np.asarray(op[2]))) for op in ops])
         assert 14 <= passes <= 18, (seed, passes)
+
+
+_PAULI = [np.eye(2), np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1, -1])]
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_scheduler_randomized_op_mixes(block):
+    """Random mixes of dense / diagonal 1- and 2-qubit gates and per-state Paulis (densities from none to 80 %, optionally
+    concentrated on five qubits, 1-3 states, double and single precision): absorption, pass packing, slot / generic
+    rounds, folded and stand-alone Paulis, leftovers.  1000 seeds of this generator were run when the scheduler was
+    written; 60 stay in the suite."""
+    for seed in range(15 * block, 15 * block + 15):
+        rng = np.random.default_rng(seed)
+        n, S = int(rng.integers(12, 15)), int(rng.integers(1, 4))
+        nops = int(rng.integers(1, 140))
+        ppauli, pdiag, p1q = rng.choice([0.0, 0.2, 0.5, 0.8]), rng.choice([0.0, 0.2, 0.6]), rng.choice([0.1, 0.5, 0.9])
+        pool = min(n, 5) if rng.random() < 0.3 else n
+        ops, nslots = [], 0
+        for _ in range(nops):
+            if rng.random() < ppauli:
+                ops.append((3, [int(rng.integers(0, pool))], nslots))
+                nslots += 1
+                continue
+            k = 1 if rng.random() < p1q else 2
+            qs = [int(q) for q in rng.choice(pool, size=k, replace=False)]
+            m = np.diag(np.exp(1j * rng.uniform(0, 6.28, 1 << k))) if rng.random() < pdiag else opgen.haar_unitary(rng, 1 << k)
+            ops.append((k, qs, opgen.colmajor(m)))
+        if all(o[0] == 3 for o in ops):
+            ops.append((1, [0], opgen.colmajor(opgen.haar_unitary(rng, 2))))
+        codes = rng.choice(4, size=(max(nslots, 1), S), p=[0.5, 0.2, 0.15, 0.15]).astype(np.uint8)
+        dtype = np.complex128 if (nslots or rng.random() < 0.6) else np.complex64
+        if dtype == np.complex64:
+            n = max(n, 13)
+        states = [opgen.random_state(rng, n) for _ in range(S)]
+        state = np.concatenate(states).astype(dtype)
+        selftest(n, state, ops, num_states=S, codes=codes if nslots else None)
+        got = state.reshape(S, -1).astype(np.complex128)
+        for si, st in enumerate(states):
+            o = OracleQV(n)
+            o.set_state(st)
+            for k, qs, m in ops:
+                o.apply_matrix(qs, opgen.colmajor(_PAULI[int(codes[m, si])].astype(np.complex128)) if k == 3 else m)
+            gap = opgen.fidelity_gap(o.vector(), got[si])
+            assert gap < (1e-11 if dtype == np.complex128 else 1e-5), (seed, n, S, nops, gap)

@@ -1,15 +1,22 @@
-// b200sv tile-blocked multi-gate pass (sm_100a).
+// b200sv tile engine: whole runs of 1- and 2-qubit gates per HBM pass (sm_100a).
 //
-// One HBM pass applies a whole *sequence* of 1- and 2-qubit dense gates whose
-// qubits fit a 12-bit tile: every CTA stages 2^12 amplitudes (64 KiB) in shared
-// memory with cp.async (LDGSTS.128, no register staging), runs the gates as
-// "rounds" -- each thread pulls the 16 amplitudes of a 4-qubit sub-block into
-// registers, applies every gate of the round there (16 DFMA per amplitude per
-// 2-qubit gate instead of 4*2^k for a fused dense block), writes them back --
-// and streams the tile out again.  HBM traffic per pass stays 2*16*2^n bytes
-// while 5-8 gates ride on it, which is what moves QV-style circuits from
-// ~2 gates per pass (dense k<=4 fusion) to the FP64/HBM balance point
-// (~90 DFMA per amplitude per pass on B200).
+// One HBM pass applies a *sequence* of 1-/2-qubit gates (and, for batched noisy shots, per-state Pauli ops) whose
+// qubits fit a 12-bit tile: 2^12 amplitudes (64 KiB) are staged in shared memory with cp.async (LDGSTS.128, no
+// register staging), the gates run as "rounds" -- each thread pulls the 16 amplitudes of a 4-bit sub-block into
+// registers, applies the round's gates there (16 DFMA per amplitude per 2-qubit gate instead of 4*2^k for a fused
+// dense block), writes them back -- and the tile is streamed out again.  HBM traffic per pass stays 2*16*2^n bytes
+// while ~9 gates ride on it, which moves QV-style circuits from ~2 gates per pass (dense k<=4 fusion) past the
+// FP64/HBM balance point (~90 DFMA per amplitude per pass on B200): the passes are FP64 bound.
+//
+// File map (top to bottom):
+//   device   round code (apply2 / apply1 / diagonal / Pauli forms, run_rounds<MODE>), tile_pass_kernel (one tile per
+//            CTA), tile_pipe_kernel (three tile buffers per SM), run_rounds_f32 (float2 slot pairs), tile_pipe2_kernel
+//            (16 compute warps + 4 memory warps, mbarrier hand-offs: the default for dense-gate and noisy passes)
+//   host     emulate_tile_pass (CPU interpreter of a parameter block: scheduler self-test), build_round /
+//            plan_segments (swizzle-aware lane choice, warp-local segments), build_slot_rounds (fast rounds, folded
+//            Paulis), run_tile_pass / run_tile_pass_f32, PassPacker (ready-set pass selection),
+//            absorb_one_qubit_gates (queue-level fusion), apply_gate_sequence (entry point of the C ABI calls)
+// DESIGN.md "The tile engine" has the measurements behind each of these pieces.
 //
 // Reference counterpart: the blocked-gate queue of the Thrust path
 // (chunk/device_chunk_container.hpp:999-1108 queue_blocked_gate,
@@ -20,7 +27,7 @@
 //
 // Shared-memory layout: tile-local index j (bit u of j <-> global bit tb[u],
 // tb sorted ascending and always containing the low global bits so that global
-// accesses stay in >= 64 B runs) is stored at 16-byte slot  j ^ S(j)  with
+// accesses stay in >= 128 B runs) is stored at 16-byte slot  j ^ S(j)  with
 //   S(j) = XOR_{u >= 3, bit u of j set} v[u],  v = {.,.,., 1,2,4, 3,6,5, 7, 1, 2}
 // a GF(2)-linear swizzle chosen so that for ANY 4 round positions three of the
 // remaining eight positions have linearly independent bank vectors: the host

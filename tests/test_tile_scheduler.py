@@ -265,3 +265,31 @@ def test_scheduler_randomized_op_mixes(block):
                 o.apply_matrix(qs, opgen.colmajor(_PAULI[int(codes[m, si])].astype(np.complex128)) if k == 3 else m)
             gap = opgen.fidelity_gap(o.vector(), got[si])
             assert gap < (1e-11 if dtype == np.complex128 else 1e-5), (seed, n, S, nops, gap)
+
+
+@pytest.mark.parametrize("world,max_exchanges,max_passes", [(2, 2, 21), (4, 2, 20), (8, 3, 24)])
+def test_sharded_plan_quality(world, max_exchanges, max_passes):
+    """Epoch planner + pass packer on the bench's sharded workloads (33 local qubits per GPU), without any state:
+    number of global-qubit exchange steps and of HBM passes per rank."""
+    from qiskit_aer_b200 import sharded
+    g = int(np.log2(world))
+    n = 33 + g
+    ops = circuits.quantum_volume(n, 10, 1234)
+    r = object.__new__(sharded.ShardedRunner)  # the planner only reads these fields
+    r.nl, r.gbits, r.n, r.phys, r.multi_swap = 33, g, n, list(range(n)), True
+    r.world, r.rank, r.min_run_bits, r.exchange = world, 0, 20, "p2p"
+    plan = r.plan(ops)
+    exchanges = sum(1 for op in plan if op[0] in ("swap", "mswap"))
+    if world == 2:
+        exchanges = sum(1 for op in plan if op[0] == "swap")
+    passes, seg = 0, []
+    for op in plan + [("swap",)]:
+        if op[0] in ("swap", "mswap"):
+            if seg:
+                passes += _plan_only_passes(33, [(list(o[1]), opgen.colmajor(np.asarray(o[2]))) for o in seg])
+            seg = []
+        else:
+            seg.append(op)
+    assert exchanges <= max_exchanges, exchanges
+    assert passes <= max_passes, passes
+    assert sorted(r.phys) == list(range(n))  # still a permutation of the physical positions

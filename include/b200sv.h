@@ -150,6 +150,20 @@ int b200sv_selftest_op_sequence(int num_qubits, int64_t num_states, int precisio
                                 const int *kind, const uint64_t *qubits, const double *mats, const int *slot,
                                 const uint8_t *codes, int nslots, int *passes_out);
 
+/* Epoch planner for a register sharded over 2^(num_qubits - local_qubits) devices by its top qubits (host code, no
+ * device).  Ops are given by their logical qubits (op i = op_qubits[op_off[i] .. op_off[i+1]), need_local[] flags the
+ * qubits that must be chunk-local for the op: targets of non-diagonal ops; controls and diagonal ops are resolved from
+ * the chunk index).  phys[] (logical -> physical position, >= local_qubits means "selects the device") is updated.
+ * plan_out receives int64 records: {0, op, nq, physical qubits...} | {1, local position, global bit} (pairwise exchange)
+ * | {2, k, local positions..., global bits...} (one all-to-all pass, multi_swap != 0).  Every op runs as soon as its
+ * qubits are local under the current map; at each stall the wanted global qubits replace the local ones whose next use is
+ * farthest away; evicted positions >= min_run_bits are preferred (long contiguous runs for the exchange).
+ * Role of CacheBlocking::optimize_circuit + swap insertion (src/transpile/cacheblocking.hpp:52, block_circuit :82, insert_swap :182) and of
+ * ParallelStateExecutor::apply_chunk_swap scheduling (src/simulators/parallel_state_executor.hpp:1134). */
+int b200sv_plan_epochs(int num_qubits, int local_qubits, int nops, const int *op_off, const int *op_qubits,
+                       const uint8_t *need_local, int min_run_bits, int multi_swap, int *phys, int64_t *plan_out,
+                       int64_t plan_cap, int64_t *plan_len);
+
 /* Per-state measurement collapse for batched containers (apply_batched_measure / apply_batched_reset,
  * qubitvector_thrust.hpp:2251-2460: check_measure_probability_func + reset_after_measure_func): for every
  * state s with active[s] != 0, amplitudes whose `qubits` bits differ from outcomes[s] are zeroed and the

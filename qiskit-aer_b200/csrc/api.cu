@@ -496,6 +496,29 @@ int b200sv_selftest_op_sequence(int num_qubits, int64_t num_states, int precisio
   });
 }
 
+int b200sv_plan_epochs(int num_qubits, int local_qubits, int nops, const int *op_off, const int *op_qubits,
+                       const uint8_t *need_local, int min_run_bits, int multi_swap, int *phys, int64_t *plan_out,
+                       int64_t plan_cap, int64_t *plan_len) {
+  return guard([&] {
+    if (num_qubits < 1 || num_qubits > 62 || local_qubits < 1 || local_qubits > num_qubits || nops < 0 || !phys ||
+        !plan_len || (nops > 0 && (!op_off || !op_qubits || !need_local)))
+      throw Error("plan_epochs: bad arguments");
+    std::vector<char> seen(num_qubits, 0);
+    for (int q = 0; q < num_qubits; q++) {
+      if (phys[q] < 0 || phys[q] >= num_qubits || seen[phys[q]]) throw Error("plan_epochs: phys is not a permutation");
+      seen[phys[q]] = 1;
+    }
+    for (int k = 0; k < (nops ? op_off[nops] : 0); k++)
+      if (op_qubits[k] < 0 || op_qubits[k] >= num_qubits) throw Error("plan_epochs: qubit out of range");
+    std::vector<int64_t> out;
+    plan_epochs(num_qubits, local_qubits, num_qubits - local_qubits, nops, op_off, op_qubits, need_local, min_run_bits,
+                multi_swap != 0, phys, out);
+    *plan_len = (int64_t)out.size();
+    if ((int64_t)out.size() > plan_cap || (out.size() && !plan_out)) throw Error("plan_epochs: plan buffer too small");
+    std::copy(out.begin(), out.end(), plan_out);
+  });
+}
+
 int b200sv_apply_batched_pauli(b200sv_handle h, const uint64_t *masks4) {
   return guard([&] { select(H); launch_batched_pauli(*H, masks4); });
 }

@@ -124,6 +124,10 @@ void launch_multi_swap_peer(State &s, int k, const int *local_q, uint32_t my_g, 
 int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats, int low_bits,
                         const int *slot = nullptr, const uint8_t *codes_host = nullptr, int nslots = 0);
 
+// ---- epoch planner for sharded registers (planner.cu, host only)
+void plan_epochs(int n, int nl, int gbits, int nops, const int *op_off, const int *op_qubits, const uint8_t *need_local,
+                 int min_run_bits, bool multi_swap, int *phys, std::vector<int64_t> &out);
+
 // ---- reductions (reduce.cu) -------------------------------------------------
 void reduce_norm(State &s, double *out);
 void reduce_norm_matrix(State &s, const int *qubits, int k, const double *mat, double *out);

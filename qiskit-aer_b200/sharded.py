@@ -64,7 +64,59 @@ class ShardedRunner:
 
     # ---------------------------------------------------------------- planning (host, deterministic)
     def plan(self, ops, phys=None):
-        """Rewrite logical ops to physical ones, inserting ("swap", local_pos, global_bit) steps.
+        """Rewrite logical ops to physical ones, inserting ("swap", local_pos, global_bit) / ("mswap", ...) steps.
+        The scheduling itself is b200sv_plan_epochs (csrc/planner.cu); `_plan_py` below is the same algorithm in
+        Python, kept as the cross-check of tests/test_host_logic.py."""
+        import ctypes as C
+        from . import capi
+        phys = list(self.phys if phys is None else phys)
+        off, qs, need = [0], [], []
+        for op in ops:
+            q = list(op[1]) if op[0] in ("unitary", "diagonal") else list(op[2])
+            if op[0] == "diagonal" or (op[0] == "gate" and op[1] == "cp"):
+                loc = []
+            else:
+                loc = list(op[1]) if op[0] == "unitary" else self._gate_targets(op)
+            qs += q
+            need += [1 if x in loc else 0 for x in q]
+            off.append(len(qs))
+        n_ops = len(ops)
+        a_off = np.asarray(off, dtype=np.int32)
+        a_qs = np.asarray(qs if qs else [0], dtype=np.int32)
+        a_need = np.asarray(need if need else [0], dtype=np.uint8)
+        a_phys = np.asarray(phys, dtype=np.int32)
+        cap = len(qs) + 13 * (n_ops + 1)
+        buf = np.zeros(cap, dtype=np.int64)
+        plen = C.c_int64(0)
+        capi.check(capi.lib().b200sv_plan_epochs(
+            self.n, self.nl, n_ops, a_off.ctypes.data_as(C.POINTER(C.c_int)), a_qs.ctypes.data_as(C.POINTER(C.c_int)),
+            a_need.ctypes.data_as(C.POINTER(C.c_uint8)), int(self.min_run_bits), 1 if self.multi_swap else 0,
+            a_phys.ctypes.data_as(C.POINTER(C.c_int)), buf.ctypes.data_as(C.POINTER(C.c_int64)), cap, C.byref(plen)))
+        out, i = [], 0
+        rec = buf[:plen.value].tolist()
+        while i < len(rec):
+            if rec[i] == 0:
+                op, k = ops[rec[i + 1]], rec[i + 2]
+                pq = rec[i + 3:i + 3 + k]
+                if op[0] == "unitary":
+                    out.append(("unitary", pq, op[2]))
+                elif op[0] == "diagonal":
+                    out.append(("diagonal", pq, op[2]))
+                else:
+                    out.append(("gate", op[1], pq, op[3]))
+                i += 3 + k
+            elif rec[i] == 1:
+                out.append(("swap", rec[i + 1], rec[i + 2]))
+                i += 3
+            else:
+                k = rec[i + 1]
+                out.append(("mswap", rec[i + 2:i + 2 + k], rec[i + 2 + k:i + 2 + 2 * k]))
+                i += 2 + 2 * k
+        self.phys = [int(x) for x in a_phys]
+        return out
+
+    def _plan_py(self, ops, phys=None):
+        """Reference implementation of plan() (same algorithm, pure Python).
 
         Epoch scheduling: run EVERY gate that is executable under the current qubit map (respecting
         dependencies through shared qubits), then bring in the global qubit(s) the blocked gates wait

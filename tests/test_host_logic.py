@@ -96,3 +96,44 @@ def test_epoch_planner_invariants(world, n):
         assert [e for e in emitted if q in e[2]] == [w for w in want if q in w[2]]
     nsw = sum(1 if p[0] == "swap" else len(p[1]) if p[0] == "mswap" else 0 for p in plan)
     assert 0 < nsw <= 4 * r.gbits * 9  # far fewer than one exchange per layer and global qubit
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_cpp_epoch_planner_equals_python_reference(seed):
+    """b200sv_plan_epochs (csrc/planner.cu, what ShardedRunner.plan calls) against the same algorithm in Python
+    (ShardedRunner._plan_py): identical plans and final qubit maps on random circuits mixing dense / diagonal ops and
+    named gates with controls, random initial maps, pairwise and all-to-all swap modes."""
+    import qiskit_aer_b200  # noqa: F401
+    from qiskit_aer_b200 import circuits, sharded
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(8, 15))
+    gbits = int(rng.integers(1, 4))
+    ops = []
+    for _ in range(int(rng.integers(5, 120))):
+        kind = rng.integers(0, 6)
+        if kind <= 1:
+            k = int(rng.integers(1, 4))
+            ops.append(("unitary", [int(q) for q in rng.choice(n, size=k, replace=False)], np.eye(1 << k)))
+        elif kind == 2:
+            k = int(rng.integers(1, 4))
+            ops.append(("diagonal", [int(q) for q in rng.choice(n, size=k, replace=False)], np.ones(1 << k)))
+        else:
+            name = ["h", "cx", "cp", "swap", "ccx"][int(rng.integers(0, 5))]
+            k = {"h": 1, "cx": 2, "cp": 2, "swap": 2, "ccx": 3}[name]
+            ops.append(("gate", name, [int(q) for q in rng.choice(n, size=k, replace=False)], [0.3] if name == "cp" else []))
+    ops += circuits.quantum_volume(n, 2, seed)
+    phys0 = [int(x) for x in rng.permutation(n)]
+    plans = []
+    for fn in ("plan", "_plan_py"):
+        r = sharded.ShardedRunner.__new__(sharded.ShardedRunner)
+        r.n, r.gbits, r.nl, r.world, r.rank = n, gbits, n - gbits, 1 << gbits, 0
+        r.min_run_bits = int(rng.integers(0, n)) if fn == "plan" else plans[0][2]
+        r.multi_swap = bool(seed % 2)
+        r.phys = list(phys0)
+        mrb = r.min_run_bits
+        plan = getattr(r, fn)(ops)
+        plans.append(([(p[0], [int(x) for x in p[1]], None) if p[0] in ("unitary", "diagonal") else
+                       (p[0], p[1], [int(x) for x in p[2]]) if p[0] == "gate" else
+                       (p[0], p[1], p[2]) for p in plan], list(r.phys), mrb))
+    assert plans[0][0] == plans[1][0]
+    assert plans[0][1] == plans[1][1]

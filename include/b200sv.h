@@ -164,6 +164,17 @@ int b200sv_plan_epochs(int num_qubits, int local_qubits, int nops, const int *op
                        const uint8_t *need_local, int min_run_bits, int multi_swap, int *phys, int64_t *plan_out,
                        int64_t plan_cap, int64_t *plan_len);
 
+/* The engine's gate fusion (host code, no device; role of Fusion::optimize_circuit, src/transpile/fusion.hpp:849, with
+ * a B200 cost model instead of the CPU one of :1002-1136): dense blocks up to max_qubit qubits, purely diagonal blocks
+ * up to max_diag_qubit, diagonal gates commute.  b200sv_fuse_assign maps every op (given by its qubits and a "is
+ * diagonal" flag) to a block id (blocks are numbered in execution order); b200sv_fuse_block_matrix multiplies the gates
+ * of one block (row-major 2^m x 2^m complex<double> each, bit j of a gate index <-> its j-th qubit) into the block's
+ * 2^k x 2^k row-major matrix, or its 2^k diagonal when diag != 0 (bit i of the index <-> block_qubits[i]). */
+int b200sv_fuse_assign(int nops, const int *op_off, const int *op_qubits, const uint8_t *op_is_diag, int max_qubit,
+                       int window, int max_diag_qubit, int *block_of_op, int *nblocks);
+int b200sv_fuse_block_matrix(int k, const int *block_qubits, int ngates, const int *gate_off, const int *gate_qubits,
+                             const int64_t *gate_moff, const double *gate_mats, int diag, double *out);
+
 /* Per-state measurement collapse for batched containers (apply_batched_measure / apply_batched_reset,
  * qubitvector_thrust.hpp:2251-2460: check_measure_probability_func + reset_after_measure_func): for every
  * state s with active[s] != 0, amplitudes whose `qubits` bits differ from outcomes[s] are zeroed and the

@@ -47,6 +47,10 @@ SIGNATURES = {
     "b200sv_apply_gate_sequence": [_vp, C.c_int, C.POINTER(C.c_int), _u64p, _f64p, C.POINTER(C.c_int)],
     "b200sv_plan_epochs": [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint8),
                            C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int64)],
+    "b200sv_fuse_assign": [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int,
+                           C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "b200sv_fuse_block_matrix": [C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int64), _f64p, C.c_int, _f64p],
     "b200sv_selftest_op_sequence": [C.c_int, C.c_int64, C.c_int, _vp, C.c_int, C.POINTER(C.c_int), _u64p, _f64p,
                                     C.POINTER(C.c_int), C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int)],
     "b200sv_collapse": [_vp, _u64p, C.c_int, _u64p, _f64p, C.POINTER(C.c_uint8)],

@@ -519,6 +519,28 @@ int b200sv_plan_epochs(int num_qubits, int local_qubits, int nops, const int *op
   });
 }
 
+int b200sv_fuse_assign(int nops, const int *op_off, const int *op_qubits, const uint8_t *op_is_diag, int max_qubit,
+                       int window, int max_diag_qubit, int *block_of_op, int *nblocks) {
+  return guard([&] {
+    if (nops < 0 || !nblocks || (nops > 0 && (!op_off || !op_qubits || !op_is_diag || !block_of_op)) || max_qubit < 1 ||
+        max_qubit > 10 || max_diag_qubit < 1 || max_diag_qubit > 28 || window < 1)
+      throw Error("fuse_assign: bad arguments");
+    for (int k = 0; k < (nops ? op_off[nops] : 0); k++)
+      if (op_qubits[k] < 0 || op_qubits[k] > 62) throw Error("fuse_assign: qubit out of range");
+    fuse_assign(nops, op_off, op_qubits, op_is_diag, max_qubit, window, max_diag_qubit, block_of_op, nblocks);
+  });
+}
+
+int b200sv_fuse_block_matrix(int k, const int *block_qubits, int ngates, const int *gate_off, const int *gate_qubits,
+                             const int64_t *gate_moff, const double *gate_mats, int diag, double *out) {
+  return guard([&] {
+    if (k < 1 || k > (diag ? 28 : 10) || ngates < 1 || !block_qubits || !gate_off || !gate_qubits || !gate_moff ||
+        !gate_mats || !out)
+      throw Error("fuse_block_matrix: bad arguments");
+    fuse_block_matrix(k, block_qubits, ngates, gate_off, gate_qubits, gate_moff, gate_mats, diag, out);
+  });
+}
+
 int b200sv_apply_batched_pauli(b200sv_handle h, const uint64_t *masks4) {
   return guard([&] { select(H); launch_batched_pauli(*H, masks4); });
 }

@@ -128,6 +128,11 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
 void plan_epochs(int n, int nl, int gbits, int nops, const int *op_off, const int *op_qubits, const uint8_t *need_local,
                  int min_run_bits, bool multi_swap, int *phys, std::vector<int64_t> &out);
 
+void fuse_assign(int nops, const int *op_off, const int *op_qubits, const uint8_t *op_is_diag, int max_qubit, int window,
+                 int max_diag_qubit, int *block_of_op, int *nblocks_out);
+void fuse_block_matrix(int k, const int *block_qubits, int ngates, const int *gate_off, const int *gate_qubits,
+                       const int64_t *gate_moff, const double *gate_mats, int diag, double *out);
+
 // ---- reductions (reduce.cu) -------------------------------------------------
 void reduce_norm(State &s, double *out);
 void reduce_norm_matrix(State &s, const int *qubits, int k, const double *mat, double *out);

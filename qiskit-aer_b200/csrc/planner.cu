@@ -8,6 +8,7 @@
 // global qubits the blocked ops wait for, evicting the local qubits whose next use is farthest away (Belady), repeat.
 // Diagonal ops and controls never block on a global qubit (they are resolved from the chunk index).
 #include "common.cuh"
+#include <complex>
 
 namespace b200sv {
 
@@ -86,6 +87,104 @@ void plan_epochs(int n, int nl, int gbits, int nops, const int *op_off, const in
       for (auto &pr : pairs) { out.push_back(1); out.push_back(pr.first); out.push_back(pr.second); }
     }
   }
+}
+
+}  // namespace b200sv
+
+// ------------------------------------------------------------------------------------------ gate fusion (host)
+// The engine's own fusion pass (role of Fusion::optimize_circuit, src/transpile/fusion.hpp:849, cost model
+// :1002-1136) with the B200 cost model of DESIGN.md section 3: dense blocks grow to max_qubit (4 in double
+// precision: the last size that is still HBM bound), purely diagonal blocks to max_diag_qubit (their table streams
+// from shared memory / L2), and diagonal gates commute with each other, so a diagonal gate only depends on the
+// last NON-diagonal block that shares a qubit with it.  List scheduling over open blocks: a gate may join block B
+// iff no block emitted after B conflicts with it; preference: the last block it depends on, then any later block that
+// stays within the size limit, else a new block.
+namespace b200sv {
+
+void fuse_assign(int nops, const int *op_off, const int *op_qubits, const uint8_t *op_is_diag, int max_qubit,
+                 int window, int max_diag_qubit, int *block_of_op, int *nblocks_out) {
+  struct Blk { uint64_t mask = 0; bool diag = true; };
+  std::vector<Blk> blocks;
+  for (int i = 0; i < nops; i++) {
+    uint64_t qs = 0;
+    for (int k = op_off[i]; k < op_off[i + 1]; k++) qs |= 1ull << op_qubits[k];
+    const bool gdiag = op_is_diag[i] != 0;
+    const int nb = (int)blocks.size(), lo = std::max(0, nb - window);
+    int last_dep = -1;
+    for (int b = nb - 1; b >= lo; b--)
+      if ((qs & blocks[b].mask) && !(gdiag && blocks[b].diag)) { last_dep = b; break; }
+    if (lo > 0 && last_dep < 0) last_dep = lo - 1;  // cannot prove independence from blocks outside the window
+    int target = -1;
+    for (int pass = 0; pass < 2 && target < 0; pass++) {
+      const int b0 = pass == 0 ? last_dep : std::max(last_dep + 1, lo), b1 = pass == 0 ? last_dep + 1 : nb;
+      if (pass == 0 && last_dep < lo) continue;
+      for (int b = b0; b < b1; b++) {
+        const int uni = __builtin_popcountll(blocks[b].mask | qs);
+        const bool ok = (blocks[b].diag && gdiag) ? uni <= std::max(max_diag_qubit, max_qubit) : uni <= max_qubit;
+        if (ok) { target = b; break; }
+      }
+    }
+    if (target < 0) { blocks.emplace_back(); target = (int)blocks.size() - 1; }
+    blocks[target].mask |= qs;
+    blocks[target].diag = blocks[target].diag && gdiag;
+    block_of_op[i] = target;
+  }
+  *nblocks_out = (int)blocks.size();
+}
+
+// product of the gates of one block on `k` block qubits (bit i of the matrix index <-> block_qubits[i]); gate g acts
+// on gate_qubits[gate_off[g]..], its matrix is row-major 2^m x 2^m at gate_mats + gate_moff[g] (complex pairs).
+// diag != 0: out = 2^k diagonal entries; else out = 2^k x 2^k row-major.
+void fuse_block_matrix(int k, const int *block_qubits, int ngates, const int *gate_off, const int *gate_qubits,
+                       const int64_t *gate_moff, const double *gate_mats, int diag, double *out) {
+  typedef std::complex<double> cd;
+  const size_t dim = (size_t)1 << k;
+  cd *O = reinterpret_cast<cd *>(out);
+  auto pos_of = [&](int q) {
+    for (int i = 0; i < k; i++)
+      if (block_qubits[i] == q) return i;
+    throw Error("fuse_block_matrix: gate qubit outside the block");
+  };
+  if (diag) {
+    for (size_t i = 0; i < dim; i++) O[i] = 1.0;
+    for (int g = 0; g < ngates; g++) {
+      const int m = gate_off[g + 1] - gate_off[g];
+      const cd *U = reinterpret_cast<const cd *>(gate_mats) + gate_moff[g];
+      int pos[16];
+      for (int j = 0; j < m; j++) pos[j] = pos_of(gate_qubits[gate_off[g] + j]);
+      const size_t gd = (size_t)1 << m;
+      for (size_t i = 0; i < dim; i++) {
+        size_t sub = 0;
+        for (int j = 0; j < m; j++) sub |= ((i >> pos[j]) & 1) << j;
+        O[i] *= U[sub * gd + sub];
+      }
+    }
+    return;
+  }
+  std::vector<cd> M(dim * dim, 0.0), T(dim * dim);
+  for (size_t i = 0; i < dim; i++) M[i * dim + i] = 1.0;
+  for (int g = 0; g < ngates; g++) {  // M <- embed(U) M : rows of M mix inside each 2^m group
+    const int m = gate_off[g + 1] - gate_off[g];
+    const cd *U = reinterpret_cast<const cd *>(gate_mats) + gate_moff[g];
+    int pos[16];
+    for (int j = 0; j < m; j++) pos[j] = pos_of(gate_qubits[gate_off[g] + j]);
+    const size_t gd = (size_t)1 << m;
+    for (size_t r = 0; r < dim; r++) {
+      size_t sub_r = 0, base = r;
+      for (int j = 0; j < m; j++) { sub_r |= ((r >> pos[j]) & 1) << j; base &= ~((size_t)1 << pos[j]); }
+      for (size_t c = 0; c < dim; c++) {
+        cd acc = 0;
+        for (size_t e = 0; e < gd; e++) {
+          size_t src = base;
+          for (int j = 0; j < m; j++) src |= ((e >> j) & 1) << pos[j];
+          acc += U[sub_r * gd + e] * M[src * dim + c];
+        }
+        T[r * dim + c] = acc;
+      }
+    }
+    M.swap(T);
+  }
+  std::copy(M.begin(), M.end(), O);
 }
 
 }  // namespace b200sv

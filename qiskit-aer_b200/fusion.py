@@ -93,6 +93,62 @@ def _is_diag(U):
 
 def fuse(ops, max_qubit=5, window=64, max_diag_qubit=10):
     """Returns a list of ("unitary", qubits, U) / ("diagonal", qubits, d) ops equivalent to `ops`.
+    The block assignment and the block matrix products run in the library (b200sv_fuse_assign /
+    b200sv_fuse_block_matrix, csrc/planner.cu); `_fuse_py` below is the same algorithm in numpy, kept as the
+    cross-check of tests/test_host_logic.py."""
+    import ctypes as C
+    from . import capi
+    lib = capi.lib()
+    mats = [op_matrix(op) for op in ops]
+    n_ops = len(mats)
+    if n_ops == 0:
+        return []
+    off = np.zeros(n_ops + 1, dtype=np.int32)
+    for i, (q, _) in enumerate(mats):
+        off[i + 1] = off[i] + len(q)
+    qs = np.asarray([x for q, _ in mats for x in q], dtype=np.int32)
+    isd = np.asarray([1 if _is_diag(U) else 0 for _, U in mats], dtype=np.uint8)
+    blk = np.zeros(n_ops, dtype=np.int32)
+    nb = C.c_int(0)
+    ip = C.POINTER(C.c_int)
+    capi.check(lib.b200sv_fuse_assign(n_ops, off.ctypes.data_as(ip), qs.ctypes.data_as(ip),
+                                      isd.ctypes.data_as(C.POINTER(C.c_uint8)), int(max_qubit), int(window),
+                                      int(max_diag_qubit), blk.ctypes.data_as(ip), C.byref(nb)))
+    members = [[] for _ in range(nb.value)]
+    for i in range(n_ops):
+        members[blk[i]].append(i)
+    out = []
+    for ms in members:
+        bq = []
+        for i in ms:
+            for x in mats[i][0]:
+                if x not in bq:
+                    bq.append(x)
+        diag = all(isd[i] for i in ms)
+        goff = np.zeros(len(ms) + 1, dtype=np.int32)
+        moff = np.zeros(len(ms), dtype=np.int64)
+        flat, gq, pos = [], [], 0
+        for j, i in enumerate(ms):
+            q, U = mats[i]
+            goff[j + 1] = goff[j] + len(q)
+            gq += q
+            moff[j] = pos
+            U = np.ascontiguousarray(U, dtype=np.complex128)
+            flat.append(U.reshape(-1))
+            pos += U.size
+        gm = np.concatenate(flat)
+        k = len(bq)
+        res = np.empty((1 << k) if diag else (1 << k, 1 << k), dtype=np.complex128)
+        capi.check(lib.b200sv_fuse_block_matrix(
+            k, np.asarray(bq, dtype=np.int32).ctypes.data_as(ip), len(ms), goff.ctypes.data_as(ip),
+            np.asarray(gq, dtype=np.int32).ctypes.data_as(ip), moff.ctypes.data_as(C.POINTER(C.c_int64)),
+            gm.ctypes.data_as(C.POINTER(C.c_double)), 1 if diag else 0, res.ctypes.data_as(C.POINTER(C.c_double))))
+        out.append(("diagonal", list(bq), res) if diag else ("unitary", list(bq), res))
+    return out
+
+
+def _fuse_py(ops, max_qubit=5, window=64, max_diag_qubit=10):
+    """Reference implementation of fuse() in numpy (same algorithm).
 
     Commutation aware: diagonal gates commute with each other, so a diagonal gate only depends on the
     last NON-diagonal block that shares a qubit with it, and purely diagonal blocks may grow to

@@ -137,3 +137,43 @@ def test_cpp_epoch_planner_equals_python_reference(seed):
                        (p[0], p[1], p[2]) for p in plan], list(r.phys), mrb))
     assert plans[0][0] == plans[1][0]
     assert plans[0][1] == plans[1][1]
+
+
+@pytest.mark.parametrize("case", ["qft", "qv", "mixed0", "mixed1", "mixed2"])
+@pytest.mark.parametrize("mq,md", [(4, 16), (5, 10), (3, 12)])
+def test_cpp_fusion_equals_python_reference(case, mq, md):
+    """b200sv_fuse_assign / b200sv_fuse_block_matrix (what fusion.fuse calls) against fusion._fuse_py: same blocks in the
+    same order, matrices / diagonals equal to rounding."""
+    import qiskit_aer_b200  # noqa: F401
+    from qiskit_aer_b200 import circuits, fusion
+    n = 11
+    if case == "qft":
+        ops = circuits.qft(n)
+    elif case == "qv":
+        ops = circuits.quantum_volume(n, 6, 3)
+    else:
+        rng = np.random.default_rng(int(case[-1]))
+        ops = []
+        for _ in range(150):
+            r = rng.integers(0, 6)
+            if r == 0:
+                ops.append(("gate", "h", [int(rng.integers(0, n))], []))
+            elif r == 1:
+                a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+                ops.append(("gate", "cp", [a, b], [float(rng.uniform(0, 3))]))
+            elif r == 2:
+                a, b = (int(x) for x in rng.choice(n, size=2, replace=False))
+                ops.append(("gate", "cx", [a, b], []))
+            elif r == 3:
+                k = int(rng.integers(1, 4))
+                ops.append(("diagonal", [int(x) for x in rng.choice(n, size=k, replace=False)],
+                            np.exp(1j * rng.uniform(0, 6.28, 1 << k))))
+            else:
+                k = int(rng.integers(1, 3))
+                ops.append(("unitary", [int(x) for x in rng.choice(n, size=k, replace=False)], opgen.haar_unitary(rng, 1 << k)))
+    a = fusion.fuse(ops, max_qubit=mq, max_diag_qubit=md)
+    b = fusion._fuse_py(ops, max_qubit=mq, max_diag_qubit=md)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x[0] == y[0] and list(x[1]) == list(y[1])
+        assert np.max(np.abs(np.asarray(x[2]) - np.asarray(y[2]))) < 1e-13

@@ -455,9 +455,11 @@ tile_pipe_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
       // the group's first warp fetches them (uniform branch, uniform parameter index: anything thread-indexed here makes
       // the compiler move the parameter block to local memory and the gate matrices off the uniform datapath)
       if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0) {
-        for (int i = 0; i < p.npauli; i++)
-          scodes[grp * (kMaxRounds + 16) + i] = p.codes[(size_t)p.pauli_slot[i] * p.nstates + (t >> p.state_shift)];
-        scodes[grp * (kMaxRounds + 16) + kMaxRounds] = 0;  // "no Pauli"
+        for (int i = 0; i < p.npauli; i++) {  // every lane reads (uniform address), lane 0 writes
+          const uint8_t v = p.codes[(size_t)p.pauli_slot[i] * p.nstates + (t >> p.state_shift)];
+          if ((tid & 31) == 0) scodes[grp * (kMaxRounds + 16) + i] = v;
+        }
+        if ((tid & 31) == 0) scodes[grp * (kMaxRounds + 16) + kMaxRounds] = 0;  // "no Pauli"
       }
       if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
       else asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -628,8 +630,11 @@ __global__ void __maxnreg__(96) tile_pipe2_kernel(double2 *__restrict__ psi, con
     uint8_t *sc = scodes + (grp * 2 + (kk & 1)) * (kMaxRounds + 16);
     if (MODE == 4) {
       if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0) {
-        for (int i = 0; i < p.npauli; i++) sc[i] = p.codes[(size_t)p.pauli_slot[i] * p.nstates + (t >> p.state_shift)];
-        sc[kMaxRounds] = 0;
+        for (int i = 0; i < p.npauli; i++) {  // every lane reads (uniform address), lane 0 writes
+          const uint8_t v = p.codes[(size_t)p.pauli_slot[i] * p.nstates + (t >> p.state_shift)];
+          if ((tid & 31) == 0) sc[i] = v;
+        }
+        if ((tid & 31) == 0) sc[kMaxRounds] = 0;
       }
       if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
       else asm volatile("bar.sync 1, 256;" ::: "memory");

@@ -1706,6 +1706,8 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
       if ((Q >> q) & 1) tile_bits.push_back(q);
     const std::vector<int> back = run_tile_pass(s, gates, sel, tile_bits, dev_codes, kTB);
     passes++;
+    static const int env_trace = [] { const char *e = getenv("B200SV_TILE_TRACE"); return e ? atoi(e) : 0; }();
+    if (env_trace) fprintf(stderr, "b200sv tile pass %d: %zu ops (%zu deferred)\n", passes, sel.size(), back.size());
     if (env_pack) {
       if (back.size() == sel.size()) throw Error("tile pass: no progress");
       packer.commit(sel, back);

@@ -51,6 +51,10 @@ const char *b200sv_last_error(void);
 /* number of visible CUDA devices (chunk_manager.hpp:166-190) */
 int b200sv_device_count(int *count);
 
+/* free / total memory of one device: what DeviceChunkContainer::Allocate sizes its chunk count from
+ * (chunk/device_chunk_container.hpp:391-404 cudaMemGetInfo; circuit_executor.hpp:378-392 get_gpu_memory_mb) */
+int b200sv_mem_info(int device, uint64_t *free_bytes, uint64_t *total_bytes);
+
 /* QubitVector(), set_num_qubits (qubitvector.hpp:922; thrust :860 chunk_setup).
  * Allocates num_states << num_qubits amplitudes on `device` and a private stream. */
 int b200sv_create(b200sv_handle *out, int num_qubits, int64_t num_states, int precision, int device);
@@ -221,6 +225,15 @@ int b200sv_chunk_swap_peer(b200sv_handle h, int local_q, void *peer_dev_ptr, int
  * (balanced), in place, both NVLink directions busy: (1 - 2^-k) of the slice crosses the links once instead
  * of k half-slice exchanges. */
 int b200sv_multi_swap_peer(b200sv_handle h, int k, const int *local_q, uint32_t my_g, void *const *peer_dev_ptrs);
+/* apply_chunk_swap(chunk, dest_offset, src_offset, size) (qubitvector.hpp:1824-1840; the sub-block shuffle of
+ * apply_multi_chunk_swap, parallel_state_executor.hpp:1474-1500) and the whole-chunk exchange of a swap between two
+ * global qubits (qubitvector.hpp:1765-1776): `count` amplitudes at this[dest_offset] trade places with
+ * peer_dev_ptr[src_offset].  The peer chunk may live on another GPU of this process (peer access is enabled on first
+ * use, chunk_manager.hpp:129-135) or be an IPC mapping. */
+int b200sv_swap_range_peer(b200sv_handle h, uint64_t dest_offset, void *peer_dev_ptr, uint64_t src_offset, uint64_t count);
+/* one-way variant (write_back = false, qubitvector.hpp:1771-1775; initialize(const QubitVector&) :1121): this[dest_offset ..)
+ * <- peer_dev_ptr[src_offset ..), stream-ordered device-to-device copy */
+int b200sv_copy_range_peer(b200sv_handle h, uint64_t dest_offset, const void *peer_dev_ptr, uint64_t src_offset, uint64_t count);
 /* staging variant for NCCL send/recv: gather/scatter the half-slice of amplitudes whose
  * local qubit `local_q` equals `bit`, slice [begin, begin+count) of that half, to/from a
  * contiguous device buffer (send_buffer/recv_buffer, qubitvector.hpp:1061-1081). */
@@ -237,6 +250,55 @@ int b200sv_ipc_open(b200sv_handle h, const void *handle64, void **peer_dev_ptr);
 int b200sv_ipc_close(b200sv_handle h, void *peer_dev_ptr);
 /* run this handle's kernels on a caller-owned stream from now on (e.g. the torch stream NCCL is ordered on) */
 int b200sv_set_stream(b200sv_handle h, void *cuda_stream);
+
+/* ---- sharded registers: the executor (csrc/sharded.cu) ------------------------------------------------------------
+ * One register of num_qubits qubits split over `world` = 2^g shards by its top g qubits, one shard per GPU -- the
+ * B200 counterpart of ParallelStateExecutor + ChunkManager (src/simulators/parallel_state_executor.hpp:318-376 chunk
+ * placement, :772 apply_ops_chunks, :1134-1552 chunk swaps; statevector/chunk/chunk_manager.hpp:129-135,166-396
+ * devices, peer access, memory sizing) and of Statevector::Executor's cross-chunk reductions
+ * (statevector/statevector_executor.hpp:551 expval_pauli, :1149 sample_measure), with the host side in C++:
+ * epoch planning, gate queues, tile passes, the exchange and its overlap with the passes next to it all run behind
+ * these calls.  The shards listed in local_ranks live in THIS process on devices[i] (one process may drive all GPUs --
+ * the layout of Aer's Controller -- or one GPU each under torchrun); shards of other processes are attached from the
+ * 128-byte blobs their owners export (CUDA IPC: slice + staging / flag area).  staging_bytes = size of each shard's
+ * staging area for the pipelined exchange ((uint64_t)-1: what the device can spare; 0: in-place exchange only). */
+typedef struct b200sv_sharded *b200sv_sharded_handle;
+enum { B200SV_OP_MATRIX = 0, B200SV_OP_DIAGONAL = 1, B200SV_OP_MCX = 2, B200SV_OP_MCY = 3, B200SV_OP_MCPHASE = 4,
+       B200SV_OP_MCSWAP = 5, B200SV_OP_MCU = 6 };
+int b200sv_sharded_create(b200sv_sharded_handle *out, int num_qubits, int precision, int world, int nlocal,
+                          const int *local_ranks, const int *devices, uint64_t staging_bytes);
+int b200sv_sharded_destroy(b200sv_sharded_handle h);
+int b200sv_sharded_ipc_export(b200sv_sharded_handle h, int rank, void *blob128);
+int b200sv_sharded_ipc_attach(b200sv_sharded_handle h, int rank, const void *blob128);
+/* the plain handle of a local shard (download, norm, ... through the calls above; owned by the sharded handle) */
+int b200sv_sharded_shard_handle(b200sv_sharded_handle h, int rank, b200sv_handle *out);
+/* |0...0> of the whole register (Executor::initialize_qreg, statevector_executor.hpp:437-470); resets the qubit map */
+int b200sv_sharded_initialize(b200sv_sharded_handle h);
+/* waits for all local shards; reports a partner that never arrived at an exchange */
+int b200sv_sharded_synchronize(b200sv_sharded_handle h);
+/* Apply a circuit given by LOGICAL qubits: op i has kind kinds[i], qubits op_qubits[op_off[i] .. op_off[i+1]) (controls
+ * first, targets last) and data[data_off[i] .. data_off[i+1]) doubles (matrix: 2*4^k column-major like
+ * b200sv_apply_matrix; diagonal: 2*2^k; mcphase: re, im; mcu: 8; mcx / mcy / mcswap: none).  Asynchronous. */
+int b200sv_sharded_apply_ops(b200sv_sharded_handle h, int nops, const int *kinds, const int *op_off, const int *op_qubits,
+                             const int64_t *data_off, const double *data);
+/* host-only: what apply_ops would do on a register of `world` shards with the given staging size -- out8 = {tile
+ * passes of shard 0, exchanges, staged, in place, passes taken along by exchanges, finest slab count, coarsest slab
+ * count, qubit swaps} (test and sizing aid; no device involved) */
+int b200sv_sharded_plan_only(int num_qubits, int precision, int world, uint64_t staging_bytes, int nops, const int *kinds,
+                             const int *op_off, const int *op_qubits, const int64_t *data_off, const double *data,
+                             double *out8);
+/* of the last apply_ops: {tile passes, exchanges, staged, in place, kernel launches, DMA copies, bytes sent per shard,
+ * passes that ran slab-wise next to an exchange} */
+int b200sv_sharded_stats(b200sv_sharded_handle h, double *out8);
+/* device time of the last apply_ops (CUDA events on the shards' compute streams, max over local shards) */
+int b200sv_sharded_elapsed_ms(b200sv_sharded_handle h, double *ms);
+/* logical qubit -> physical position (>= local qubits: selects the shard) */
+int b200sv_sharded_qubit_map(b200sv_sharded_handle h, int *phys);
+int b200sv_sharded_restore_order(b200sv_sharded_handle h);
+int b200sv_sharded_norms(b200sv_sharded_handle h, double *out_world);
+int b200sv_sharded_expval_pauli(b200sv_sharded_handle h, const uint64_t *qubits, int k, const char *pauli, double *partial);
+int b200sv_sharded_sample_measure(b200sv_sharded_handle h, const double *rnds, int64_t shots, const double *norms_world,
+                                  uint64_t *out);
 
 /* ---- host RNG identical to Aer's RngEngine (framework/rng.hpp:31-99) ------ */
 /* n draws of rand(0,1) from std::mt19937_64 seeded with `seed` (what

@@ -17,12 +17,18 @@
 // Three modes, chosen by how the executors call chunk_setup():
 //  * single state (Executor::run_circuit_*): one vector = one handle;
 //  * cache blocking (ParallelStateExecutor): one vector = one chunk = one handle;
-//    like the CPU class it reports support_global_indexing() == false, so the
-//    State rewrites global-qubit diagonals/controls per chunk on the host
-//    (statevector_state.hpp:735-753) and chunk swaps arrive through
-//    apply_chunk_swap(qubits, other_chunk, write_back);
+//    the chunks of a register are spread over the target GPUs in contiguous runs
+//    (chunk i of C lives on target_gpus[i * G / C], as chunk_manager.hpp:330-353
+//    places them), like the CPU class it reports support_global_indexing() ==
+//    false, so the State rewrites global-qubit diagonals/controls per chunk on
+//    the host (statevector_state.hpp:735-753) and chunk swaps arrive through
+//    apply_chunk_swap(qubits, other_chunk, write_back) /
+//    apply_chunk_swap(other_chunk, dest_offset, src_offset, size): in-place
+//    kernels over NVLink peer access when the two chunks sit on different GPUs;
 //  * batched shots (BatchShotsExecutor, `batched_shots_gpu`): every vector of a
 //    group is a view on ONE container handle with num_states = shots.  With
+//    (one container per target GPU, shots split evenly: the executor sees one
+//    group per GPU and drives them from parallel OpenMP threads).  With
 //    enable_batch(true) the first vector executes for all states in one launch
 //    and the others return immediately (the get_chunk_count() contract,
 //    qubitvector_thrust.hpp:1201-1214); with enable_batch(false) a vector acts
@@ -98,6 +104,36 @@ struct Batch {
   OpQueue queue;
   ~Batch() { if (h) b200sv_destroy(h); }
 };
+// the containers of one multi-shot allocation, one per target GPU (chunk_manager.hpp:223-264 spreads the shots
+// over the devices); part p holds the states [first[p], first[p + 1]) of the allocation
+struct BatchSet {
+  std::vector<std::shared_ptr<Batch>> parts;
+  std::vector<uint_t> first;
+};
+// the chunks of one cache-blocked register: which GPU holds which chunk
+struct ChunkGroup {
+  std::vector<int> devices;
+  uint_t first_index = 0, num_chunks = 1;
+  int device_of(uint_t chunk_index) const {
+    const uint_t local = chunk_index - first_index;
+    return devices[(size_t)(local * devices.size() / num_chunks)];
+  }
+};
+// target GPUs of an allocation: the executor's list (circuit_executor.hpp:340-359), else every visible device.
+// B200SV_VIRTUAL_GPUS=k (test knob) repeats the list k times so that a one-GPU box exercises the multi-device
+// placement, grouping and peer-swap paths.
+inline std::vector<int> resolve_devices(const reg_t &targets, int fallback) {
+  std::vector<int> d;
+  for (auto t : targets) d.push_back((int)t);
+  if (d.empty()) d.push_back(fallback);
+  if (const char *e = getenv("B200SV_VIRTUAL_GPUS")) {
+    const int k = atoi(e);
+    std::vector<int> rep;
+    for (int i = 0; i < k; i++) rep.insert(rep.end(), d.begin(), d.end());
+    if (!rep.empty()) d.swap(rep);
+  }
+  return d;
+}
 }  // namespace b200detail
 
 template <typename data_t = double> class QubitVectorB200 {
@@ -112,7 +148,9 @@ public:
       if (o.h_) o.flush();
       release();
       h_ = o.h_; num_qubits_ = o.num_qubits_; data_size_ = o.data_size_; chunk_index_ = o.chunk_index_;
-      batch_ = std::move(o.batch_); batch_pos_ = o.batch_pos_; view_ = o.view_; tmp_view_ = o.tmp_view_;
+      batch_ = std::move(o.batch_); batch_set_ = std::move(o.batch_set_); group_ = std::move(o.group_);
+      batch_pos_ = o.batch_pos_; view_ = o.view_; tmp_view_ = o.tmp_view_; tmp_view_state_ = o.tmp_view_state_;
+      device_ = o.device_; target_gpus_ = o.target_gpus_; queue_ = std::move(o.queue_);
       o.h_ = nullptr; o.view_ = nullptr; o.tmp_view_ = nullptr; o.num_qubits_ = 0; o.data_size_ = 0;
     }
     return *this;
@@ -131,10 +169,12 @@ public:
     }
     if (h_ && num_qubits == num_qubits_) return;
     release();
-    ck(b200sv_create(&h_, (int)num_qubits, 1, sizeof(data_t) == 8 ? B200SV_F64 : B200SV_F32, device()));
+    ck(b200sv_create(&h_, (int)num_qubits, 1, sizeof(data_t) == 8 ? B200SV_F64 : B200SV_F32, my_device()));
     num_qubits_ = num_qubits;
     data_size_ = 1ull << num_qubits;
   }
+  // GPU this vector's amplitudes live on: its chunk's place in a cache-blocked register, else the first target GPU
+  int my_device() const { return group_ ? group_->device_of(chunk_index_) : (device_ >= 0 ? device_ : device()); }
   virtual uint_t num_qubits() const { return num_qubits_; }
   uint_t size() const { return data_size_; }
   size_t required_memory_mb(uint_t num_qubits) const {
@@ -142,6 +182,8 @@ public:
     size_t shift_mb = std::max<int_t>(0, num_qubits + unit - 20);
     return 1ULL << shift_mb;
   }
+  // first vector of a container (= of a GPU's share of the shots) in batched mode; every chunk is its own group in
+  // cache-blocking mode (one handle, one stream and one gate queue per chunk)
   bool top_of_group() { return batch_ ? batch_pos_ == 0 : true; }
   std::complex<data_t> *data() const { return nullptr; }  // amplitudes live in HBM
   void *device_data() const { void *p = nullptr; flush(); ck(b200sv_device_ptr(Hs(), &p)); return p; }
@@ -154,14 +196,17 @@ public:
   uint_t get_omp_threshold() { return omp_threshold_; }
   void set_num_threads_per_group(int) {}
   void cuStateVec_enable(bool) {}
-  void set_target_gpus(reg_t &t) { if (!t.empty()) device() = (int)t[0]; }
+  void set_target_gpus(reg_t &t) {
+    target_gpus_ = t;
+    if (!t.empty()) { device() = (int)t[0]; device_ = (int)t[0]; }
+  }
   void set_sample_measure_index_size(int n) { sample_measure_index_size_ = n; }
   int get_sample_measure_index_size() { return sample_measure_index_size_; }
   void set_max_matrix_bits(int_t) {}
   void set_max_sampling_shots(int_t) {}
   void synchronize(void) { if (batch_ || h_) { flush(); ck(b200sv_synchronize(Hs())); } }
   bool support_global_indexing(void) { return false; }
-  virtual bool batched_optimization_supported(void) { return sizeof(data_t) == 8; }
+  virtual bool batched_optimization_supported(void) { return true; }
 
   // enable_batch (qubitvector_thrust.hpp:1184-1198): returns the previous setting
   virtual bool enable_batch(bool flg) const {
@@ -178,29 +223,57 @@ public:
   uint_t chunk_setup(int chunk_bits, int num_qubits, uint_t chunk_index, uint_t num_local_chunks) {
     chunk_index_ = chunk_index;
     drop_batch();
-    if (chunk_bits == num_qubits && num_local_chunks > 1 && sizeof(data_t) == 8) {
+    group_.reset();
+    const std::vector<int> devs = b200detail::resolve_devices(target_gpus_, device());
+    if (chunk_bits == num_qubits && num_local_chunks > 1) {
+      // multi-shot containers, one per target GPU; single precision included (aer_controller.hpp:642-646 batches
+      // QubitVectorThrust<float> too)
       release();
-      batch_ = std::make_shared<b200detail::Batch>();
-      ck(b200sv_create(&batch_->h, chunk_bits, (int64_t)num_local_chunks, B200SV_F64, device()));
-      batch_->nq = chunk_bits;
-      batch_->nstates = num_local_chunks;
-      batch_->first_index = chunk_index;
-      batch_->cregs.resize(num_local_chunks);
+      const size_t G = std::min<size_t>(devs.size(), (size_t)num_local_chunks);
+      batch_set_ = std::make_shared<b200detail::BatchSet>();
+      for (size_t g = 0; g < G; g++) {
+        const uint_t lo = num_local_chunks * g / G, hi = num_local_chunks * (g + 1) / G;
+        auto b = std::make_shared<b200detail::Batch>();
+        ck(b200sv_create(&b->h, chunk_bits, (int64_t)(hi - lo), sizeof(data_t) == 8 ? B200SV_F64 : B200SV_F32, devs[g]));
+        b->nq = chunk_bits;
+        b->nstates = hi - lo;
+        b->first_index = chunk_index + lo;
+        b->cregs.resize(hi - lo);
+        batch_set_->parts.push_back(b);
+        batch_set_->first.push_back(chunk_index + lo);
+      }
+      batch_set_->first.push_back(chunk_index + num_local_chunks);
+      batch_ = batch_set_->parts[0];
       batch_pos_ = 0;
       num_qubits_ = chunk_bits;
       data_size_ = 1ull << chunk_bits;
+    } else if (chunk_bits < num_qubits && num_local_chunks > 1) {
+      // cache blocking: chunk i of the register lives on devs[i * G / C]
+      auto g = std::make_shared<b200detail::ChunkGroup>();
+      g->devices = devs;
+      g->first_index = chunk_index;
+      g->num_chunks = num_local_chunks;
+      if (h_ && g->device_of(chunk_index) != my_device()) release();
+      group_ = g;
     }
     return num_local_chunks;
   }
   uint_t chunk_setup(QubitVectorB200<data_t> &base, const uint_t chunk_index) {
     chunk_index_ = chunk_index;
     drop_batch();
-    if (base.batch_) {
+    group_.reset();
+    if (base.batch_set_) {
       release();
-      batch_ = base.batch_;
+      const auto &bs = *base.batch_set_;
+      size_t p = 0;
+      while (p + 1 < bs.parts.size() && chunk_index >= bs.first[p + 1]) p++;
+      batch_ = bs.parts[p];
       batch_pos_ = chunk_index - batch_->first_index;
       num_qubits_ = batch_->nq;
       data_size_ = 1ull << batch_->nq;
+    } else if (base.group_) {
+      if (h_ && base.group_->device_of(chunk_index) != my_device()) release();
+      group_ = base.group_;
     }
     return 0;
   }
@@ -214,37 +287,50 @@ public:
   void release_send_buffer(void) const {}
   void release_recv_buffer(void) const {}
 
-  // apply_chunk_swap(qubits, chunk, write_back): qubitvector.hpp:1753-1790
+  // apply_chunk_swap(qubits, chunk, write_back): qubitvector.hpp:1753-1790.  The partner chunk may live on another
+  // GPU: the kernels reach it over NVLink peer access (enabled by the library on first use).
   void apply_chunk_swap(const reg_t &qubits, QubitVectorB200<data_t> &src, bool write_back = true) {
     uint_t q0 = qubits[qubits.size() - 2], q1 = qubits[qubits.size() - 1];
     if (q0 > q1) std::swap(q0, q1);
     synchronize();
     src.synchronize();
-    if (q0 >= num_qubits_) {  // both global: exchange (or copy) whole chunks
-      const size_t bytes = data_size_ * sizeof(std::complex<data_t>);
-      std::vector<char> a(bytes), b(bytes);  // rare path (X on a global qubit): staged through the host
-      ck(b200sv_download(src.Hs(), b.data(), 0, data_size_));
-      if (write_back) { ck(b200sv_download(Hs(), a.data(), 0, data_size_)); ck(b200sv_upload(src.Hs(), a.data(), 0, data_size_)); }
-      ck(b200sv_upload(Hs(), b.data(), 0, data_size_));
+    void *peer = src.device_data();
+    if (q0 >= num_qubits_) {  // both global: exchange whole chunks on the device
+      if (write_back) ck(b200sv_swap_range_peer(Hs(), 0, peer, 0, data_size_));
+      else ck(b200sv_copy_range_peer(Hs(), 0, peer, 0, data_size_));  // copy only (qubitvector.hpp:1771-1775)
+      synchronize();
       return;
     }
     // this (lower chunk: its q0=1 half) <-> src (q0=0 half); the kernel moves both directions
     const bool this_is_upper = !(chunk_index_ < src.chunk_index_);
-    void *peer = src.device_data();
     ck(b200sv_chunk_swap_peer(Hs(), (int)q0, peer, this_is_upper ? 1 : 0, 0));
     ck(b200sv_chunk_swap_peer(Hs(), (int)q0, peer, this_is_upper ? 1 : 0, 1));
     synchronize();
   }
+  // MPI-only overload (parallel_state_executor.hpp:1331, inside #ifdef AER_MPI): inter-process exchange is NCCL / NVLink
+  // here (b200sv_sharded_*), so this entry point is unreachable in a build without AER_MPI.
   void apply_chunk_swap(const reg_t &, uint_t) { throw std::runtime_error("QubitVectorB200: remote (MPI) chunk swap is not supported"); }
-  void apply_chunk_swap(QubitVectorB200<data_t> &, uint_t, uint_t, uint_t) { throw std::runtime_error("QubitVectorB200: multi chunk swap is not supported"); }
+  // apply_chunk_swap(chunk, dest_offset, src_offset, size) (qubitvector.hpp:1824-1840): the sub-block shuffle of
+  // ParallelStateExecutor::apply_multi_chunk_swap (:1474-1500) -- `size` amplitudes of this chunk trade places with
+  // `size` amplitudes of `src`, in place on the device(s).
+  void apply_chunk_swap(QubitVectorB200<data_t> &src, uint_t dest_offset, uint_t src_offset, uint_t size) {
+    if (src.chunk_index_ == chunk_index_)
+      throw std::runtime_error("QubitVectorB200: receive-buffer copy belongs to the MPI path, which is not supported");
+    synchronize();
+    src.synchronize();
+    ck(b200sv_swap_range_peer(Hs(), dest_offset, src.device_data(), src_offset, size));
+    synchronize();
+  }
 
   //---------------------------------------------------------------- data
   void zero() { if (idle()) return; drop_queue(); ck(b200sv_zero(H())); }
   void initialize() { if (idle()) return; drop_queue(); ck(b200sv_initialize(H())); }
   void initialize(const QubitVectorB200<data_t> &obj) {
     set_num_qubits(obj.num_qubits_);
-    auto v = obj.copy_to_vector();
-    flush(); ck(b200sv_upload(Hs(), v.data(), 0, data_size_));
+    drop_queue();  // whatever was queued would act on data that is overwritten now
+    const_cast<QubitVectorB200<data_t> &>(obj).synchronize();
+    ck(b200sv_copy_range_peer(Hs(), 0, obj.device_data(), 0, data_size_));
+    ck(b200sv_synchronize(Hs()));
   }
   template <typename list_t> void initialize_from_vector(const list_t &vec) {
     if (data_size_ != vec.size()) throw std::runtime_error("QubitVector::initialize input vector is incorrect length");
@@ -689,7 +775,11 @@ protected:
     flush();
     if (batch_ && batch_->on) {  // set_statevec in batched mode: every shot starts from the same vector
       if (batch_pos_ != 0) return;
-      for (size_t s = 0; s < batch_->nstates; s++) ck(b200sv_upload(batch_->h, data, s << num_qubits_, data_size_));
+      // one host -> device transfer, then stream-ordered device copies into the other shots
+      ck(b200sv_upload(batch_->h, data, 0, data_size_));
+      void *base = nullptr;
+      ck(b200sv_device_ptr(batch_->h, &base));
+      for (size_t s = 1; s < batch_->nstates; s++) ck(b200sv_copy_range_peer(batch_->h, s << num_qubits_, base, 0, data_size_));
       return;
     }
     ck(b200sv_upload(Hs(), data, 0, data_size_));
@@ -773,6 +863,7 @@ protected:
     if (view_) { b200sv_destroy(view_); view_ = nullptr; }
     if (tmp_view_) { b200sv_destroy(tmp_view_); tmp_view_ = nullptr; }
     batch_.reset();
+    batch_set_.reset();
     batch_pos_ = 0;
   }
   void release() {
@@ -789,6 +880,10 @@ protected:
   double json_chop_threshold_ = 0;
   mutable b200detail::OpQueue queue_;
   std::shared_ptr<b200detail::Batch> batch_;
+  std::shared_ptr<b200detail::BatchSet> batch_set_;   // first vector of a multi-shot allocation only
+  std::shared_ptr<b200detail::ChunkGroup> group_;     // cache-blocking mode: placement of the register's chunks
+  reg_t target_gpus_;
+  int device_ = -1;
   size_t batch_pos_ = 0;
   mutable b200sv_handle view_ = nullptr, tmp_view_ = nullptr;
   mutable size_t tmp_view_state_ = 0;

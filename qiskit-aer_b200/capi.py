@@ -64,6 +64,9 @@ SIGNATURES = {
                                  C.c_double, _f64p],
     "b200sv_chunk_swap_peer": [_vp, C.c_int, _vp, C.c_int, C.c_int],
     "b200sv_multi_swap_peer": [_vp, C.c_int, C.POINTER(C.c_int), C.c_uint32, C.POINTER(_vp)],
+    "b200sv_swap_range_peer": [_vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64],
+    "b200sv_copy_range_peer": [_vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64],
+    "b200sv_mem_info": [C.c_int, _u64p, _u64p],
     "b200sv_pack_half": [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _vp],
     "b200sv_unpack_half": [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _vp],
     "b200sv_ipc_export": [_vp, _vp],
@@ -71,6 +74,26 @@ SIGNATURES = {
     "b200sv_ipc_close": [_vp, _vp],
     "b200sv_set_stream": [_vp, _vp],
     "b200sv_rng_uniform": [C.c_uint64, C.c_int64, _f64p],
+    # sharded executor (csrc/sharded.cu)
+    "b200sv_sharded_create": [C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                              C.c_uint64],
+    "b200sv_sharded_destroy": [_vp],
+    "b200sv_sharded_ipc_export": [_vp, C.c_int, _vp],
+    "b200sv_sharded_ipc_attach": [_vp, C.c_int, _vp],
+    "b200sv_sharded_shard_handle": [_vp, C.c_int, C.POINTER(_vp)],
+    "b200sv_sharded_initialize": [_vp],
+    "b200sv_sharded_synchronize": [_vp],
+    "b200sv_sharded_apply_ops": [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int64), _f64p],
+    "b200sv_sharded_plan_only": [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_int), C.POINTER(C.c_int64), _f64p, _f64p],
+    "b200sv_sharded_stats": [_vp, _f64p],
+    "b200sv_sharded_elapsed_ms": [_vp, _f64p],
+    "b200sv_sharded_qubit_map": [_vp, C.POINTER(C.c_int)],
+    "b200sv_sharded_restore_order": [_vp],
+    "b200sv_sharded_norms": [_vp, _f64p],
+    "b200sv_sharded_expval_pauli": [_vp, _u64p, C.c_int, C.c_char_p, _f64p],
+    "b200sv_sharded_sample_measure": [_vp, _f64p, C.c_int64, _f64p, _u64p],
 }
 
 _lib = None

@@ -112,6 +112,43 @@ template <typename F> static int guard(F f) {
   }
 }
 
+// Peer access for pointers that live on another GPU of this process (chunk_manager.hpp:129-135,
+// device_chunk_container.hpp:336-351: cudaDeviceEnablePeerAccess between the devices that hold chunks), enabled
+// lazily the first time a handle is handed such a pointer.  IPC-mapped pointers were opened with
+// cudaIpcMemLazyEnablePeerAccess and need nothing.
+void ensure_peer(const State &s, const void *ptr) {
+  if (!ptr) return;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) { cudaGetLastError(); return; }
+  if (attr.type != cudaMemoryTypeDevice || attr.device == s.device) return;
+  static bool enabled[64][64] = {};
+  if (attr.device < 0 || attr.device >= 64 || s.device >= 64 || enabled[s.device][attr.device]) return;
+  int can = 0;
+  B200_CUDA(cudaDeviceCanAccessPeer(&can, s.device, attr.device));
+  if (!can) throw Error("GPU " + std::to_string(s.device) + " cannot access GPU " + std::to_string(attr.device) + " (no peer path)");
+  cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);  // current device = s.device (select() ran)
+  if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) B200_CUDA(e);
+  cudaGetLastError();
+  enabled[s.device][attr.device] = true;
+}
+
+// Per-state kernels index the state with blockIdx.y (<= 65535): containers with more states run them slab by slab on
+// views of <= 65535 states (the reference sizes shot groups by memory only, chunk_manager.hpp:223-264).
+template <typename F> static void for_state_slabs(State *s, F f) {
+  constexpr int64_t kMaxY = 65535;
+  if (s->nstates <= kMaxY) { f(*s, (int64_t)0); return; }
+  for (int64_t s0 = 0; s0 < s->nstates; s0 += kMaxY) {
+    State v = *s;
+    v.nstates = std::min<int64_t>(kMaxY, s->nstates - s0);
+    v.data = (char *)s->data + ((uint64_t)s0 << s->nq) * s->amp_bytes();
+    v.owns_data = false;
+    if (v.checkpoint) v.checkpoint = (char *)s->checkpoint + ((uint64_t)s0 << s->nq) * s->amp_bytes();
+    f(v, s0);
+    s->scratch = v.scratch; s->scratch_bytes = v.scratch_bytes;  // the view may have grown the shared buffers
+    s->pinned = v.pinned; s->pinned_bytes = v.pinned_bytes;
+  }
+}
+
 static State *make_state(int nq, int64_t nstates, int precision, int device) {
   if (nq < 0 || nq > 40) throw Error("num_qubits out of range");
   if (nstates < 1) throw Error("num_states must be >= 1");
@@ -152,6 +189,18 @@ int b200sv_device_count(int *count) {
   });
 }
 
+int b200sv_mem_info(int device, uint64_t *free_bytes, uint64_t *total_bytes) {
+  return guard([&] {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) throw Error("mem_info: device index out of range");
+    size_t f = 0, t = 0;
+    B200_CUDA(cudaSetDevice(device));
+    B200_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+  });
+}
+
 int b200sv_create(b200sv_handle *out, int num_qubits, int64_t num_states, int precision, int device) {
   return guard([&] {
     State *s = make_state(num_qubits, num_states, precision, device);
@@ -174,6 +223,7 @@ int b200sv_create_external(b200sv_handle *out, int num_qubits, int64_t num_state
                            void *dev_ptr, void *cuda_stream) {
   return guard([&] {
     if (!dev_ptr || ((uintptr_t)dev_ptr & 15)) throw Error("external device pointer must be non-null and 16-byte aligned");
+    // (kernels with 256-bit accesses check for 32-byte alignment themselves and take their 128-bit variants otherwise)
     State *s = make_state(num_qubits, num_states, precision, device);
     s->data = dev_ptr;
     s->stream = (cudaStream_t)cuda_stream;
@@ -278,7 +328,7 @@ int b200sv_inner_product(b200sv_handle h, double *re, double *im) {
   return guard([&] {
     select(H);
     if (!H->checkpoint) throw Error("inner_product: no checkpoint");
-    reduce_inner_product(*H, H->checkpoint, re, im);
+    for_state_slabs(H, [&](State &v, int64_t s0) { reduce_inner_product(v, v.checkpoint, re + s0, im + s0); });
   });
 }
 
@@ -542,7 +592,10 @@ int b200sv_fuse_block_matrix(int k, const int *block_qubits, int ngates, const i
 }
 
 int b200sv_apply_batched_pauli(b200sv_handle h, const uint64_t *masks4) {
-  return guard([&] { select(H); launch_batched_pauli(*H, masks4); });
+  return guard([&] {
+    select(H);
+    for_state_slabs(H, [&](State &v, int64_t s0) { launch_batched_pauli(v, masks4 + 4 * s0); });
+  });
 }
 
 int b200sv_collapse(b200sv_handle h, const uint64_t *qubits, int k, const uint64_t *outcomes, const double *scales,
@@ -551,7 +604,7 @@ int b200sv_collapse(b200sv_handle h, const uint64_t *qubits, int k, const uint64
     select(H);
     auto q = checked_qubits(*H, qubits, k);
     if (!outcomes || !scales || !active) throw Error("collapse: null argument");
-    launch_collapse(*H, q.data(), k, outcomes, scales, active);
+    for_state_slabs(H, [&](State &v, int64_t s0) { launch_collapse(v, q.data(), k, outcomes + s0, scales + s0, active + s0); });
   });
 }
 
@@ -570,14 +623,16 @@ int b200sv_create_view(b200sv_handle *out, b200sv_handle parent, int64_t first_s
 }
 
 // ------------------------------------------------------------------ reductions
-int b200sv_norm(b200sv_handle h, double *out) { return guard([&] { select(H); reduce_norm(*H, out); }); }
+int b200sv_norm(b200sv_handle h, double *out) {
+  return guard([&] { select(H); for_state_slabs(H, [&](State &v, int64_t s0) { reduce_norm(v, out + s0); }); });
+}
 
 int b200sv_norm_matrix(b200sv_handle h, const uint64_t *qubits, int k, const double *mat, double *out) {
   return guard([&] {
     select(H);
     if (k < 1) throw Error("norm(qubits, mat): empty qubit list");
     auto q = checked_qubits(*H, qubits, k);
-    reduce_norm_matrix(*H, q.data(), k, mat, out);
+    for_state_slabs(H, [&](State &v, int64_t s0) { reduce_norm_matrix(v, q.data(), k, mat, out + s0); });
   });
 }
 
@@ -585,13 +640,18 @@ int b200sv_probabilities(b200sv_handle h, const uint64_t *qubits, int k, double 
   return guard([&] {
     select(H);
     auto q = checked_qubits(*H, qubits, k);
-    if (k == 0) { reduce_norm(*H, out); return; }
-    reduce_probabilities(*H, q.data(), k, out);
+    for_state_slabs(H, [&](State &v, int64_t s0) {
+      if (k == 0) reduce_norm(v, out + s0);
+      else reduce_probabilities(v, q.data(), k, out + ((uint64_t)s0 << k));
+    });
   });
 }
 
 int b200sv_sample_measure(b200sv_handle h, const double *rnds, int64_t shots, uint64_t *out) {
-  return guard([&] { select(H); sample_measure(*H, rnds, shots, out); });
+  return guard([&] {
+    select(H);
+    for_state_slabs(H, [&](State &v, int64_t s0) { sample_measure(v, rnds + s0 * shots, shots, out + s0 * shots); });
+  });
 }
 
 int b200sv_expval_pauli(b200sv_handle h, const uint64_t *qubits, int k, const char *pauli, double pre, double pim,
@@ -600,9 +660,12 @@ int b200sv_expval_pauli(b200sv_handle h, const uint64_t *qubits, int k, const ch
     select(H);
     auto q = checked_qubits(*H, qubits, k);
     PauliMasks m = pauli_masks(q, pauli);
-    if (m.x + m.z == 0) { reduce_norm(*H, out); return; }  // qubitvector.hpp:2309-2311
+    if (m.x + m.z == 0) {  // qubitvector.hpp:2309-2311
+      for_state_slabs(H, [&](State &v, int64_t s0) { reduce_norm(v, out + s0); });
+      return;
+    }
     add_y_phase(m.num_y, pre, pim);
-    reduce_expval_pauli(*H, m.x, m.z, m.x_max, pre, pim, nullptr, 0, 0, out);
+    for_state_slabs(H, [&](State &v, int64_t s0) { reduce_expval_pauli(v, m.x, m.z, m.x_max, pre, pim, nullptr, 0, 0, out + s0); });
   });
 }
 
@@ -614,6 +677,7 @@ int b200sv_expval_pauli_pair(b200sv_handle h, const uint64_t *qubits, int k, con
     auto q = checked_qubits(*H, qubits, k);
     PauliMasks m = pauli_masks(q, pauli);
     add_y_phase(m.num_y, pre, pim);
+    ensure_peer(*H, pair_dev_ptr);
     reduce_expval_pauli(*H, m.x, m.z, m.x_max, pre, pim, pair_dev_ptr ? pair_dev_ptr : H->data, z_count, z_count_pair,
                         out);
   });
@@ -626,6 +690,7 @@ int b200sv_chunk_swap_peer(b200sv_handle h, int local_q, void *peer, int upper, 
     if (local_q < 0 || local_q >= H->nq) throw Error("chunk swap: local qubit out of range");
     if (H->nstates != 1) throw Error("chunk swap: not available on batched containers");
     if (H->nq < 2) throw Error("chunk swap: chunk too small");
+    ensure_peer(*H, peer);
     launch_chunk_swap_peer(*H, local_q, peer, upper, half);
   });
 }
@@ -640,7 +705,28 @@ int b200sv_multi_swap_peer(b200sv_handle h, int k, const int *local_q, uint32_t 
         if (local_q[c] == local_q[b]) throw Error("multi swap: duplicate local qubit");
     }
     if (my_g >> k) throw Error("multi swap: my_g out of range");
+    for (uint32_t v = 0; v < (1u << k); v++)
+      if (v != my_g) ensure_peer(*H, peers[v]);
     launch_multi_swap_peer(*H, k, local_q, my_g, peers);
+  });
+}
+int b200sv_swap_range_peer(b200sv_handle h, uint64_t dest_offset, void *peer, uint64_t src_offset, uint64_t count) {
+  return guard([&] {
+    select(H);
+    if (!peer) throw Error("swap range: null peer pointer");
+    if (dest_offset + count > H->total_amps()) throw Error("swap range: range exceeds the chunk");
+    ensure_peer(*H, peer);
+    launch_swap_range_peer(*H, dest_offset, peer, src_offset, count);
+  });
+}
+int b200sv_copy_range_peer(b200sv_handle h, uint64_t dest_offset, const void *peer, uint64_t src_offset, uint64_t count) {
+  return guard([&] {
+    select(H);
+    if (!peer) throw Error("copy range: null peer pointer");
+    if (dest_offset + count > H->total_amps()) throw Error("copy range: range exceeds the chunk");
+    ensure_peer(*H, peer);
+    B200_CUDA(cudaMemcpyAsync((char *)H->data + dest_offset * H->amp_bytes(), (const char *)peer + src_offset * H->amp_bytes(),
+                              count * H->amp_bytes(), cudaMemcpyDeviceToDevice, H->stream));
   });
 }
 int b200sv_pack_half(b200sv_handle h, int local_q, int bit, uint64_t begin, uint64_t count, void *buf) {

@@ -64,6 +64,15 @@ __host__ __device__ __forceinline__ uint64_t insert_zeros(uint64_t v, const Inse
   return v;
 }
 
+struct TilePlan;  // tile.cu: captured tile passes (parameter blocks + kernel variants)
+// a sub-cube of the state: `nbits` global index positions held at the bits of `value`
+struct SlabSpec {
+  int nbits = 0;
+  int pos[4] = {0, 0, 0, 0};
+  uint32_t value = 0;
+  int sm_limit = 0;   // > 0: use at most this many SMs (leave the rest to a concurrent kernel)
+};
+
 // ---------------------------------------------------------------------------
 struct State {
   int device = 0;
@@ -89,6 +98,7 @@ struct State {
   void *selftest_host = nullptr;
   bool plan_only = false;  // selftest without a host array: count the passes only
   const uint8_t *selftest_codes = nullptr;
+  TilePlan *capture = nullptr;  // set while tile_plan_build runs: passes are recorded instead of launched
 
   uint64_t amps_per_state() const { return 1ull << nq; }
   uint64_t total_amps() const { return (uint64_t)nstates << nq; }
@@ -119,10 +129,18 @@ void launch_init_component(State &s, const int *qubits, int k, const double *sta
 void launch_pack_half(State &s, int q, int bit, uint64_t begin, uint64_t count, void *buf, bool unpack);
 void launch_chunk_swap_peer(State &s, int q, void *peer, int upper, int half);
 void launch_multi_swap_peer(State &s, int k, const int *local_q, uint32_t my_g, void *const *peers);
+void launch_swap_range_peer(State &s, uint64_t dest_offset, void *peer, uint64_t src_offset, uint64_t count);
 
 // ---- tile-blocked multi-gate passes (tile.cu)
 int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats, int low_bits,
                         const int *slot = nullptr, const uint8_t *codes_host = nullptr, int nslots = 0);
+
+// plan once, launch later (whole state or slab by slab): the sharded executor's view of the tile engine
+TilePlan *tile_plan_build(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats);
+void tile_plan_free(TilePlan *plan);
+int tile_plan_passes(const TilePlan *plan);
+uint64_t tile_plan_pass_mask(const TilePlan *plan, int pass);
+void tile_plan_launch(State &s, const TilePlan *plan, int pass, const SlabSpec *slab);
 
 // ---- epoch planner for sharded registers (planner.cu, host only)
 void plan_epochs(int n, int nl, int gbits, int nops, const int *op_off, const int *op_qubits, const uint8_t *need_local,

@@ -151,9 +151,11 @@ static void launch_dense_t(State &s, const int *targets, const int *controls, in
   p.ngroups = s.total_amps() >> (K + nc);
   if constexpr (K == 5 && std::is_same<T, double>::value) {
     static const int env_dmma = [] { const char *e = getenv("B200SV_DENSE5_DMMA"); return e ? atoi(e) : 1; }();
-    if (env_dmma && nc == 0 && p.ngroups >= 8) {
+    // the kernel walks batches of 8 groups: batched containers whose group count is not a multiple of 8 (e.g. 10 states
+    // of 5 qubits) take the register kernel; the 256-bit stores of the PAIR variant need a 32-byte aligned state
+    if (env_dmma && nc == 0 && p.ngroups >= 8 && (p.ngroups & 7) == 0) {
       const int grid5 = (int)std::min<uint64_t>((p.ngroups / 8 + 7) / 8, (uint64_t)s.num_sms * 3);
-      if (p.ins.pos[0] > 0) dense5_dmma_kernel<true><<<grid5, 256, 0, s.stream>>>((double2 *)s.data, p);
+      if (p.ins.pos[0] > 0 && ((uintptr_t)s.data & 31) == 0) dense5_dmma_kernel<true><<<grid5, 256, 0, s.stream>>>((double2 *)s.data, p);
       else dense5_dmma_kernel<false><<<grid5, 256, 0, s.stream>>>((double2 *)s.data, p);
       B200_CUDA(cudaGetLastError());
       return;
@@ -757,6 +759,53 @@ void launch_chunk_swap_peer(State &s, int q, void *peer, int upper, int half) {
     chunk_swap_peer_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, (double2 *)peer, q, mine_mask, peer_mask, begin, count);
   else
     chunk_swap_peer_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, (float2 *)peer, q, mine_mask, peer_mask, begin, count);
+  B200_CUDA(cudaGetLastError());
+}
+
+// Contiguous range swap between two chunks (apply_chunk_swap(chunk, dest_offset, src_offset, size),
+// qubitvector.hpp:1824-1840: the sub-block shuffle of apply_multi_chunk_swap; also the whole-chunk exchange of a swap
+// between two global qubits).  `peer` may live on another GPU (peer access over NVLink) or alias this chunk's device.
+// 32-byte accesses, 4 in flight per thread in each direction.
+__global__ void __launch_bounds__(256) swap_range_kernel(ulonglong4 *__restrict__ a, ulonglong4 *__restrict__ b,
+                                                         uint64_t count32) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  for (uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < count32; j0 += stride * U) {
+    ulonglong4 x[U], y[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t j = j0 + u * stride;
+      if (j < count32) { y[u] = b[j]; x[u] = a[j]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t j = j0 + u * stride;
+      if (j < count32) { a[j] = y[u]; b[j] = x[u]; }
+    }
+  }
+}
+__global__ void __launch_bounds__(256) swap_range16_kernel(uint4 *__restrict__ a, uint4 *__restrict__ b, uint64_t count16) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < count16; j += stride) {
+    const uint4 x = a[j], y = b[j];
+    a[j] = y;
+    b[j] = x;
+  }
+}
+void launch_swap_range_peer(State &s, uint64_t dest_offset, void *peer, uint64_t src_offset, uint64_t count) {
+  char *a = (char *)s.data + dest_offset * s.amp_bytes();
+  char *b = (char *)peer + src_offset * s.amp_bytes();
+  const uint64_t bytes = count * s.amp_bytes();
+  if (bytes == 0) return;
+  if ((((uintptr_t)a | (uintptr_t)b | bytes) & 31) == 0) {
+    const uint64_t n32 = bytes >> 5;
+    swap_range_kernel<<<grid_for(s, (n32 + 3) / 4, 256, 8), 256, 0, s.stream>>>((ulonglong4 *)a, (ulonglong4 *)b, n32);
+  } else if ((((uintptr_t)a | (uintptr_t)b | bytes) & 15) == 0) {
+    const uint64_t n16 = bytes >> 4;
+    swap_range16_kernel<<<grid_for(s, n16, 256, 8), 256, 0, s.stream>>>((uint4 *)a, (uint4 *)b, n16);
+  } else {
+    throw Error("swap range: ranges must be 16-byte aligned");
+  }
   B200_CUDA(cudaGetLastError());
 }
 

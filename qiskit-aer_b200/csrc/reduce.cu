@@ -389,6 +389,9 @@ constexpr int kSampleB = 12;
 template <typename T>
 __global__ void __launch_bounds__(256)
 block_sums_kernel(const cx<T> *__restrict__ psi, int B, uint64_t nblocks, double *__restrict__ bsum) {
+  // blockIdx.y = state of a batched container (its amplitudes and its nblocks + 1 sums are contiguous)
+  psi += ((uint64_t)blockIdx.y * nblocks) << B;
+  bsum += (uint64_t)blockIdx.y * (nblocks + 1);
   for (uint64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
     const cx<T> *blk = psi + (b << B);
     double a = 0;
@@ -404,6 +407,7 @@ block_sums_kernel(const cx<T> *__restrict__ psi, int B, uint64_t nblocks, double
 // in-place exclusive scan by one CTA of 1024 threads; writes total to bsum[n]
 __global__ void __launch_bounds__(1024) scan_kernel(double *__restrict__ bsum, uint64_t n) {
   __shared__ double tsum[1024];
+  bsum += (uint64_t)blockIdx.x * (n + 1);  // one CTA per state
   const uint64_t per = (n + 1023) / 1024;
   const uint64_t b0 = per * threadIdx.x, b1 = b0 + per < n ? b0 + per : n;
   double a = 0;
@@ -426,6 +430,10 @@ sample_kernel(const cx<T> *__restrict__ psi, int B, uint64_t nblocks, const doub
   const int lane = threadIdx.x & 31;
   const int64_t shot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (shot >= shots) return;
+  psi += ((uint64_t)blockIdx.y * nblocks) << B;  // blockIdx.y = state; rnds / out are [state][shot]
+  excl += (uint64_t)blockIdx.y * (nblocks + 1);
+  rnds += (int64_t)blockIdx.y * shots;
+  out += (int64_t)blockIdx.y * shots;
   const double rnd = rnds[shot];
   // last block whose exclusive prefix is <= rnd  (== first block with rnd < inclusive prefix)
   uint64_t lo = 0, hi = nblocks;  // invariant: excl[lo] <= rnd (excl[0] = 0), answer in [lo, hi)
@@ -465,37 +473,38 @@ void sample_measure(State &s, const double *rnds, int64_t shots, uint64_t *out) 
   if (shots <= 0) return;
   const int B = std::min(kSampleB, s.nq);
   const uint64_t nblocks = s.amps_per_state() >> B;
-  // scratch layout: [bsum (nblocks+1)] [rnds] [out]
-  const size_t off_r = ((nblocks + 1) * sizeof(double) + 255) & ~(size_t)255;
-  const size_t off_o = off_r + (((size_t)shots * sizeof(double) + 255) & ~(size_t)255);
-  const size_t total = off_o + (size_t)shots * sizeof(uint64_t);
+  const size_t S = (size_t)s.nstates, tot = S * (size_t)shots;
+  // scratch layout: [bsum (nblocks+1) per state] [rnds] [out]; all states ride on one launch of each kernel and the
+  // draws / samples cross PCIe in one transfer each (batched measure of 10k shots: 3 launches, not 30k)
+  const size_t off_r = (S * (nblocks + 1) * sizeof(double) + 255) & ~(size_t)255;
+  const size_t off_o = off_r + ((tot * sizeof(double) + 255) & ~(size_t)255);
+  const size_t total = off_o + tot * sizeof(uint64_t);
   char *scr = (char *)s.ensure_scratch(total);
-  char *pin = (char *)s.ensure_pinned((size_t)shots * 8);
-  for (int64_t st = 0; st < s.nstates; st++) {
-    double *bsum = (double *)scr;
-    double *d_r = (double *)(scr + off_r);
-    uint64_t *d_o = (uint64_t *)(scr + off_o);
-    B200_CUDA(cudaStreamSynchronize(s.stream));
-    memcpy(pin, rnds + st * shots, (size_t)shots * 8);
-    B200_CUDA(cudaMemcpyAsync(d_r, pin, (size_t)shots * 8, cudaMemcpyHostToDevice, s.stream));
-    const int g1 = (int)std::min<uint64_t>(nblocks, (uint64_t)s.num_sms * 8);
-    const int g3 = (int)((shots * 32 + 255) / 256);
-    if (s.precision == B200SV_F64) {
-      const double2 *psi = (const double2 *)s.data + ((uint64_t)st << s.nq);
-      block_sums_kernel<double><<<g1, 256, 0, s.stream>>>(psi, B, nblocks, bsum);
-      scan_kernel<<<1, 1024, 0, s.stream>>>(bsum, nblocks);
-      sample_kernel<double><<<g3, 256, 0, s.stream>>>(psi, B, nblocks, bsum, d_r, shots, d_o);
-    } else {
-      const float2 *psi = (const float2 *)s.data + ((uint64_t)st << s.nq);
-      block_sums_kernel<float><<<g1, 256, 0, s.stream>>>(psi, B, nblocks, bsum);
-      scan_kernel<<<1, 1024, 0, s.stream>>>(bsum, nblocks);
-      sample_kernel<float><<<g3, 256, 0, s.stream>>>(psi, B, nblocks, bsum, d_r, shots, d_o);
-    }
-    B200_CUDA(cudaGetLastError());
-    B200_CUDA(cudaMemcpyAsync(pin, d_o, (size_t)shots * 8, cudaMemcpyDeviceToHost, s.stream));
-    B200_CUDA(cudaStreamSynchronize(s.stream));
-    memcpy(out + st * shots, pin, (size_t)shots * 8);
+  char *pin = (char *)s.ensure_pinned(tot * 8);
+  double *bsum = (double *)scr;
+  double *d_r = (double *)(scr + off_r);
+  uint64_t *d_o = (uint64_t *)(scr + off_o);
+  B200_CUDA(cudaStreamSynchronize(s.stream));
+  memcpy(pin, rnds, tot * 8);
+  B200_CUDA(cudaMemcpyAsync(d_r, pin, tot * 8, cudaMemcpyHostToDevice, s.stream));
+  const int per_state = (int)std::max<uint64_t>(1, (uint64_t)s.num_sms * 8 / S);
+  dim3 g1((unsigned)std::min<uint64_t>(nblocks, (uint64_t)per_state), (unsigned)S);
+  dim3 g3((unsigned)((shots * 32 + 255) / 256), (unsigned)S);
+  if (s.precision == B200SV_F64) {
+    const double2 *psi = (const double2 *)s.data;
+    block_sums_kernel<double><<<g1, 256, 0, s.stream>>>(psi, B, nblocks, bsum);
+    scan_kernel<<<(unsigned)S, 1024, 0, s.stream>>>(bsum, nblocks);
+    sample_kernel<double><<<g3, 256, 0, s.stream>>>(psi, B, nblocks, bsum, d_r, shots, d_o);
+  } else {
+    const float2 *psi = (const float2 *)s.data;
+    block_sums_kernel<float><<<g1, 256, 0, s.stream>>>(psi, B, nblocks, bsum);
+    scan_kernel<<<(unsigned)S, 1024, 0, s.stream>>>(bsum, nblocks);
+    sample_kernel<float><<<g3, 256, 0, s.stream>>>(psi, B, nblocks, bsum, d_r, shots, d_o);
   }
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(pin, d_o, tot * 8, cudaMemcpyDeviceToHost, s.stream));
+  B200_CUDA(cudaStreamSynchronize(s.stream));
+  memcpy(out, pin, tot * 8);
 }
 
 }  // namespace b200sv

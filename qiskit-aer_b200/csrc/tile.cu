@@ -1077,6 +1077,73 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
   return any_pauli;
 }
 
+// ------------------------------------------------------------------------------------------ planned passes
+// A pass is fully described by its parameter block and the kernel variant that consumes it.  Passes are launched at
+// once (the C ABI's immediate path) or captured into a TilePlan (State::capture) and launched later, possibly several
+// times and possibly restricted to a SLAB of the state: a sub-cube in which some global index bits outside the tile are
+// held fixed.  A slab launch only changes how tile indices map to addresses -- the fixed positions join the tile's
+// zero-insertion list, the fixed bit values become a pointer offset, the tile count shrinks -- so the kernels are
+// unchanged.  Slabs are what lets the sharded executor overlap a global-qubit exchange with the passes next to it.
+enum TileVariant { TV_PIPE2_PAULI, TV_PIPE_PAULI, TV_PIPE2_FAST, TV_PIPE_FAST, TV_PIPE_GENERIC, TV_PASS12, TV_PASS11,
+                   TV_PIPE2_F32, TV_DENSE };
+struct TilePlannedPass {
+  TileVariant variant;
+  TilePassParams p;        // unused for TV_DENSE
+  int dq[2] = {0, 0}, dnq = 0;
+  double dmat[32];         // TV_DENSE: one streaming pass for one gate (states too small for tiles)
+};
+struct TilePlan {
+  std::vector<TilePlannedPass> passes;
+};
+
+static void launch_tile_variant(State &s, const TilePassParams &p, TileVariant v, double2 *psi, int grid_cap) {
+  // function attributes are per device: one flag per device ordinal (a process may drive several GPUs)
+  static bool attr_set_dev[64] = {};
+  bool &attr_set = attr_set_dev[s.device & 63];
+  const int smem_pipe = kPipeBufs * (16 << 12) + 64;
+  const int smem_pauli = smem_pipe + 4 * (kMaxRounds + 16);
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 12)));
+    B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 11)));
+    B200_CUDA(cudaFuncSetAttribute(tile_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pipe));
+    B200_CUDA(cudaFuncSetAttribute(tile_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pipe));
+    B200_CUDA(cudaFuncSetAttribute(tile_pipe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pauli));
+    B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pauli));
+    B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pipe));
+    B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pipe));
+    attr_set = true;
+  }
+  const uint64_t sms = (uint64_t)std::max(1, grid_cap > 0 ? std::min(grid_cap, s.num_sms) : s.num_sms);
+  const int grid = (int)std::min<uint64_t>(p.ntiles, sms);
+  switch (v) {
+  case TV_PIPE2_PAULI: tile_pipe2_kernel<4><<<grid, 640, smem_pauli, s.stream>>>(psi, p); break;
+  case TV_PIPE_PAULI: tile_pipe_kernel<4><<<grid, 512, smem_pauli, s.stream>>>(psi, p); break;
+  case TV_PIPE2_FAST: tile_pipe2_kernel<1><<<grid, 640, smem_pipe, s.stream>>>(psi, p); break;
+  case TV_PIPE_FAST: tile_pipe_kernel<1><<<grid, 512, smem_pipe, s.stream>>>(psi, p); break;
+  case TV_PIPE_GENERIC: tile_pipe_kernel<2><<<grid, 512, smem_pipe, s.stream>>>(psi, p); break;
+  case TV_PIPE2_F32: tile_pipe2_kernel<3><<<grid, 640, smem_pipe, s.stream>>>(psi, p); break;
+  case TV_PASS12:
+    tile_pass_kernel<12><<<(int)std::min<uint64_t>(p.ntiles, sms * 2), 256, 16 << 12, s.stream>>>(psi, p);
+    break;
+  case TV_PASS11:
+    tile_pass_kernel<11><<<(int)std::min<uint64_t>(p.ntiles, sms * 4), 128, 16 << 11, s.stream>>>(psi, p);
+    break;
+  default: throw Error("tile pass: bad kernel variant");
+  }
+  B200_CUDA(cudaGetLastError());
+}
+
+// launch now, or record into the plan being captured
+static void emit_tile_pass(State &s, const TilePassParams &p, TileVariant v) {
+  if (s.capture) {
+    s.capture->passes.emplace_back();
+    s.capture->passes.back().variant = v;
+    s.capture->passes.back().p = p;
+    return;
+  }
+  launch_tile_variant(s, p, v, (double2 *)s.data, 0);
+}
+
 // One pass: gates[sel] all fit the tile; tile_bits sorted global positions (kTB of them).
 // Returns the entries of `sel` that did not fit (round or matrix-slot budget): the caller re-queues them.
 static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates, const std::vector<int> &sel,
@@ -1226,60 +1293,14 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
     if (!s.plan_only) emulate_tile_pass<double>(p, s.selftest_host, s.selftest_codes, false);
     return leftover;
   }
-  // function attributes are per device: one flag per device ordinal (a process may drive several GPUs)
-  static bool attr_set_dev[64] = {};
-  bool &attr_set = attr_set_dev[s.device & 63];
-  if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 12)));
-    B200_CUDA(cudaFuncSetAttribute(tile_pass_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16 << 11)));
-    B200_CUDA(cudaFuncSetAttribute(tile_pipe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kPipeBufs * (16 << 12) + 64));
-    B200_CUDA(cudaFuncSetAttribute(tile_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kPipeBufs * (16 << 12) + 64));
-    attr_set = true;
-  }
   bool all_fast = true;
   for (int r = 0; r < p.nrounds; r++) all_fast = all_fast && p.rounds[r].fast;
-  if (slot_pauli) {  // fast rounds + sampled-noise Paulis
-    static bool attr4_dev[64] = {};
-    bool &attr4 = attr4_dev[s.device & 63];
-    const int smem4 = kPipeBufs * (16 << 12) + 64 + 4 * (kMaxRounds + 16);
-    if (!attr4) {
-      B200_CUDA(cudaFuncSetAttribute(tile_pipe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-      B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-      attr4 = true;
-    }
-    const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms);
-    if (env_pipe == 2) tile_pipe2_kernel<4><<<grid, 640, smem4, s.stream>>>((double2 *)s.data, p);
-    else tile_pipe_kernel<4><<<grid, 512, smem4, s.stream>>>((double2 *)s.data, p);
-    B200_CUDA(cudaGetLastError());
-    return leftover;
-  }
-  if (kTB == 12 && env_pipe == 2 && all_fast) {  // memory-warp variant: fast-only code fits its 112-register budget
-    static bool attr2_dev[64] = {};
-    bool &attr2 = attr2_dev[s.device & 63];
-    const int smem2 = kPipeBufs * (16 << 12) + 64;
-    if (!attr2) {
-      B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
-      attr2 = true;
-    }
-    const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms);
-    tile_pipe2_kernel<1><<<grid, 640, smem2, s.stream>>>((double2 *)s.data, p);
-    B200_CUDA(cudaGetLastError());
-    return leftover;
-  }
-  if (kTB == 12 && env_pipe) {
-    const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms);
-    if (all_fast) tile_pipe_kernel<1><<<grid, 512, kPipeBufs * (16 << 12) + 64, s.stream>>>((double2 *)s.data, p);
-    else tile_pipe_kernel<2><<<grid, 512, kPipeBufs * (16 << 12) + 64, s.stream>>>((double2 *)s.data, p);
-    B200_CUDA(cudaGetLastError());
-    return leftover;
-  }
-  const int per_sm = kTB == 12 ? 2 : 4;
-  const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms * per_sm);
-  if (kTB == 12) tile_pass_kernel<12><<<grid, 256, 16 << 12, s.stream>>>((double2 *)s.data, p);
-  else tile_pass_kernel<11><<<grid, 128, 16 << 11, s.stream>>>((double2 *)s.data, p);
-  B200_CUDA(cudaGetLastError());
+  TileVariant v;
+  if (slot_pauli) v = env_pipe == 2 ? TV_PIPE2_PAULI : TV_PIPE_PAULI;   // fast rounds + sampled-noise Paulis
+  else if (kTB == 12 && env_pipe == 2 && all_fast) v = TV_PIPE2_FAST;   // memory-warp variant: fast-only code fits its register budget
+  else if (kTB == 12 && env_pipe) v = all_fast ? TV_PIPE_FAST : TV_PIPE_GENERIC;
+  else v = kTB == 12 ? TV_PASS12 : TV_PASS11;
+  emit_tile_pass(s, p, v);
   return leftover;
 }
 
@@ -1469,16 +1490,7 @@ static std::vector<int> run_tile_pass_f32(State &s, const std::vector<QGate> &ga
     if (!s.plan_only) emulate_tile_pass<float>(p, s.selftest_host, nullptr, true);
     return leftover;
   }
-  static bool attr_dev[64] = {};
-  bool &attr = attr_dev[s.device & 63];
-  const int smem = kPipeBufs * (16 << 12) + 64;
-  if (!attr) {
-    B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
-  const int grid = (int)std::min<uint64_t>(p.ntiles, (uint64_t)s.num_sms);
-  tile_pipe2_kernel<3><<<grid, 640, smem, s.stream>>>((double2 *)s.data, p);
-  B200_CUDA(cudaGetLastError());
+  emit_tile_pass(s, p, TV_PIPE2_F32);
   return leftover;
 }
 
@@ -1645,7 +1657,17 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
   if (!tiled && s.selftest_host) throw Error("selftest: this state size / precision / op mix does not take the tile passes");
   if (!tiled) {  // small or single-precision states: one streaming pass per op
     for (auto &g : gates) {
+      if (g.mat && s.capture) {
+        s.capture->passes.emplace_back();
+        TilePlannedPass &pp = s.capture->passes.back();
+        pp.variant = TV_DENSE;
+        pp.dnq = g.nq;
+        pp.dq[0] = g.q[0]; pp.dq[1] = g.nq == 2 ? g.q[1] : 0;
+        std::copy(g.mat, g.mat + 32, pp.dmat);
+        continue;
+      }
       if (g.mat) { launch_dense(s, g.q, g.nq, nullptr, 0, g.mat); continue; }
+      if (s.capture) throw Error("tile plan: per-state Pauli ops cannot be captured");
       std::vector<uint64_t> m4(4 * (size_t)s.nstates, 0);  // batched_pauli_func masks (qubitvector_thrust.hpp:2819)
       for (int64_t st = 0; st < s.nstates; st++) {
         const int code = codes_host[(size_t)g.slot * s.nstates + st];
@@ -1720,6 +1742,66 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
     rem.swap(rest);
   }
   return passes;
+}
+
+// ------------------------------------------------------------------------------------------ plan API (sharded executor)
+TilePlan *tile_plan_build(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats) {
+  TilePlan *plan = new TilePlan();
+  s.capture = plan;
+  try {
+    if (ngates > 0) apply_gate_sequence(s, ngates, nq, qubits, mats, 3);
+  } catch (...) {
+    s.capture = nullptr;
+    delete plan;
+    throw;
+  }
+  s.capture = nullptr;
+  return plan;
+}
+void tile_plan_free(TilePlan *plan) { delete plan; }
+int tile_plan_passes(const TilePlan *plan) { return (int)plan->passes.size(); }
+// global index bits a pass addresses inside its tiles (a slab may only fix bits outside this mask); ~0 for passes
+// that cannot be restricted to a slab
+uint64_t tile_plan_pass_mask(const TilePlan *plan, int i) {
+  const TilePlannedPass &pp = plan->passes.at(i);
+  if (pp.variant == TV_DENSE) return ~0ull;
+  uint64_t m = 0;
+  const int shift = pp.variant == TV_PIPE2_F32 ? 1 : 0;  // float passes address 16-byte slots: position - 1, qubit 0 inside
+  for (int u = 0; u < pp.p.ins.n; u++) m |= 1ull << (pp.p.ins.pos[u] + shift);
+  if (shift) m |= 1ull;
+  return m;
+}
+void tile_plan_launch(State &s, const TilePlan *plan, int i, const SlabSpec *slab) {
+  const TilePlannedPass &pp = plan->passes.at(i);
+  const bool has_slab = slab && slab->nbits > 0;
+  if (pp.variant == TV_DENSE) {
+    if (has_slab) throw Error("tile plan: this pass cannot be restricted to a slab");
+    launch_dense(s, pp.dq, pp.dnq, nullptr, 0, pp.dmat);
+    return;
+  }
+  if (!has_slab) {
+    launch_tile_variant(s, pp.p, pp.variant, (double2 *)s.data, slab ? slab->sm_limit : 0);
+    return;
+  }
+  static thread_local TilePassParams q;
+  q = pp.p;
+  const int shift = pp.variant == TV_PIPE2_F32 ? 1 : 0;
+  uint64_t offset = 0;  // in amplitudes
+  std::vector<int> pos(q.ins.pos, q.ins.pos + q.ins.n);
+  for (int b = 0; b < slab->nbits; b++) {
+    const int sp = slab->pos[b];
+    if (sp < shift || sp >= s.nq) throw Error("tile plan: slab bit out of range");
+    if (std::find(pos.begin(), pos.end(), sp - shift) != pos.end()) throw Error("tile plan: slab bit lies inside the pass's tile");
+    pos.push_back(sp - shift);
+    if ((slab->value >> b) & 1u) offset |= 1ull << sp;
+  }
+  std::sort(pos.begin(), pos.end());
+  if ((int)pos.size() > kMaxInsert) throw Error("tile plan: too many fixed bits");
+  q.ins.n = (int)pos.size();
+  for (size_t u = 0; u < pos.size(); u++) q.ins.pos[u] = (uint8_t)pos[u];
+  q.ntiles = pp.p.ntiles >> slab->nbits;
+  char *base = (char *)s.data + offset * s.amp_bytes();
+  launch_tile_variant(s, q, pp.variant, (double2 *)base, slab->sm_limit);
 }
 
 #ifdef B200SV_TILE_PROFILE

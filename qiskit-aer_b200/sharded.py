@@ -446,3 +446,225 @@ class ShardedRunner:
             out[mine] = (local + np.uint64(self.rank << self.nl)).astype(np.float64)
         out = self._allreduce(out)
         return self.physical_to_logical(out.astype(np.uint64))
+
+
+# ======================================================================================================================
+class ShardedState:
+    """The C++ sharded executor (csrc/sharded.cu, b200sv_sharded_*): epoch planning, gate queues, tile passes, the
+    staged / pipelined global-qubit exchange and the cross-shard reductions all run inside libb200sv.  This class only
+    encodes op tuples and -- in the one-process-per-GPU layout -- moves 128-byte IPC blobs and per-rank scalars with
+    torch.distributed (plumbing).
+
+    Single process, several shards (Aer's Controller layout; device ids may repeat, which puts several shards on one
+    GPU -- how the 1-GPU test tier covers the exchange paths):
+        ShardedState(n, devices=[0, 1, 2, 3])
+    One process per GPU under torchrun:
+        ShardedState(n, world=W, rank=r, device=local_rank, dist=torch.distributed)
+    """
+
+    KIND = {"matrix": 0, "diagonal": 1, "mcx": 2, "mcy": 3, "mcphase": 4, "mcswap": 5, "mcu": 6}
+
+    def __init__(self, n, devices=None, world=None, rank=None, device=0, dist=None, dtype=np.complex128,
+                 staging_bytes=None):
+        import ctypes as C
+        from . import capi
+        self._C, self._capi, self._lib = C, capi, capi.lib()
+        self.n = int(n)
+        self.dist = dist
+        self.dtype = np.dtype(dtype)
+        prec = 64 if self.dtype == np.complex128 else 32
+        if devices is not None:
+            self.world = len(devices)
+            self.local_ranks = list(range(self.world))
+            devs = [int(d) for d in devices]
+        else:
+            self.world, self.local_ranks, devs = int(world), [int(rank)], [int(device)]
+        self.gbits = int(np.log2(self.world))
+        self.nl = self.n - self.gbits
+        self.h = C.c_void_p()
+        lr = (C.c_int * len(devs))(*self.local_ranks)
+        dv = (C.c_int * len(devs))(*devs)
+        sb = (1 << 64) - 1 if staging_bytes is None else int(staging_bytes)
+        capi.check(self._lib.b200sv_sharded_create(C.byref(self.h), self.n, prec, self.world, len(devs), lr, dv,
+                                                   C.c_uint64(sb)))
+        if devices is None and self.world > 1:
+            blob = C.create_string_buffer(128)
+            capi.check(self._lib.b200sv_sharded_ipc_export(self.h, self.local_ranks[0], blob))
+            blobs = [None] * self.world
+            dist.all_gather_object(blobs, bytes(blob.raw))
+            for r in range(self.world):
+                if r != self.local_ranks[0]:
+                    capi.check(self._lib.b200sv_sharded_ipc_attach(self.h, r, C.create_string_buffer(blobs[r], 128)))
+            dist.barrier()
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self._lib.b200sv_sharded_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- op encoding (the slice of Statevector::State::apply_op's gate table the workloads use,
+    # statevector_state.hpp:314-384,757-960)
+    @classmethod
+    def encode(cls, ops):
+        from .fusion import gate_matrix
+        K = cls.KIND
+        kinds, off, qs, doff, data = [], [0], [], [0], []
+
+        def put(kind, qubits, payload=()):
+            kinds.append(kind)
+            qs.extend(int(q) for q in qubits)
+            off.append(len(qs))
+            data.extend(payload)
+            doff.append(len(data))
+
+        def flat(z):
+            z = np.ascontiguousarray(np.asarray(z, dtype=np.complex128).reshape(-1))
+            return z.view(np.float64).tolist()
+
+        for op in ops:
+            if op[0] == "unitary":
+                put(K["matrix"], op[1], flat(np.asarray(op[2], dtype=np.complex128).reshape(-1, order="F")))
+            elif op[0] == "diagonal":
+                put(K["diagonal"], op[1], flat(op[2]))
+            elif op[0] == "gate":
+                name, qubits, params = op[1], op[2], op[3]
+                if name in ("x", "cx", "ccx", "mcx"):
+                    put(K["mcx"], qubits)
+                elif name in ("y", "cy"):
+                    put(K["mcy"], qubits)
+                elif name in ("z", "cz", "ccz"):
+                    put(K["mcphase"], qubits, [-1.0, 0.0])
+                elif name in ("cp", "p", "mcphase", "cu1"):
+                    ph = np.exp(1j * params[0])
+                    put(K["mcphase"], qubits, [ph.real, ph.imag])
+                elif name in ("s", "sdg", "t", "tdg"):
+                    ph = {"s": 1j, "sdg": -1j, "t": np.exp(0.25j * np.pi), "tdg": np.exp(-0.25j * np.pi)}[name]
+                    put(K["mcphase"], qubits, [ph.real, ph.imag])
+                elif name in ("swap", "cswap"):
+                    put(K["mcswap"], qubits)
+                elif name == "rz":
+                    put(K["diagonal"], qubits, flat(np.diag(gate_matrix("rz", params))))
+                elif name in ("h", "sx"):
+                    put(K["mcu"], qubits, flat(np.asarray(gate_matrix(name, params)).reshape(-1, order="F")))
+                else:
+                    raise ValueError("unsupported gate %s" % name)
+            else:
+                raise ValueError(op[0])
+        return (np.asarray(kinds, dtype=np.int32), np.asarray(off, dtype=np.int32),
+                np.asarray(qs if qs else [0], dtype=np.int32), np.asarray(doff, dtype=np.int64),
+                np.asarray(data if data else [0.0], dtype=np.float64))
+
+    @classmethod
+    def plan_only(cls, n, world, ops, staging_bytes, dtype=np.complex128):
+        """Host-only: passes / exchanges / overlap decisions apply_ops would take (no device)."""
+        import ctypes as C
+        from . import capi
+        kinds, off, qs, doff, data = cls.encode(ops)
+        out = np.zeros(8)
+        capi.check(capi.lib().b200sv_sharded_plan_only(
+            int(n), 64 if np.dtype(dtype) == np.complex128 else 32, int(world), C.c_uint64(int(staging_bytes)), int(kinds.size),
+            kinds.ctypes.data_as(C.POINTER(C.c_int)), off.ctypes.data_as(C.POINTER(C.c_int)),
+            qs.ctypes.data_as(C.POINTER(C.c_int)), doff.ctypes.data_as(C.POINTER(C.c_int64)),
+            data.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double))))
+        keys = ("passes", "exchanges", "staged", "inplace", "passes_overlapped", "slabs_max", "slabs_min", "qubit_swaps")
+        return {k: int(v) for k, v in zip(keys, out)}
+
+    # ---- execution
+    def initialize(self):
+        self._capi.check(self._lib.b200sv_sharded_initialize(self.h))
+
+    def apply_ops(self, ops=None, encoded=None):
+        C = self._C
+        kinds, off, qs, doff, data = encoded if encoded is not None else self.encode(ops)
+        self._capi.check(self._lib.b200sv_sharded_apply_ops(
+            self.h, int(kinds.size), kinds.ctypes.data_as(C.POINTER(C.c_int)), off.ctypes.data_as(C.POINTER(C.c_int)),
+            qs.ctypes.data_as(C.POINTER(C.c_int)), doff.ctypes.data_as(C.POINTER(C.c_int64)),
+            data.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def synchronize(self):
+        self._capi.check(self._lib.b200sv_sharded_synchronize(self.h))
+        if self.dist is not None and self.world > 1 and len(self.local_ranks) < self.world:
+            self.dist.barrier()
+
+    def stats(self):
+        out = np.zeros(8)
+        self._capi.check(self._lib.b200sv_sharded_stats(self.h, out.ctypes.data_as(self._C.POINTER(self._C.c_double))))
+        keys = ("passes", "exchanges", "staged", "inplace", "launches", "copies", "bytes_sent_per_shard", "overlapped_passes")
+        return {k: (float(v) if k.startswith("bytes") else int(v)) for k, v in zip(keys, out)}
+
+    def elapsed_ms(self):
+        v = self._C.c_double(0)
+        self._capi.check(self._lib.b200sv_sharded_elapsed_ms(self.h, self._C.byref(v)))
+        return v.value
+
+    @property
+    def phys(self):
+        a = np.zeros(self.n, dtype=np.int32)
+        self._capi.check(self._lib.b200sv_sharded_qubit_map(self.h, a.ctypes.data_as(self._C.POINTER(self._C.c_int))))
+        return [int(x) for x in a]
+
+    def restore_order(self):
+        self._capi.check(self._lib.b200sv_sharded_restore_order(self.h))
+
+    # ---- reductions (per-process partials summed with torch.distributed when the shards live in several processes)
+    def _sum(self, arr):
+        arr = np.asarray(arr, dtype=np.float64)
+        if self.dist is None or len(self.local_ranks) == self.world:
+            return arr
+        import torch
+        t = torch.as_tensor(arr).cuda()
+        self.dist.all_reduce(t)
+        return t.cpu().numpy()
+
+    def norms(self):
+        self.synchronize()
+        out = np.zeros(self.world)
+        self._capi.check(self._lib.b200sv_sharded_norms(self.h, out.ctypes.data_as(self._C.POINTER(self._C.c_double))))
+        return self._sum(out)
+
+    def norm(self):
+        return float(self.norms().sum())
+
+    def expval_pauli(self, qubits, pauli):
+        C = self._C
+        self.synchronize()
+        q = np.ascontiguousarray(list(qubits), dtype=np.uint64)
+        v = C.c_double(0)
+        self._capi.check(self._lib.b200sv_sharded_expval_pauli(self.h, q.ctypes.data_as(C.POINTER(C.c_uint64)), int(q.size),
+                                                               pauli.encode(), C.byref(v)))
+        return float(self._sum([v.value])[0])
+
+    def sample_measure(self, rnds, exact_order=True):
+        C = self._C
+        if exact_order:
+            self.restore_order()
+        norms = self.norms()
+        rnds = np.ascontiguousarray(rnds, dtype=np.float64)
+        out = np.zeros(rnds.size, dtype=np.uint64)
+        self._capi.check(self._lib.b200sv_sharded_sample_measure(
+            self.h, rnds.ctypes.data_as(C.POINTER(C.c_double)), int(rnds.size), norms.ctypes.data_as(C.POINTER(C.c_double)),
+            out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        if self.dist is not None and len(self.local_ranks) < self.world:
+            return self._sum(out.astype(np.float64)).astype(np.uint64)  # exact below 2^53
+        return out
+
+    def shard_vector(self, rank):
+        """Amplitudes of a local shard in PHYSICAL order (call restore_order() first for the logical slice)."""
+        C = self._C
+        self.synchronize()
+        hh = C.c_void_p()
+        self._capi.check(self._lib.b200sv_sharded_shard_handle(self.h, int(rank), C.byref(hh)))
+        out = np.empty(1 << self.nl, dtype=self.dtype)
+        self._capi.check(self._lib.b200sv_download(hh, out.ctypes.data_as(C.c_void_p), 0, 1 << self.nl))
+        return out
+
+    def vector(self):
+        """The whole register in logical order (single-process layout, small n: tests)."""
+        self.restore_order()
+        return np.concatenate([self.shard_vector(r) for r in self.local_ranks])

@@ -177,3 +177,20 @@ def test_cpp_fusion_equals_python_reference(case, mq, md):
     for x, y in zip(a, b):
         assert x[0] == y[0] and list(x[1]) == list(y[1])
         assert np.max(np.abs(np.asarray(x[2]) - np.asarray(y[2]))) < 1e-13
+
+
+def test_sharded_plan_only_counts():
+    """Host-only view of the C++ sharded executor: exchanges, staged / in-place decisions, slab counts."""
+    from qiskit_aer_b200 import circuits, sharded
+    ops = circuits.quantum_volume(36, 10, seed=1234)
+    big = sharded.ShardedState.plan_only(36, 8, ops, 34 << 30)
+    assert big["exchanges"] == 3 and big["qubit_swaps"] == 9 and big["staged"] == 3 and big["inplace"] == 0
+    assert big["passes"] <= 23 and big["passes_overlapped"] == 6 and big["slabs_min"] >= 4
+    # 112 GiB leave a shard per exchange: a 20 GiB staging area still pipelines (8 slabs, one buffer) ...
+    mid = sharded.ShardedState.plan_only(36, 8, ops, 20 << 30)
+    assert mid["staged"] == 3 and mid["slabs_min"] == 8
+    # ... a 1 GiB one does not: in-place peer swaps
+    small = sharded.ShardedState.plan_only(36, 8, ops, 1 << 30)
+    assert small["staged"] == 0 and small["inplace"] == 3
+    one = sharded.ShardedState.plan_only(33, 1, circuits.quantum_volume(33, 10, seed=1234), 0)
+    assert one["exchanges"] == 0 and one["passes"] == 17

@@ -67,6 +67,34 @@ def main():
         ok = ok and good
         print("rank %d %s min_run_bits=%d swaps=%d max|err|=%.2e ev_err=%.2e samples_equal=%s" %
               (rank, mode, min_run_bits, nsw, err, ev_err, same), flush=True)
+    # ---- the path bench.py times at N > 1: the C++ sharded executor (csrc/sharded.cu), one shard per process --
+    # un-fused gates -> epoch plan -> tile passes on the shard + staged / pipelined exchange (flag words over NVLink)
+    del runners
+    qv.close()
+    torch.cuda.synchronize()
+    for label, env, staging in (("cpp-staged", {"B200SV_SHARD_MIN_RUN_BITS": "5", "B200SV_SHARD_SLAB_BITS": "2"}, 1 << 22),
+                                ("cpp-inplace", {}, 0)):
+        os.environ.update(env)
+        st = sharded.ShardedState(n, world=world, rank=rank, device=local, dist=dist, staging_bytes=staging)
+        ops = circuits.quantum_volume(n, 6, seed=17) + circuits.qft(n)
+        ref = OracleQV(n)
+        executor.apply_ops(ref, ops)
+        for rep in range(2):
+            st.initialize()
+            st.apply_ops(ops)
+        stats = st.stats()
+        ev_err = max(abs(st.expval_pauli(qs, pl) - ref.expval_pauli(qs, pl))
+                     for qs, pl in opgen.random_paulis(5, n, 6, max_weight=3))
+        rn = q.rng_uniform(77, 500)
+        same = np.array_equal(st.sample_measure(rn), ref.sample_measure(rn))
+        mine = st.shard_vector(rank)
+        err = float(np.max(np.abs(mine - ref.vector()[rank << nl:(rank + 1) << nl])))
+        good = err < 1e-12 and ev_err < 1e-10 and same and stats["exchanges"] > 0
+        ok = ok and good
+        print("rank %d %s exchanges=%d staged=%d inplace=%d overlapped=%d max|err|=%.2e ev_err=%.2e samples_equal=%s" %
+              (rank, label, stats["exchanges"], stats["staged"], stats["inplace"], stats["overlapped_passes"], err, ev_err,
+               same), flush=True)
+        st.close()
     t = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(t)
     if rank == 0:

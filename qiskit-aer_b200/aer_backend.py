@@ -88,7 +88,8 @@ def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, m
 
 def run_circuit(n, ops, device="GPU", shots=0, seed=1234, threads=0, fusion=True, fusion_max_qubit=5,
                 fusion_threshold=14, precision="double", blocking_qubits=None, noise_model=None,
-                batched_shots_gpu=False, batched_shots_gpu_max_qubits=16, method="statevector", **circ_kw):
+                batched_shots_gpu=False, batched_shots_gpu_max_qubits=16, method="statevector", target_gpus=None,
+                chunk_swap_buffer_qubits=None, **circ_kw):
     """Runs through Controller::execute (src/controllers/aer_controller.hpp:458); returns experiment 0's dict."""
     cw = load()
     c = build_circuit(cw, n, ops, shots, seed, **circ_kw)
@@ -108,6 +109,10 @@ def run_circuit(n, ops, device="GPU", shots=0, seed=1234, threads=0, fusion=True
     if blocking_qubits is not None:
         cfg.blocking_enable = True
         cfg.blocking_qubits = int(blocking_qubits)
+    if target_gpus is not None:
+        cfg.target_gpus = [int(g) for g in target_gpus]
+    if chunk_swap_buffer_qubits is not None:
+        cfg.chunk_swap_buffer_qubits = int(chunk_swap_buffer_qubits)
     if batched_shots_gpu:
         cfg.batched_shots_gpu = True
         cfg.batched_shots_gpu_max_qubits = int(batched_shots_gpu_max_qubits)

@@ -21,11 +21,15 @@ def apply_op(qv, op):
         name, qubits, params = op[1], op[2], op[3]
         if name == "h":      # apply_mcu(u4(pi/2,0,pi,0)), statevector_state.hpp:809-811
             qv.apply_mcu(qubits, colmajor(gate_matrix("h", [])))
-        elif name in ("x", "cx"):
+        elif name in ("x", "cx", "ccx", "mcx"):
             qv.apply_mcx(qubits)
+        elif name in ("y", "cy"):
+            qv.apply_mcy(qubits)
+        elif name in ("z", "cz", "ccz"):
+            qv.apply_mcphase(qubits, -1.0)
         elif name == "cp":   # apply_mcphase, statevector_state.hpp:769-772
             qv.apply_mcphase(qubits, np.exp(1j * params[0]))
-        elif name == "swap":
+        elif name in ("swap", "cswap"):
             qv.apply_mcswap(qubits)
         elif name == "rz":
             qv.apply_diagonal_matrix(qubits, np.diag(gate_matrix("rz", params)))

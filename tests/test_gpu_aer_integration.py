@@ -95,6 +95,39 @@ def test_cache_blocking_multi_chunk_path(blocking_qubits):
     assert np.array_equal(_counts(chunked, n), _counts(plain, n))
 
 
+@pytest.mark.parametrize("virtual_gpus", [1, 2, 4])
+@pytest.mark.parametrize("blocking_qubits,buffer_qubits", [(10, 2), (17, None)])
+def test_cache_blocking_multi_chunk_swap_and_multi_device(virtual_gpus, blocking_qubits, buffer_qubits, monkeypatch):
+    """apply_multi_chunk_swap (parallel_state_executor.hpp:1339-1552) -> apply_chunk_swap(chunk, dest_offset, src_offset,
+    size) range swaps, and the chunks of the register spread over several GPUs (chunk i of C on target_gpus[i*G/C],
+    chunk_manager.hpp:330-353): with B200SV_VIRTUAL_GPUS the placement / grouping / peer-swap code runs on one GPU,
+    on a multi-GPU box the real devices are used.  Chunked == unchunked (test_chunk.py:31-168)."""
+    import torch
+    from qiskit_aer_b200 import circuits
+    be = _backend()
+    n = 13 if blocking_qubits == 10 else 20
+    ndev = torch.cuda.device_count()
+    if ndev >= 2 and virtual_gpus > 1:
+        monkeypatch.delenv("B200SV_VIRTUAL_GPUS", raising=False)
+        targets = list(range(min(ndev, virtual_gpus)))
+    else:
+        monkeypatch.setenv("B200SV_VIRTUAL_GPUS", str(virtual_gpus))
+        targets = None
+    ops = circuits.quantum_volume(n, 4, seed=3) + circuits.qft(n)[:3 * n]
+    paulis = opgen.random_paulis(1, n, 4, max_weight=3)
+    kw = dict(shots=1000, seed=21, fusion=True, fusion_max_qubit=3, fusion_threshold=1, expvals=paulis,
+              save_statevector=n <= 16)
+    chunked = be.run_circuit(n, ops, device="GPU", blocking_qubits=blocking_qubits, target_gpus=targets,
+                             chunk_swap_buffer_qubits=buffer_qubits, **kw)
+    plain = be.run_circuit(n, ops, device="CPU", **kw)
+    assert chunked["metadata"]["cacheblocking"]["enabled"]
+    if n <= 16:
+        assert opgen.fidelity_gap(np.asarray(plain["data"]["sv"]), np.asarray(chunked["data"]["sv"])) < 1e-10
+    for i in range(len(paulis)):
+        assert abs(chunked["data"]["ev%d" % i] - plain["data"]["ev%d" % i]) < 1e-10
+    assert np.array_equal(_counts(chunked, n), _counts(plain, n))
+
+
 def test_single_precision_through_controller():
     from qiskit_aer_b200 import circuits
     be = _backend()
@@ -148,9 +181,14 @@ def test_batched_shots_gpu_option_noisy_pauli_circuit():
     assert abs(ideal["data"]["ev0"] - bat["data"]["ev0"]) > 0.02  # the noise is really applied
 
 
-def test_batched_shots_mid_circuit_measure_reset_and_kraus():
+@pytest.mark.parametrize("precision", ["double", "single"])
+@pytest.mark.parametrize("virtual_gpus", [1, 3])
+def test_batched_shots_mid_circuit_measure_reset_and_kraus(precision, virtual_gpus, monkeypatch):
+    """Also: single-precision batches (aer_controller.hpp:642-646 batches QubitVectorThrust<float> too) and shot
+    containers on several GPUs (one group per GPU, batch_shots_executor.hpp:421-435)."""
     from qiskit_aer_b200 import circuits
     be = _backend()
+    monkeypatch.setenv("B200SV_VIRTUAL_GPUS", str(virtual_gpus))
     n, shots = 6, 4000
     g = 0.3  # amplitude damping Kraus pair on qubit 2
     K0 = np.array([[1, 0], [0, np.sqrt(1 - g)]], dtype=complex)
@@ -158,9 +196,9 @@ def test_batched_shots_mid_circuit_measure_reset_and_kraus():
     ops = [("gate", "h", [q], []) for q in range(n)] + [("gate", "cx", [0, 1], []), ("gate", "rx", [2], [1.1])]
     ops += [("measure", [0], [0]), ("reset", [1]), ("gate", "h", [1], []), ("kraus", [2], [K0, K1]),
             ("gate", "cx", [1, 3], []), ("gate", "ry", [4], [0.7])]
-    kw = dict(shots=shots, seed=9, fusion=False)
+    kw = dict(shots=shots, seed=9, fusion=False, precision=precision)
     bat = be.run_circuit(n, ops, device="GPU", batched_shots_gpu=True, **kw)
-    ref = be.run_circuit(n, ops, device="CPU", **kw)
+    ref = be.run_circuit(n, ops, device="CPU", **dict(kw, precision="double"))
     assert bat["metadata"].get("batched_shots_optimization") is True
     fb, fr = _freq(bat, n, shots), _freq(ref, n, shots)
     assert 0.5 * np.abs(fb - fr).sum() < 0.1

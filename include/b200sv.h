@@ -55,6 +55,11 @@ int b200sv_device_count(int *count);
  * (chunk/device_chunk_container.hpp:391-404 cudaMemGetInfo; circuit_executor.hpp:378-392 get_gpu_memory_mb) */
 int b200sv_mem_info(int device, uint64_t *free_bytes, uint64_t *total_bytes);
 
+/* Measurement aid (no reference counterpart): the FP64 FMA rate this device sustains with constant-bank multiplier
+ * operands -- the denominator of the tile passes' FP64 roofline, measured in the same run as the numbers it bounds.
+ * burst = best single launch, sustained = mean of the second half of ~duration_ms of back-to-back launches. */
+int b200sv_measure_fp64_peak(int device, double duration_ms, double *burst_tflops, double *sustained_tflops);
+
 /* QubitVector(), set_num_qubits (qubitvector.hpp:922; thrust :860 chunk_setup).
  * Allocates num_states << num_qubits amplitudes on `device` and a private stream. */
 int b200sv_create(b200sv_handle *out, int num_qubits, int64_t num_states, int precision, int device);
@@ -290,6 +295,11 @@ int b200sv_sharded_plan_only(int num_qubits, int precision, int world, uint64_t 
 /* of the last apply_ops: {tile passes, exchanges, staged, in place, kernel launches, DMA copies, bytes sent per shard,
  * passes that ran slab-wise next to an exchange} */
 int b200sv_sharded_stats(b200sv_sharded_handle h, double *out8);
+/* CUDA-event profiling of the first local shard: profile(1) starts collecting, profile(0) stops; profile_read sums
+ * {count, ms} pairs for: whole-state tile passes, staged exchange regions, pushes (copy stream), unstage kernels,
+ * slab passes, in-place exchanges */
+int b200sv_sharded_profile(b200sv_sharded_handle h, int on);
+int b200sv_sharded_profile_read(b200sv_sharded_handle h, double *out12);
 /* device time of the last apply_ops (CUDA events on the shards' compute streams, max over local shards) */
 int b200sv_sharded_elapsed_ms(b200sv_sharded_handle h, double *ms);
 /* logical qubit -> physical position (>= local qubits: selects the shard) */

@@ -67,6 +67,7 @@ SIGNATURES = {
     "b200sv_swap_range_peer": [_vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64],
     "b200sv_copy_range_peer": [_vp, C.c_uint64, _vp, C.c_uint64, C.c_uint64],
     "b200sv_mem_info": [C.c_int, _u64p, _u64p],
+    "b200sv_measure_fp64_peak": [C.c_int, C.c_double, _f64p, _f64p],
     "b200sv_pack_half": [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _vp],
     "b200sv_unpack_half": [_vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, _vp],
     "b200sv_ipc_export": [_vp, _vp],
@@ -88,6 +89,8 @@ SIGNATURES = {
     "b200sv_sharded_plan_only": [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int), C.POINTER(C.c_int64), _f64p, _f64p],
     "b200sv_sharded_stats": [_vp, _f64p],
+    "b200sv_sharded_profile": [_vp, C.c_int],
+    "b200sv_sharded_profile_read": [_vp, _f64p],
     "b200sv_sharded_elapsed_ms": [_vp, _f64p],
     "b200sv_sharded_qubit_map": [_vp, C.POINTER(C.c_int)],
     "b200sv_sharded_restore_order": [_vp],

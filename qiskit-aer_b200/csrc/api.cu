@@ -201,6 +201,15 @@ int b200sv_mem_info(int device, uint64_t *free_bytes, uint64_t *total_bytes) {
   });
 }
 
+int b200sv_measure_fp64_peak(int device, double duration_ms, double *burst_tflops, double *sustained_tflops) {
+  return guard([&] {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) throw Error("measure_fp64_peak: device index out of range");
+    if (!burst_tflops || !sustained_tflops) throw Error("measure_fp64_peak: null output");
+    measure_fp64_peak(device, duration_ms, burst_tflops, sustained_tflops);
+  });
+}
+
 int b200sv_create(b200sv_handle *out, int num_qubits, int64_t num_states, int precision, int device) {
   return guard([&] {
     State *s = make_state(num_qubits, num_states, precision, device);

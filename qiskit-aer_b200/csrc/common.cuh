@@ -135,6 +135,8 @@ void launch_swap_range_peer(State &s, uint64_t dest_offset, void *peer, uint64_t
 int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats, int low_bits,
                         const int *slot = nullptr, const uint8_t *codes_host = nullptr, int nslots = 0);
 
+void measure_fp64_peak(int device, double duration_ms, double *burst_tflops, double *sustained_tflops);
+
 // plan once, launch later (whole state or slab by slab): the sharded executor's view of the tile engine
 TilePlan *tile_plan_build(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *mats);
 void tile_plan_free(TilePlan *plan);

@@ -873,4 +873,68 @@ void launch_multi_swap_peer(State &s, int k, const int *local_q, uint32_t my_g, 
   B200_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------ FP64 issue-peak probe (measurement aid)
+// DFMA chains whose multiplier comes straight from the constant bank (the operand form the tile rounds use): what the
+// FP64 pipe of THIS device sustains, measured next to the bench numbers it is the denominator of
+// (tools/micro/dfma_operands.cu is the standalone version; profiles/r01_fp64_pipe_microbench.md).
+struct PeakParams { double m[32]; };
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, const __grid_constant__ PeakParams p, int iters) {
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = threadIdx.x * 1e-9 + i;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        a[i] = fma(a[i], p.m[j], a[i + 1]);
+        a[i + 1] = fma(a[i + 1], p.m[j], a[i + 2]);
+        a[i + 2] = fma(a[i + 2], p.m[j], a[i + 3]);
+        a[i + 3] = fma(a[i + 3], p.m[j], a[i]);
+      }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += a[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// runs the probe for ~duration_ms; burst = best single launch, sustained = mean over the second half (power-capped clock)
+void measure_fp64_peak(int device, double duration_ms, double *burst_tflops, double *sustained_tflops) {
+  B200_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B200_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 4, iters = 1024;
+  double *out = nullptr;
+  B200_CUDA(cudaMalloc(&out, (size_t)blocks * 256 * sizeof(double)));
+  PeakParams p;
+  for (int i = 0; i < 32; i++) p.m[i] = 1.0 + 1e-9 * i;
+  cudaEvent_t e0, e1;
+  B200_CUDA(cudaEventCreate(&e0));
+  B200_CUDA(cudaEventCreate(&e1));
+  const double flops = (double)blocks * 256 * iters * 32 * 16 * 2;
+  std::vector<double> tf;
+  double spent = 0;
+  dfma_peak_kernel<<<blocks, 256>>>(out, p, iters);  // warm-up
+  B200_CUDA(cudaDeviceSynchronize());
+  while (spent < duration_ms || tf.size() < 4) {
+    B200_CUDA(cudaEventRecord(e0));
+    dfma_peak_kernel<<<blocks, 256>>>(out, p, iters);
+    B200_CUDA(cudaEventRecord(e1));
+    B200_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    B200_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    tf.push_back(flops / ms / 1e9);
+    spent += ms;
+  }
+  double best = 0, sum = 0;
+  for (double v : tf) best = std::max(best, v);
+  for (size_t i = tf.size() / 2; i < tf.size(); i++) sum += tf[i];
+  *burst_tflops = best;
+  *sustained_tflops = sum / (double)(tf.size() - tf.size() / 2);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+}
+
 }  // namespace b200sv

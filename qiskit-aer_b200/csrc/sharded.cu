@@ -128,7 +128,13 @@ struct Shard {
   cudaEvent_t ev_pass[kEvRing] = {};  // compute stream -> copy stream: "pass on slab i done"
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
   bool ipc_data = false, ipc_aux = false;  // mapped through CUDA IPC (close on destroy)
+  // profiling (first local shard only): CUDA-event pairs around passes, exchange regions, pushes, unstages
+  struct Rec { int kind; cudaEvent_t a, b; };
+  std::vector<Rec> prof;
+  std::vector<cudaEvent_t> pool;
+  size_t pool_used = 0;
 };
+enum { PR_PASS = 0, PR_REGION = 1, PR_PUSH = 2, PR_UNSTAGE = 3, PR_SLAB_PASS = 4, PR_INPLACE = 5, PR_KINDS = 6 };
 
 struct Sharded {
   int n = 0, nl = 0, gbits = 0, world = 1, precision = B200SV_F64;
@@ -140,6 +146,7 @@ struct Sharded {
   int min_run_bits = 20;
   int want_slab_bits = 3;
   bool allow_staged = true;
+  bool profile = false;
   // statistics of the last run
   int64_t stat_passes = 0, stat_exchanges = 0, stat_staged = 0, stat_inplace = 0, stat_launches = 0, stat_copies = 0;
   int64_t stat_overlapped_passes = 0;
@@ -149,6 +156,37 @@ struct Sharded {
 };
 
 static void sel(const Shard &s) { B200_CUDA(cudaSetDevice(s.st->device)); }
+
+// profiling scope: records an event pair on `stream` around a piece of work of the first local shard
+struct ProfScope {
+  Shard *m = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kind = 0;
+  static cudaEvent_t take(Shard &m) {
+    if (m.pool_used == m.pool.size()) {
+      cudaEvent_t e;
+      B200_CUDA(cudaEventCreate(&e));
+      m.pool.push_back(e);
+    }
+    return m.pool[m.pool_used++];
+  }
+  ProfScope(Sharded &S, Shard &sh, cudaStream_t st, int k) {
+    if (!S.profile || sh.rank != S.local[0]) return;
+    m = &sh; stream = st; kind = k;
+    sel(sh);
+    a = take(sh); b = take(sh);
+    B200_CUDA(cudaEventRecord(a, stream));
+  }
+  void end() {
+    if (!m) return;
+    cudaSetDevice(m->st->device);
+    cudaEventRecord(b, stream);
+    m->prof.push_back({kind, a, b});
+    m = nullptr;
+  }
+  ~ProfScope() { end(); }
+};
 
 // ------------------------------------------------------------------------------------------ cross-shard ordering
 // signal: "everything issued so far on `stream` of local shard `me` is done" becomes visible under (kind, seq) to the
@@ -582,6 +620,7 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
       Shard &m = S.sh[me];
       if (before.valid_for(me)) {
         spec.value = (uint32_t)i;
+        ProfScope ps(S, m, m.st->stream, PR_SLAB_PASS);
         launch_pass(S, m, *before.step, before.index(me), s ? &spec : nullptr);
         if (i == 0) S.stat_overlapped_passes++;
       }
@@ -599,6 +638,7 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
       const uint64_t need_unstaged = c0_unstaged + (uint64_t)std::max(0, i - nbuf + 1);
       wait(S, me, m.xs, F_UNSTAGED, need_unstaged, group_of(x, me, false));
       const uint32_t my_g = gval_of(x, me);
+      ProfScope ps_push(S, m, m.xs, PR_PUSH);
       for (uint32_t v = 0; v < (1u << k); v++) {
         if (v == my_g) continue;
         const Shard &peer = S.sh[peer_of(x, me, v)];
@@ -606,6 +646,7 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
         const uint32_t slot = my_g < v ? my_g : my_g - 1;  // the receiver (id v) skips its own id
         push_subblock(S, m, fixed_pos, fixed_mask(v, i), peer.staging + (size_t)b * buf_bytes + (size_t)slot * slot_bytes);
       }
+      ps_push.end();
       signal(S, me, m.xs, F_PUSHED, c0_pushed + i + 1, group_of(x, me, true));
     }
     // 3. unstage slab i and run the pass after the exchange on it
@@ -626,14 +667,17 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
       const unsigned gx = (unsigned)std::min<uint64_t>((sub + 1023) / 1024, std::max<uint64_t>(1, (uint64_t)m.st->num_sms * 8 / up.nslots));
       dim3 grid(std::max(gx, 1u), (unsigned)up.nslots);
       const char *src = m.staging + (size_t)b * buf_bytes;
+      ProfScope ps_un(S, m, m.st->stream, PR_UNSTAGE);
       if (S.precision == B200SV_F64) unstage_kernel<uint4><<<grid, 256, 0, m.st->stream>>>((uint4 *)m.data, (const uint4 *)src, up);
       else unstage_kernel<uint2><<<grid, 256, 0, m.st->stream>>>((uint2 *)m.data, (const uint2 *)src, up);
       B200_CUDA(cudaGetLastError());
+      ps_un.end();
       S.stat_launches++;
       // to every shard: the next exchange may pair this shard with different partners
       signal(S, me, m.st->stream, F_UNSTAGED, c0_unstaged + i + 1, all_others(S, me));
       if (after.valid_for(me)) {
         spec.value = (uint32_t)i;
+        ProfScope ps(S, m, m.st->stream, PR_SLAB_PASS);
         launch_pass(S, m, *after.step, after.index(me), s ? &spec : nullptr);
         if (i == 0) S.stat_overlapped_passes++;
       }
@@ -713,7 +757,10 @@ static void run_program(Sharded &S, const Program &prog, const std::vector<ShOp>
     if (st.type == 0) {
       for (int me : S.local) {
         const int np = tile_plan_passes(st.plans[me]);
-        for (int p = first_taken[si] ? 1 : 0; p < (last_taken[si] ? np - 1 : np); p++) launch_pass(S, S.sh[me], st, p, nullptr);
+        for (int p = first_taken[si] ? 1 : 0; p < (last_taken[si] ? np - 1 : np); p++) {
+          ProfScope ps(S, S.sh[me], S.sh[me].st->stream, PR_PASS);
+          launch_pass(S, S.sh[me], st, p, nullptr);
+        }
         if (me == S.local[0]) S.stat_passes += np;
       }
       continue;
@@ -722,12 +769,15 @@ static void run_program(Sharded &S, const Program &prog, const std::vector<ShOp>
     const XSched &d = xs[si];
     S.stat_exchanges++;
     S.stat_bytes_exchanged += (double)(1ull << S.nl) * (1.0 - 1.0 / (1 << x.k)) * S.amp_bytes();
+    Shard &first = S.sh[S.local[0]];
     if (d.staged) {
       PassRef before, after;
       if (d.use_before) { before.step = &prog.steps[si - 1]; before.last = true; }
       if (d.use_after) { after.step = &prog.steps[si + 1]; after.last = false; }
+      ProfScope ps(S, first, first.st->stream, PR_REGION);
       exchange_staged(S, x, before, after, d.slab_bits, d.nbuf);
     } else {
+      ProfScope ps(S, first, first.st->stream, PR_INPLACE);
       exchange_inplace(S, x);
     }
   }
@@ -746,6 +796,7 @@ static void destroy(Sharded *S) {
           if (m.ev[kd][i]) cudaEventDestroy(m.ev[kd][i]);
       for (int i = 0; i < kEvRing; i++)
         if (m.ev_pass[i]) cudaEventDestroy(m.ev_pass[i]);
+      for (cudaEvent_t e : m.pool) cudaEventDestroy(e);
       if (m.ev_t0) cudaEventDestroy(m.ev_t0);
       if (m.ev_t1) cudaEventDestroy(m.ev_t1);
       if (m.aux) cudaFree(m.aux);
@@ -1021,6 +1072,35 @@ int b200sv_sharded_stats(b200sv_sharded_handle h, double *out8) {
     out8[5] = (double)SH->stat_copies;
     out8[6] = SH->stat_bytes_exchanged;
     out8[7] = (double)SH->stat_overlapped_passes;
+  });
+}
+
+// Profiling of the first local shard: on = 1 starts collecting CUDA-event pairs (cleared), on = 0 stops.  After a
+// synchronize, b200sv_sharded_profile_read sums them: out12 = {count, ms} for whole-state tile passes, exchange
+// regions (staged: from the first slab pass before to the last slab pass after), pushes (copy stream), unstage
+// kernels, slab passes, in-place exchanges.
+int b200sv_sharded_profile(b200sv_sharded_handle h, int on) {
+  return sguard([&] {
+    Shard &m = SH->sh[SH->local[0]];
+    B200_CUDA(cudaSetDevice(m.st->device));
+    B200_CUDA(cudaDeviceSynchronize());
+    m.prof.clear();
+    m.pool_used = 0;
+    SH->profile = on != 0;
+  });
+}
+int b200sv_sharded_profile_read(b200sv_sharded_handle h, double *out12) {
+  return sguard([&] {
+    Shard &m = SH->sh[SH->local[0]];
+    B200_CUDA(cudaSetDevice(m.st->device));
+    B200_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < 2 * PR_KINDS; i++) out12[i] = 0.0;
+    for (const Shard::Rec &r : m.prof) {
+      float ms = 0;
+      B200_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+      out12[2 * r.kind] += 1.0;
+      out12[2 * r.kind + 1] += ms;
+    }
   });
 }
 

@@ -598,6 +598,23 @@ class ShardedState:
         keys = ("passes", "exchanges", "staged", "inplace", "launches", "copies", "bytes_sent_per_shard", "overlapped_passes")
         return {k: (float(v) if k.startswith("bytes") else int(v)) for k, v in zip(keys, out)}
 
+    def profile(self, on):
+        self._capi.check(self._lib.b200sv_sharded_profile(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        out = np.zeros(12)
+        self._capi.check(self._lib.b200sv_sharded_profile_read(self.h, out.ctypes.data_as(self._C.POINTER(self._C.c_double))))
+        keys = ("tile_pass", "exchange_region", "push", "unstage", "slab_pass", "exchange_inplace")
+        return {k: {"count": int(out[2 * i]), "ms": float(out[2 * i + 1])} for i, k in enumerate(keys)}
+
+    def compute_stream(self):
+        """cudaStream_t of the first local shard's compute stream (for CUDA-event timing from the caller)."""
+        C = self._C
+        hh, p = C.c_void_p(), C.c_void_p()
+        self._capi.check(self._lib.b200sv_sharded_shard_handle(self.h, self.local_ranks[0], C.byref(hh)))
+        self._capi.check(self._lib.b200sv_stream(hh, C.byref(p)))
+        return p.value
+
     def elapsed_ms(self):
         v = self._C.c_double(0)
         self._capi.check(self._lib.b200sv_sharded_elapsed_ms(self.h, self._C.byref(v)))

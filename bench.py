@@ -605,17 +605,22 @@ def extra_noisy20():
     dt = time.perf_counter() - t0
     ev_gpu = np.array([float(r["data"]["ev%d" % i]) for i in range(len(obs))])
     t0 = time.perf_counter()
-    c = aer_backend.run_circuit(n, ops, device="CPU", shots=cpu_shots, threads=host_cores(), **kw)
+    # per-shot values on the CPU side ("list"): their spread gives the standard error of both shot means
+    c = aer_backend.run_circuit(n, ops, device="CPU", shots=cpu_shots, threads=host_cores(), expval_subtype="list", **kw)
     dtc = time.perf_counter() - t0
-    ev_cpu = np.array([float(c["data"]["ev%d" % i]) for i in range(len(obs))])
-    # per-shot expectation values lie in [-1, 1]: standard error of a shot mean <= 1/sqrt(shots)
-    sigma = np.sqrt(np.maximum(1.0 - ev_gpu ** 2, 1e-3) * (1.0 / shots + 1.0 / cpu_shots))
+    per_shot = np.array([[float(v) for v in c["data"]["ev%d" % i]] for i in range(len(obs))])  # [obs][shot]
+    ev_cpu = per_shot.mean(axis=1)
+    std = per_shot.std(axis=1, ddof=1)
+    sigma = np.maximum(std * np.sqrt(1.0 / shots + 1.0 / cpu_shots), 1e-12)
     dev_sigma = float(np.max(np.abs(ev_gpu - ev_cpu) / sigma))
     return {"workload": "noisy_random_circuit", "qubits": n, "depth": depth, "gates": len(ops), "shots": shots,
             "p1": 1e-3, "p2": 1e-2, "observables": len(obs), "seconds": dt, "shots_per_s": shots / dt,
             "batched_shots_optimization": bool(r["metadata"].get("batched_shots_optimization")),
             "reference_cpu": {"shots": cpu_shots, "seconds": dtc, "shots_per_s": cpu_shots / dtc,
-                              "threads": int(c["metadata"].get("parallel_state_update", 0)) or host_cores()},
+                              "threads": max(int(c["metadata"].get("parallel_state_update", 1)),
+                                             int(c["metadata"].get("parallel_shots", 1)))},
+            "expval_gpu": [float(x) for x in ev_gpu], "expval_cpu": [float(x) for x in ev_cpu],
+            "expval_sigma": [float(x) for x in sigma],
             "expval_max_deviation_sigma": dev_sigma, "expval_within_5_sigma": bool(dev_sigma < 5.0)}
 
 
@@ -627,9 +632,17 @@ def extra_vs_reference_gpu():
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "gpu", "controller_wrappers.so")):
         return {"unavailable": "oracle/_ref/gpu/controller_wrappers.so not built (make -C oracle ref-gpu)"}
     n = 31
-    ref = h2h.run("reference_gpu", n, "qv", True, 5)
-    same = h2h.run("b200_engine", n, "qv", True, 5)
-    best = h2h.run("b200_engine", n, "qv", False, 5)
+
+    def side(name, fusion):
+        smp = ClockSampler(0)
+        smp.start()
+        r = h2h.run(name, n, "qv", fusion, 5)
+        r["clocks"] = smp.stop()
+        return r
+
+    same = side("b200_engine", True)
+    ref = side("reference_gpu", True)
+    best = side("b200_engine", False)
     out = {"workload": "qv31_depth10", "reference_thrust_sm100_fusion5": ref, "b200_engine_same_options": same,
            "b200_engine_gate_queue": best}
     try:

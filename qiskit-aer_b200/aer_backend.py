@@ -52,7 +52,7 @@ def load():
 
 
 def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, measure=True, save_probs=None,
-                  save_density_matrix=False):
+                  save_density_matrix=False, expval_subtype="average"):
     c = cw.AerCircuit()
     c.num_qubits = n
     c.num_memory = n if (shots and measure) else 0
@@ -74,7 +74,7 @@ def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, m
         else:
             raise ValueError(op[0])
     for i, (qs, p) in enumerate(expvals):
-        c.save_expval([int(q) for q in qs], "save_expval", [p], [1.0], [0.0], "average", "ev%d" % i)
+        c.save_expval([int(q) for q in qs], "save_expval", [p], [1.0], [0.0], expval_subtype, "ev%d" % i)
     if save_probs is not None:
         c.save_state([int(q) for q in save_probs], "save_probabilities", "average", "probs")
     if save_statevector:

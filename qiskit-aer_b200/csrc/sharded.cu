@@ -123,7 +123,11 @@ struct Shard {
   // local shards only
   State *st = nullptr;
   char *aux = nullptr;
-  cudaStream_t xs = nullptr;  // copy stream
+  cudaStream_t xs = nullptr;  // copy stream (ordering of the pushes of one slab)
+  cudaStream_t us = nullptr;  // unstage stream (copy-engine unstage)
+  cudaStream_t px[8] = {};    // push streams: the copies of one slab fan out over several copy engines
+  cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
+  unsigned push_rr = 0;
   cudaEvent_t ev[F_KINDS][kEvRing] = {};
   cudaEvent_t ev_pass[kEvRing] = {};  // compute stream -> copy stream: "pass on slab i done"
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
@@ -146,6 +150,8 @@ struct Sharded {
   int min_run_bits = 20;
   int want_slab_bits = 3;
   bool allow_staged = true;
+  bool unstage_dma = false;   // move received slabs into place with the copy engines instead of a kernel
+  int push_streams = 4;
   bool profile = false;
   // statistics of the last run
   int64_t stat_passes = 0, stat_exchanges = 0, stat_staged = 0, stat_inplace = 0, stat_launches = 0, stat_copies = 0;
@@ -271,7 +277,7 @@ static std::vector<int> all_others(const Sharded &S, int rank) {
 // read `slab`, in index order, into a contiguous destination.  Runs of 2^F0 amplitudes; runs that repeat with a fixed
 // stride go out as one 2-D copy.
 static void push_subblock(Sharded &S, Shard &m, const std::vector<int> &fixed_pos /*sorted*/, uint64_t fixed_mask,
-                          char *dst) {
+                          char *compact, bool scatter = false, cudaStream_t only = nullptr) {
   const size_t ab = S.amp_bytes();
   const int nf = (int)fixed_pos.size();
   const int free_bits = S.nl - nf;
@@ -288,15 +294,25 @@ static void push_subblock(Sharded &S, Shard &m, const std::vector<int> &fixed_po
   else group = nruns;
   group = std::min(group, nruns);
   const bool use_2d = group > 1 && 2 * run_bytes < (1ull << 31);
-  for (uint64_t r = 0; r < nruns; r += use_2d ? group : 1) {
+  // a 2-D copy that spans a whole group is split so that every push stream gets a share
+  uint64_t rows = use_2d ? group : 1;
+  const int nstreams = only ? 1 : std::max(1, S.push_streams);
+  if (use_2d && nruns / group < (uint64_t)nstreams) rows = std::max<uint64_t>(1, group * (nruns / group) / nstreams);
+  for (uint64_t r = 0; r < nruns;) {
+    const uint64_t in_group = use_2d ? std::min(rows, group - (r % group)) : 1;
     const uint64_t idx = insert_zeros(r << f0, ins) | fixed_mask;
-    const char *src = m.data + idx * ab;
-    char *d = dst + (r << f0) * ab;
-    if (use_2d)
-      B200_CUDA(cudaMemcpy2DAsync(d, run_bytes, src, 2 * run_bytes, run_bytes, group, cudaMemcpyDeviceToDevice, m.xs));
-    else
-      B200_CUDA(cudaMemcpyAsync(d, src, run_bytes, cudaMemcpyDeviceToDevice, m.xs));
+    char *strided = m.data + idx * ab;
+    char *packed = compact + (r << f0) * ab;
+    cudaStream_t st = only ? only : m.px[m.push_rr++ % nstreams];
+    if (use_2d && in_group > 1) {
+      if (scatter) B200_CUDA(cudaMemcpy2DAsync(strided, 2 * run_bytes, packed, run_bytes, run_bytes, in_group, cudaMemcpyDeviceToDevice, st));
+      else B200_CUDA(cudaMemcpy2DAsync(packed, run_bytes, strided, 2 * run_bytes, run_bytes, in_group, cudaMemcpyDeviceToDevice, st));
+    } else {
+      if (scatter) B200_CUDA(cudaMemcpyAsync(strided, packed, run_bytes, cudaMemcpyDeviceToDevice, st));
+      else B200_CUDA(cudaMemcpyAsync(packed, strided, run_bytes, cudaMemcpyDeviceToDevice, st));
+    }
     S.stat_copies++;
+    r += in_group;
   }
 }
 
@@ -639,12 +655,18 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
       wait(S, me, m.xs, F_UNSTAGED, need_unstaged, group_of(x, me, false));
       const uint32_t my_g = gval_of(x, me);
       ProfScope ps_push(S, m, m.xs, PR_PUSH);
+      B200_CUDA(cudaEventRecord(m.ev_fork, m.xs));
+      for (int j = 0; j < S.push_streams; j++) B200_CUDA(cudaStreamWaitEvent(m.px[j], m.ev_fork, 0));
       for (uint32_t v = 0; v < (1u << k); v++) {
         if (v == my_g) continue;
         const Shard &peer = S.sh[peer_of(x, me, v)];
         if (!peer.staging) throw Error("sharded: shard " + std::to_string(peer.rank) + " is not attached");
         const uint32_t slot = my_g < v ? my_g : my_g - 1;  // the receiver (id v) skips its own id
         push_subblock(S, m, fixed_pos, fixed_mask(v, i), peer.staging + (size_t)b * buf_bytes + (size_t)slot * slot_bytes);
+      }
+      for (int j = 0; j < S.push_streams; j++) {
+        B200_CUDA(cudaEventRecord(m.ev_join[j], m.px[j]));
+        B200_CUDA(cudaStreamWaitEvent(m.xs, m.ev_join[j], 0));
       }
       ps_push.end();
       signal(S, me, m.xs, F_PUSHED, c0_pushed + i + 1, group_of(x, me, true));
@@ -653,28 +675,42 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
     for (int me : S.local) {
       Shard &m = S.sh[me];
       sel(m);
-      wait(S, me, m.st->stream, F_PUSHED, c0_pushed + i + 1, group_of(x, me, true));
-      UnstageParams up;
-      up.sub = sub;
-      up.nslots = (1 << k) - 1;
-      up.ins.n = (int)fixed_pos.size();
-      for (size_t u = 0; u < fixed_pos.size(); u++) up.ins.pos[u] = (uint8_t)fixed_pos[u];
       const uint32_t my_g = gval_of(x, me);
-      for (uint32_t u = 0, slot = 0; u < (1u << k); u++) {
-        if (u == my_g) continue;
-        up.fixed[slot++] = fixed_mask(u, i);
-      }
-      const unsigned gx = (unsigned)std::min<uint64_t>((sub + 1023) / 1024, std::max<uint64_t>(1, (uint64_t)m.st->num_sms * 8 / up.nslots));
-      dim3 grid(std::max(gx, 1u), (unsigned)up.nslots);
       const char *src = m.staging + (size_t)b * buf_bytes;
-      ProfScope ps_un(S, m, m.st->stream, PR_UNSTAGE);
-      if (S.precision == B200SV_F64) unstage_kernel<uint4><<<grid, 256, 0, m.st->stream>>>((uint4 *)m.data, (const uint4 *)src, up);
-      else unstage_kernel<uint2><<<grid, 256, 0, m.st->stream>>>((uint2 *)m.data, (const uint2 *)src, up);
-      B200_CUDA(cudaGetLastError());
-      ps_un.end();
-      S.stat_launches++;
-      // to every shard: the next exchange may pair this shard with different partners
-      signal(S, me, m.st->stream, F_UNSTAGED, c0_unstaged + i + 1, all_others(S, me));
+      if (S.unstage_dma) {
+        // copy engines again (unstage stream): the compute stream only waits for the result
+        wait(S, me, m.us, F_PUSHED, c0_pushed + i + 1, group_of(x, me, true));
+        ProfScope ps_un(S, m, m.us, PR_UNSTAGE);
+        for (uint32_t u = 0, slot = 0; u < (1u << k); u++) {
+          if (u == my_g) continue;
+          push_subblock(S, m, fixed_pos, fixed_mask(u, i), const_cast<char *>(src) + (size_t)slot * slot_bytes, true, m.us);
+          slot++;
+        }
+        ps_un.end();
+        signal(S, me, m.us, F_UNSTAGED, c0_unstaged + i + 1, all_others(S, me));
+        wait(S, me, m.st->stream, F_UNSTAGED, c0_unstaged + i + 1, std::vector<int>(1, me));
+      } else {
+        wait(S, me, m.st->stream, F_PUSHED, c0_pushed + i + 1, group_of(x, me, true));
+        UnstageParams up;
+        up.sub = sub;
+        up.nslots = (1 << k) - 1;
+        up.ins.n = (int)fixed_pos.size();
+        for (size_t u = 0; u < fixed_pos.size(); u++) up.ins.pos[u] = (uint8_t)fixed_pos[u];
+        for (uint32_t u = 0, slot = 0; u < (1u << k); u++) {
+          if (u == my_g) continue;
+          up.fixed[slot++] = fixed_mask(u, i);
+        }
+        const unsigned gx = (unsigned)std::min<uint64_t>((sub + 1023) / 1024, std::max<uint64_t>(1, (uint64_t)m.st->num_sms * 8 / up.nslots));
+        dim3 grid(std::max(gx, 1u), (unsigned)up.nslots);
+        ProfScope ps_un(S, m, m.st->stream, PR_UNSTAGE);
+        if (S.precision == B200SV_F64) unstage_kernel<uint4><<<grid, 256, 0, m.st->stream>>>((uint4 *)m.data, (const uint4 *)src, up);
+        else unstage_kernel<uint2><<<grid, 256, 0, m.st->stream>>>((uint2 *)m.data, (const uint2 *)src, up);
+        B200_CUDA(cudaGetLastError());
+        ps_un.end();
+        S.stat_launches++;
+        // to every shard: the next exchange may pair this shard with different partners
+        signal(S, me, m.st->stream, F_UNSTAGED, c0_unstaged + i + 1, all_others(S, me));
+      }
       if (after.valid_for(me)) {
         spec.value = (uint32_t)i;
         ProfScope ps(S, m, m.st->stream, PR_SLAB_PASS);
@@ -791,6 +827,12 @@ static void destroy(Sharded *S) {
       cudaSetDevice(m.st->device);
       cudaStreamSynchronize(m.st->stream);
       if (m.xs) { cudaStreamSynchronize(m.xs); cudaStreamDestroy(m.xs); }
+      if (m.us) { cudaStreamSynchronize(m.us); cudaStreamDestroy(m.us); }
+      for (int j = 0; j < 8; j++) {
+        if (m.px[j]) { cudaStreamSynchronize(m.px[j]); cudaStreamDestroy(m.px[j]); }
+        if (m.ev_join[j]) cudaEventDestroy(m.ev_join[j]);
+      }
+      if (m.ev_fork) cudaEventDestroy(m.ev_fork);
       for (int kd = 0; kd < F_KINDS; kd++)
         for (int i = 0; i < kEvRing; i++)
           if (m.ev[kd][i]) cudaEventDestroy(m.ev[kd][i]);
@@ -844,6 +886,8 @@ int b200sv_sharded_create(b200sv_sharded_handle *out, int num_qubits, int precis
     if (const char *e = getenv("B200SV_SHARD_MIN_RUN_BITS")) S->min_run_bits = atoi(e);
     if (const char *e = getenv("B200SV_SHARD_SLAB_BITS")) S->want_slab_bits = std::max(0, std::min(4, atoi(e)));
     if (const char *e = getenv("B200SV_SHARD_STAGED")) S->allow_staged = atoi(e) != 0;
+    if (const char *e = getenv("B200SV_SHARD_UNSTAGE")) S->unstage_dma = !strcmp(e, "dma");
+    if (const char *e = getenv("B200SV_SHARD_PUSH_STREAMS")) S->push_streams = std::max(1, std::min(8, atoi(e)));
     S->min_run_bits = std::max(1, std::min(S->min_run_bits, std::max(S->nl - 1, 1)));
     const size_t slice_bytes = ((size_t)1 << S->nl) * S->amp_bytes();
     for (int i = 0; i < nlocal; i++) {
@@ -885,6 +929,12 @@ int b200sv_sharded_create(b200sv_sharded_handle *out, int num_qubits, int precis
       m.flags = (uint64_t *)m.aux;
       m.staging = m.aux + kFlagBytes;
       B200_CUDA(cudaStreamCreateWithFlags(&m.xs, cudaStreamNonBlocking));
+      B200_CUDA(cudaStreamCreateWithFlags(&m.us, cudaStreamNonBlocking));
+      for (int j = 0; j < S->push_streams; j++) {
+        B200_CUDA(cudaStreamCreateWithFlags(&m.px[j], cudaStreamNonBlocking));
+        B200_CUDA(cudaEventCreateWithFlags(&m.ev_join[j], cudaEventDisableTiming));
+      }
+      B200_CUDA(cudaEventCreateWithFlags(&m.ev_fork, cudaEventDisableTiming));
       for (int kd = 0; kd < F_KINDS; kd++)
         for (int i = 0; i < kEvRing; i++) B200_CUDA(cudaEventCreateWithFlags(&m.ev[kd][i], cudaEventDisableTiming));
       for (int i = 0; i < kEvRing; i++) B200_CUDA(cudaEventCreateWithFlags(&m.ev_pass[i], cudaEventDisableTiming));
@@ -964,6 +1014,7 @@ int b200sv_sharded_synchronize(b200sv_sharded_handle h) {
       Shard &m = SH->sh[r];
       B200_CUDA(cudaSetDevice(m.st->device));
       B200_CUDA(cudaStreamSynchronize(m.xs));
+      B200_CUDA(cudaStreamSynchronize(m.us));
       B200_CUDA(cudaStreamSynchronize(m.st->stream));
       uint32_t err = 0;
       B200_CUDA(cudaMemcpy(&err, m.flags + (size_t)F_KINDS * SH->world, 4, cudaMemcpyDeviceToHost));

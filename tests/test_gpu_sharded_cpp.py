@@ -33,7 +33,8 @@ def _devices(world):
 
 def _make(n, world, staging, env=None, dtype=np.complex128):
     from qiskit_aer_b200 import sharded
-    keys = ("B200SV_SHARD_MIN_RUN_BITS", "B200SV_SHARD_SLAB_BITS", "B200SV_SHARD_STAGED")
+    keys = ("B200SV_SHARD_MIN_RUN_BITS", "B200SV_SHARD_SLAB_BITS", "B200SV_SHARD_STAGED", "B200SV_SHARD_UNSTAGE",
+            "B200SV_SHARD_PUSH_STREAMS")
     saved = {k: os.environ.get(k) for k in keys}
     for k in keys:
         os.environ.pop(k, None)
@@ -66,13 +67,16 @@ def _check(st, n, ops, tol=1e-10, amp_tol=1e-12, seed=5):
     return stats
 
 
+@pytest.mark.parametrize("unstage,streams", [("kernel", 4), ("dma", 1), ("dma", 3)])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_qv_staged_pipelined_exchange(world):
-    """Quantum Volume: every exchange staged, slabs cut along free index bits, neighbouring passes ride along."""
+def test_qv_staged_pipelined_exchange(world, unstage, streams):
+    """Quantum Volume: every exchange staged, slabs cut along free index bits, neighbouring passes ride along.
+    Received slabs are moved into place by a kernel or by the copy engines; pushes fan out over several streams."""
     from qiskit_aer_b200 import circuits
     n = 17 + int(np.log2(world))
     ops = circuits.quantum_volume(n, 6, seed=world)
-    st = _make(n, world, staging=1 << 22, env={"B200SV_SHARD_MIN_RUN_BITS": "5", "B200SV_SHARD_SLAB_BITS": "2"})
+    st = _make(n, world, staging=1 << 22, env={"B200SV_SHARD_MIN_RUN_BITS": "5", "B200SV_SHARD_SLAB_BITS": "2",
+                                               "B200SV_SHARD_UNSTAGE": unstage, "B200SV_SHARD_PUSH_STREAMS": str(streams)})
     stats = _check(st, n, ops)
     assert stats["exchanges"] > 0 and stats["staged"] == stats["exchanges"] and stats["inplace"] == 0
     assert stats["overlapped_passes"] > 0 and stats["copies"] > 0

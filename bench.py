@@ -435,6 +435,8 @@ def b200_arm(args):
             pass
         buf = None
         torch.cuda.empty_cache()
+        from qiskit_aer_b200 import capi
+        capi.lib().b200sv_trim()   # the child processes of the head-to-head need the memory the library keeps for reuse
         for key, fn in (("qft30", lambda: extra_qft30(local_rank)), ("noisy20_10k", extra_noisy20),
                         ("vs_reference_gpu", extra_vs_reference_gpu)):
             t0 = time.perf_counter()
@@ -444,6 +446,7 @@ def b200_arm(args):
                 extras[key] = {"error": str(e)[:300]}
             extras[key]["leg_seconds"] = time.perf_counter() - t0
             torch.cuda.empty_cache()
+            capi.lib().b200sv_trim()
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -710,6 +713,8 @@ def b200_arm_sharded(args, world, rank, local_rank, dev, saved_stdout):
     err = float(np.max(np.abs(mine - want)))
     one.close()
     stc.close()
+    from qiskit_aer_b200 import capi
+    capi.lib().b200sv_trim()
     tol = 1e-12 if AMP_BYTES == 16 else 5e-6
     t = torch.tensor([err, abs(chk_norm - 1.0)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

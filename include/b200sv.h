@@ -60,6 +60,11 @@ int b200sv_mem_info(int device, uint64_t *free_bytes, uint64_t *total_bytes);
  * burst = best single launch, sustained = mean of the second half of ~duration_ms of back-to-back launches. */
 int b200sv_measure_fp64_peak(int device, double duration_ms, double *burst_tflops, double *sustained_tflops);
 
+/* Releases the device memory the library keeps for reuse: the slice of the last destroyed handle (one block per
+ * device; Aer's executors re-create the register for every circuit, and a 128 GiB cudaMalloc/cudaFree pair costs
+ * ~0.2 s).  Allocations that fail release it by themselves; call this before handing the GPU to another process. */
+int b200sv_trim(void);
+
 /* QubitVector(), set_num_qubits (qubitvector.hpp:922; thrust :860 chunk_setup).
  * Allocates num_states << num_qubits amplitudes on `device` and a private stream. */
 int b200sv_create(b200sv_handle *out, int num_qubits, int64_t num_states, int precision, int device);

@@ -14,6 +14,7 @@ _vp = C.c_void_p
 SIGNATURES = {
     "b200sv_version": [],
     "b200sv_device_count": [C.POINTER(C.c_int)],
+    "b200sv_trim": [],
     "b200sv_create": [C.POINTER(_vp), C.c_int, C.c_int64, C.c_int, C.c_int],
     "b200sv_create_external": [C.POINTER(_vp), C.c_int, C.c_int64, C.c_int, C.c_int, _vp, _vp],
     "b200sv_destroy": [_vp],

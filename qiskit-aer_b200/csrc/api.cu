@@ -4,6 +4,7 @@
 // translation.  Kernels live in gates.cu / reduce.cu.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <random>
 
 #include "common.cuh"
@@ -13,6 +14,65 @@ namespace b200sv {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string &msg) { g_last_error = msg; }
 
+// ---- device allocations.  The slice of a destroyed handle (>= 256 MiB) is kept, one block per device, for the next
+// handle of the same size: Aer's executors create and destroy the register once per circuit / experiment
+// (Executor::run_circuit_*; the reference's ChunkManager likewise keeps its chunks when the shape repeats,
+// parallel_state_executor.hpp:318-326 "can reuse allocated chunks"), and a 128 GiB cudaMalloc + cudaFree costs ~0.2 s.
+// Every allocation that fails first releases the cache and retries; b200sv_trim() releases it on demand;
+// B200SV_ALLOC_CACHE=0 switches it off.
+namespace {
+struct CachedBlock { void *ptr = nullptr; size_t bytes = 0; };
+std::mutex g_cache_mu;
+CachedBlock g_cache[64];
+bool cache_enabled() {
+  static const bool on = [] { const char *e = getenv("B200SV_ALLOC_CACHE"); return !(e && e[0] == '0'); }();
+  return on;
+}
+}  // namespace
+void trim_alloc_cache() {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < 64; d++)
+    if (g_cache[d].ptr) {
+      cudaSetDevice(d);
+      cudaFree(g_cache[d].ptr);
+      g_cache[d] = CachedBlock();
+    }
+  cudaSetDevice(cur);
+  cudaGetLastError();
+}
+void *device_alloc(int device, size_t bytes, bool may_reuse) {
+  if (may_reuse && cache_enabled() && device >= 0 && device < 64) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_cache[device].ptr && g_cache[device].bytes == bytes) {
+      void *p = g_cache[device].ptr;
+      g_cache[device] = CachedBlock();
+      return p;
+    }
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    trim_alloc_cache();
+    e = cudaMalloc(&p, bytes);
+  }
+  B200_CUDA(e);
+  return p;
+}
+void device_free(int device, void *p, size_t bytes, bool may_cache) {
+  if (!p) return;
+  if (may_cache && cache_enabled() && bytes >= ((size_t)256 << 20) && device >= 0 && device < 64) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    if (g_cache[device].ptr) cudaFree(g_cache[device].ptr);
+    g_cache[device].ptr = p;
+    g_cache[device].bytes = bytes;
+    return;
+  }
+  cudaFree(p);
+}
+
 void *State::ensure_scratch(size_t bytes) {
   if (bytes > scratch_bytes) {
     if (scratch) {
@@ -21,7 +81,7 @@ void *State::ensure_scratch(size_t bytes) {
       scratch = nullptr;
     }
     size_t want = std::max<size_t>(bytes, 1 << 20);
-    B200_CUDA(cudaMalloc(&scratch, want));
+    scratch = device_alloc(device, want, false);
     scratch_bytes = want;
   }
   return scratch;
@@ -210,11 +270,13 @@ int b200sv_measure_fp64_peak(int device, double duration_ms, double *burst_tflop
   });
 }
 
+int b200sv_trim(void) { return guard([&] { trim_alloc_cache(); }); }
+
 int b200sv_create(b200sv_handle *out, int num_qubits, int64_t num_states, int precision, int device) {
   return guard([&] {
     State *s = make_state(num_qubits, num_states, precision, device);
     try {
-      B200_CUDA(cudaMalloc(&s->data, s->total_amps() * s->amp_bytes()));
+      s->data = device_alloc(device, s->total_amps() * s->amp_bytes(), true);
       s->owns_data = true;
       B200_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
       s->owns_stream = true;
@@ -245,7 +307,7 @@ int b200sv_destroy(b200sv_handle h) {
     if (!h) return;
     select(H);
     cudaStreamSynchronize(H->stream);
-    if (H->owns_data && H->data) cudaFree(H->data);
+    if (H->owns_data && H->data) device_free(H->device, H->data, H->total_amps() * H->amp_bytes(), true);
     if (H->scratch) cudaFree(H->scratch);
     if (H->pinned) cudaFreeHost(H->pinned);
     if (H->checkpoint) cudaFree(H->checkpoint);
@@ -316,7 +378,7 @@ int b200sv_checkpoint(b200sv_handle h) {
   return guard([&] {
     select(H);
     const size_t bytes = H->total_amps() * H->amp_bytes();
-    if (!H->checkpoint) B200_CUDA(cudaMalloc(&H->checkpoint, bytes));
+    if (!H->checkpoint) H->checkpoint = device_alloc(H->device, bytes, false);
     B200_CUDA(cudaMemcpyAsync(H->checkpoint, H->data, bytes, cudaMemcpyDeviceToDevice, H->stream));
   });
 }

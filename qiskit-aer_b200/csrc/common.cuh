@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>  // header-only (the tools library is loaded on demand by an attached profiler)
+
 #include "../../include/b200sv.h"
 
 namespace b200sv {
@@ -23,6 +25,10 @@ struct Error : std::runtime_error {
 };
 
 void set_last_error(const std::string &msg);
+// device memory with the one-block-per-device reuse cache of api.cu (OOM releases the cache and retries)
+void *device_alloc(int device, size_t bytes, bool may_reuse);
+void device_free(int device, void *p, size_t bytes, bool may_cache);
+void trim_alloc_cache();
 
 #define B200_CUDA(expr)                                                                  \
   do {                                                                                   \
@@ -30,6 +36,15 @@ void set_last_error(const std::string &msg);
     if (_e != cudaSuccess)                                                               \
       throw ::b200sv::Error(std::string(#expr) + ": " + cudaGetErrorString(_e));         \
   } while (0)
+
+// NVTX range around a host-side phase (tile pass, exchange, reduction): shows up in Nsight Systems / ncu --nvtx
+// timelines (SURVEY section 5 tracing); costs a function-pointer test when no tool is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 template <typename T> struct cx_of;
 template <> struct cx_of<double> { using type = double2; };

@@ -88,6 +88,7 @@ norm_kernel(const cx<T> *__restrict__ psi, int nq, double *__restrict__ partial)
   if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
 }
 void reduce_norm(State &s, double *out) {
+  NvtxRange nvtx("b200sv norm");
   const int nb = blocks_per_state(s, s.amps_per_state());
   run_reduction(s, nb, 1, out, [&](double *partial) {
     dim3 grid(nb, (unsigned)s.nstates);
@@ -171,6 +172,7 @@ norm_matrix_kernel(const cx<T> *__restrict__ psi, const cx<T> *__restrict__ mat 
   if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc;
 }
 void reduce_norm_matrix(State &s, const int *qubits, int k, const double *mat, double *out) {
+  NvtxRange nvtx("b200sv norm(qubits, mat)");
   if (k > kMaxRegQubits) throw Error("norm(qubits, mat): more than 5 qubits is not supported");
   const int dim = 1 << k;
   const size_t bytes = (size_t)dim * dim * s.amp_bytes();
@@ -342,6 +344,7 @@ prob_kernel(const cx<T> *__restrict__ psi, const __grid_constant__ ProbParams p,
   }
 }
 void reduce_probabilities(State &s, const int *qubits, int k, double *out) {
+  NvtxRange nvtx("b200sv probabilities");
   if (k > 26) throw Error("probabilities(qubits): more than 26 measured qubits per call is not supported");
   ProbParams p;
   p.nq = s.nq; p.k = k;
@@ -470,6 +473,7 @@ sample_kernel(const cx<T> *__restrict__ psi, int B, uint64_t nblocks, const doub
 }
 
 void sample_measure(State &s, const double *rnds, int64_t shots, uint64_t *out) {
+  NvtxRange nvtx("b200sv sample_measure");
   if (shots <= 0) return;
   const int B = std::min(kSampleB, s.nq);
   const uint64_t nblocks = s.amps_per_state() >> B;

@@ -466,6 +466,7 @@ static void run_direct(Sharded &S, Shard &m, const ShOp &op, const std::vector<i
 // Compile: epoch plan (planner.cu) -> steps.  Queueable ops between two exchanges / direct ops become one tile step
 // with a plan per rank.
 static std::unique_ptr<Program> compile(Sharded &S, const std::vector<ShOp> &ops) {
+  NvtxRange nvtx("b200sv sharded compile (epoch plan + tile plans)");
   const int nops = (int)ops.size();
   std::vector<int> off(1, 0), qs;
   std::vector<uint8_t> need;
@@ -572,6 +573,7 @@ static void launch_pass(Sharded &S, Shard &m, const Step &st, int pass, const Sl
 }
 
 static void exchange_inplace(Sharded &S, const Exchange &x) {
+  NvtxRange nvtx("b200sv exchange (in place)");
   const uint64_t s_ready = ++S.seq[F_READY], s_done = ++S.seq[F_DONE];
   for (int me : S.local) signal(S, me, S.sh[me].st->stream, F_READY, s_ready, group_of(x, me, false));
   for (int me : S.local) {
@@ -612,6 +614,7 @@ static std::vector<int> pick_slab_bits(const Sharded &S, const Exchange &x, cons
 
 static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before, const PassRef &after,
                             const std::vector<int> &slab_bits, int nbuf) {
+  NvtxRange nvtx("b200sv exchange (staged, slab pipeline)");
   const int s = (int)slab_bits.size(), nslab = 1 << s, k = x.k;
   const size_t ab = S.amp_bytes();
   const uint64_t sub = 1ull << (S.nl - s - k);            // amplitudes per (slab, sender) sub-block
@@ -924,7 +927,7 @@ int b200sv_sharded_create(b200sv_sharded_handle *out, int num_qubits, int precis
     for (int r : S->local) {
       Shard &m = S->sh[r];
       B200_CUDA(cudaSetDevice(m.st->device));
-      B200_CUDA(cudaMalloc(&m.aux, kFlagBytes + S->staging_bytes));
+      m.aux = (char *)device_alloc(m.st->device, kFlagBytes + S->staging_bytes, false);
       B200_CUDA(cudaMemset(m.aux, 0, kFlagBytes));
       m.flags = (uint64_t *)m.aux;
       m.staging = m.aux + kFlagBytes;

@@ -1097,6 +1097,7 @@ struct TilePlan {
 };
 
 static void launch_tile_variant(State &s, const TilePassParams &p, TileVariant v, double2 *psi, int grid_cap) {
+  NvtxRange nvtx("b200sv tile pass");
   // function attributes are per device: one flag per device ordinal (a process may drive several GPUs)
   static bool attr_set_dev[64] = {};
   bool &attr_set = attr_set_dev[s.device & 63];

@@ -24,6 +24,8 @@ namespace {
 struct CachedBlock { void *ptr = nullptr; size_t bytes = 0; };
 std::mutex g_cache_mu;
 CachedBlock g_cache[64];
+CachedBlock g_scratch_cache[64];  // a destroyed handle's scratch buffer (reductions, sampler), per device
+CachedBlock g_pinned_cache;       // ... and its pinned host staging (cudaMallocHost / cudaFreeHost are slow and synchronise)
 bool cache_enabled() {
   static const bool on = [] { const char *e = getenv("B200SV_ALLOC_CACHE"); return !(e && e[0] == '0'); }();
   return on;
@@ -33,12 +35,18 @@ void trim_alloc_cache() {
   std::lock_guard<std::mutex> lk(g_cache_mu);
   int cur = 0;
   cudaGetDevice(&cur);
-  for (int d = 0; d < 64; d++)
+  for (int d = 0; d < 64; d++) {
     if (g_cache[d].ptr) {
       cudaSetDevice(d);
       cudaFree(g_cache[d].ptr);
       g_cache[d] = CachedBlock();
     }
+    if (g_scratch_cache[d].ptr) {
+      cudaSetDevice(d);
+      cudaFree(g_scratch_cache[d].ptr);
+      g_scratch_cache[d] = CachedBlock();
+    }
+  }
   cudaSetDevice(cur);
   cudaGetLastError();
 }
@@ -73,7 +81,40 @@ void device_free(int device, void *p, size_t bytes, bool may_cache) {
   cudaFree(p);
 }
 
+// small buffers of destroyed handles, kept for the next handle (one each)
+static void stash_small(State &s) {
+  if (!cache_enabled() || s.device < 0 || s.device >= 64) {
+    if (s.scratch) cudaFree(s.scratch);
+    if (s.pinned) cudaFreeHost(s.pinned);
+    s.scratch = s.pinned = nullptr;
+    return;
+  }
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  if (s.scratch) {
+    CachedBlock &c = g_scratch_cache[s.device];
+    if (c.ptr && c.bytes >= s.scratch_bytes) cudaFree(s.scratch);
+    else { if (c.ptr) cudaFree(c.ptr); c.ptr = s.scratch; c.bytes = s.scratch_bytes; }
+  }
+  if (s.pinned) {
+    CachedBlock &c = g_pinned_cache;
+    if (c.ptr && c.bytes >= s.pinned_bytes) cudaFreeHost(s.pinned);
+    else { if (c.ptr) cudaFreeHost(c.ptr); c.ptr = s.pinned; c.bytes = s.pinned_bytes; }
+  }
+  s.scratch = s.pinned = nullptr;
+  s.scratch_bytes = s.pinned_bytes = 0;
+}
+static bool take_cached(CachedBlock &c, size_t need, void **ptr, size_t *bytes) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  if (!c.ptr || c.bytes < need) return false;
+  *ptr = c.ptr;
+  *bytes = c.bytes;
+  c = CachedBlock();
+  return true;
+}
+
 void *State::ensure_scratch(size_t bytes) {
+  if (bytes > scratch_bytes && !scratch && cache_enabled() && device >= 0 && device < 64)
+    take_cached(g_scratch_cache[device], bytes, &scratch, &scratch_bytes);
   if (bytes > scratch_bytes) {
     if (scratch) {
       B200_CUDA(cudaStreamSynchronize(stream));
@@ -87,6 +128,7 @@ void *State::ensure_scratch(size_t bytes) {
   return scratch;
 }
 void *State::ensure_pinned(size_t bytes) {
+  if (bytes > pinned_bytes && !pinned && cache_enabled()) take_cached(g_pinned_cache, bytes, &pinned, &pinned_bytes);
   if (bytes > pinned_bytes) {
     if (pinned) {
       B200_CUDA(cudaStreamSynchronize(stream));
@@ -308,8 +350,7 @@ int b200sv_destroy(b200sv_handle h) {
     select(H);
     cudaStreamSynchronize(H->stream);
     if (H->owns_data && H->data) device_free(H->device, H->data, H->total_amps() * H->amp_bytes(), true);
-    if (H->scratch) cudaFree(H->scratch);
-    if (H->pinned) cudaFreeHost(H->pinned);
+    stash_small(*H);
     if (H->checkpoint) cudaFree(H->checkpoint);
     if (H->owns_stream && H->stream) cudaStreamDestroy(H->stream);
     delete H;

@@ -152,6 +152,7 @@ struct Sharded {
   bool allow_staged = true;
   bool unstage_dma = false;   // move received slabs into place with the copy engines instead of a kernel
   int push_streams = 4;
+  int max_ride = 2;           // passes per side of an exchange that may run slab-wise under it
   bool profile = false;
   // statistics of the last run
   int64_t stat_passes = 0, stat_exchanges = 0, stat_staged = 0, stat_inplace = 0, stat_launches = 0, stat_copies = 0;
@@ -559,11 +560,14 @@ static std::unique_ptr<Program> compile(Sharded &S, const std::vector<ShOp> &ops
 }
 
 // ------------------------------------------------------------------------------------------ execution
+// `count` passes at the end (last = true: they run before an exchange) or at the start of a tile step, taken along by
+// the exchange next to them and run slab by slab
 struct PassRef {
-  const Step *step = nullptr;  // tile step the pass belongs to (null: none)
-  bool last = false;           // its last pass (before an exchange) or its first (after)
-  int index(int rank) const { return last ? tile_plan_passes(step->plans[rank]) - 1 : 0; }
-  bool valid_for(int rank) const { return step && tile_plan_passes(step->plans[rank]) > 0; }
+  const Step *step = nullptr;  // tile step the passes belong to (null: none)
+  bool last = false;
+  int count = 0;
+  int index(int rank, int j) const { return last ? tile_plan_passes(step->plans[rank]) - count + j : j; }
+  bool valid() const { return step != nullptr && count > 0; }
 };
 
 static void launch_pass(Sharded &S, Shard &m, const Step &st, int pass, const SlabSpec *slab) {
@@ -601,8 +605,8 @@ static std::vector<int> pick_slab_bits(const Sharded &S, const Exchange &x, cons
   uint64_t used = 0;
   for (int i = 0; i < x.k; i++) used |= 1ull << x.lpos[i];
   for (int r = 0; r < S.world; r++) {
-    if (before.valid_for(r)) used |= tile_plan_pass_mask(before.step->plans[r], before.index(r));
-    if (after.valid_for(r)) used |= tile_plan_pass_mask(after.step->plans[r], after.index(r));
+    for (int j = 0; before.valid() && j < before.count; j++) used |= tile_plan_pass_mask(before.step->plans[r], before.index(r, j));
+    for (int j = 0; after.valid() && j < after.count; j++) used |= tile_plan_pass_mask(after.step->plans[r], after.index(r, j));
   }
   std::vector<int> bits;
   const int lo = std::min(S.min_run_bits, std::max(S.nl - 1, 1));
@@ -637,10 +641,10 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
   for (int i = 0; i < nslab; i++)
     for (int me : S.local) {
       Shard &m = S.sh[me];
-      if (before.valid_for(me)) {
+      for (int j = 0; before.valid() && j < before.count; j++) {
         spec.value = (uint32_t)i;
         ProfScope ps(S, m, m.st->stream, PR_SLAB_PASS);
-        launch_pass(S, m, *before.step, before.index(me), s ? &spec : nullptr);
+        launch_pass(S, m, *before.step, before.index(me, j), s ? &spec : nullptr);
         if (i == 0) S.stat_overlapped_passes++;
       }
       sel(m);
@@ -714,10 +718,10 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
         // to every shard: the next exchange may pair this shard with different partners
         signal(S, me, m.st->stream, F_UNSTAGED, c0_unstaged + i + 1, all_others(S, me));
       }
-      if (after.valid_for(me)) {
+      for (int j = 0; after.valid() && j < after.count; j++) {
         spec.value = (uint32_t)i;
         ProfScope ps(S, m, m.st->stream, PR_SLAB_PASS);
-        launch_pass(S, m, *after.step, after.index(me), s ? &spec : nullptr);
+        launch_pass(S, m, *after.step, after.index(me, j), s ? &spec : nullptr);
         if (i == 0) S.stat_overlapped_passes++;
       }
     }
@@ -730,12 +734,13 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
 // How each exchange of a program runs -- decided from the plans of ALL ranks and the handle's configuration only, so
 // that every process of a multi-process register takes the same decisions.
 struct XSched {
-  bool staged = false, use_before = false, use_after = false;
+  bool staged = false;
+  int n_before = 0, n_after = 0;   // passes of the neighbouring tile steps that ride along, slab by slab
   std::vector<int> slab_bits;
   int nbuf = 1;
 };
-static std::vector<XSched> schedule(const Sharded &S, const Program &prog, std::vector<char> &first_taken,
-                                    std::vector<char> &last_taken) {
+static std::vector<XSched> schedule(const Sharded &S, const Program &prog, std::vector<int> &first_taken,
+                                    std::vector<int> &last_taken) {
   const size_t ns = prog.steps.size();
   std::vector<XSched> xs(ns);
   first_taken.assign(ns, 0);
@@ -749,43 +754,56 @@ static std::vector<XSched> schedule(const Sharded &S, const Program &prog, std::
     for (int i = 0; i < x.k; i++)
       if (x.lpos[i] == 0) d.staged = false;  // runs of one amplitude: not a DMA shape
     if (!d.staged) continue;
-    PassRef before, after;
+    // how many passes are there to take along on either side (identical decision on every rank: all plans are known)
+    int avail_before = 0, avail_after = 0;
     if (si > 0 && prog.steps[si - 1].type == 0) {
-      before.step = &prog.steps[si - 1];
-      before.last = true;
+      avail_before = 1 << 30;
       for (int r = 0; r < S.world; r++)
-        if (tile_plan_passes(before.step->plans[r]) - (first_taken[si - 1] ? 1 : 0) < 1) before.step = nullptr;
+        avail_before = std::min(avail_before, tile_plan_passes(prog.steps[si - 1].plans[r]) - first_taken[si - 1]);
     }
     if (si + 1 < ns && prog.steps[si + 1].type == 0) {
-      after.step = &prog.steps[si + 1];
       const bool next_next_x = si + 2 < ns && prog.steps[si + 2].type == 2;
-      for (int r = 0; r < S.world && after.step; r++) {
-        const int np = tile_plan_passes(after.step->plans[r]);
-        if (np < 1 || (next_next_x && np < 2)) after.step = nullptr;  // keep a pass for the next exchange's "before"
-      }
+      avail_after = 1 << 30;
+      for (int r = 0; r < S.world; r++)  // keep one pass for the next exchange's "before" side
+        avail_after = std::min(avail_after, tile_plan_passes(prog.steps[si + 1].plans[r]) - (next_next_x ? 1 : 0));
     }
+    avail_before = std::max(0, std::min(avail_before, S.max_ride));
+    avail_after = std::max(0, std::min(avail_after, S.max_ride));
     const double out_bytes = (double)(1ull << S.nl) * S.amp_bytes() * (1.0 - 1.0 / (1 << x.k));
-    // finest pipeline the free index bits allow; it must fit the staging area
-    d.slab_bits = pick_slab_bits(S, x, before, after, (before.step || after.step) ? S.want_slab_bits : 0);
-    const int sb = (int)d.slab_bits.size();
-    if (out_bytes / (double)(1u << sb) > (double)S.staging_bytes) {
-      // not even the finest slabs fit: try without the neighbouring passes (more free bits), else in place
-      d.slab_bits = pick_slab_bits(S, x, PassRef(), PassRef(), 4);
-      before.step = after.step = nullptr;
-      if (out_bytes / (double)(1u << d.slab_bits.size()) > (double)S.staging_bytes) { d.staged = false; continue; }
+    auto fits = [&](size_t nbits) { return out_bytes / (double)(1u << nbits) <= (double)S.staging_bytes; };
+    // widest overlap window first; a window needs at least two slabs to be worth its slab launches
+    bool chosen = false;
+    for (int total = avail_before + avail_after; total >= 1 && !chosen; total--)
+      for (int nb = std::min(avail_before, total); nb >= 0 && !chosen; nb--) {
+        const int na = total - nb;
+        if (na > avail_after || na < 0) continue;
+        PassRef before, after;
+        if (nb) { before.step = &prog.steps[si - 1]; before.last = true; before.count = nb; }
+        if (na) { after.step = &prog.steps[si + 1]; after.last = false; after.count = na; }
+        std::vector<int> bits = pick_slab_bits(S, x, before, after, S.want_slab_bits);
+        const size_t need_bits = total >= 3 ? 2 : 1;
+        if (bits.size() < need_bits || !fits(bits.size())) continue;
+        d.slab_bits = bits;
+        d.n_before = nb;
+        d.n_after = na;
+        chosen = true;
+      }
+    if (!chosen) {
+      // nothing rides along: pipeline pushes against unstages only, with as many slabs as the staging area needs
+      d.slab_bits = pick_slab_bits(S, x, PassRef(), PassRef(), 0);
+      if (!fits(0)) d.slab_bits = pick_slab_bits(S, x, PassRef(), PassRef(), 4);
+      if (!fits(d.slab_bits.size())) { d.staged = false; continue; }
     }
     d.nbuf = (2.0 * out_bytes / (double)(1u << d.slab_bits.size()) <= (double)S.staging_bytes) ? 2 : 1;
-    d.use_before = before.step != nullptr;
-    d.use_after = after.step != nullptr;
-    if (d.use_before) last_taken[si - 1] = 1;
-    if (d.use_after) first_taken[si + 1] = 1;
+    if (d.n_before) last_taken[si - 1] = d.n_before;
+    if (d.n_after) first_taken[si + 1] = d.n_after;
   }
   return xs;
 }
 
 static void run_program(Sharded &S, const Program &prog, const std::vector<ShOp> &ops) {
   const size_t ns = prog.steps.size();
-  std::vector<char> first_taken, last_taken;  // tile steps whose first / last pass rides an exchange
+  std::vector<int> first_taken, last_taken;  // tile steps: how many of their first / last passes ride an exchange
   const std::vector<XSched> xs = schedule(S, prog, first_taken, last_taken);
   for (size_t si = 0; si < ns; si++) {
     const Step &st = prog.steps[si];
@@ -796,7 +814,7 @@ static void run_program(Sharded &S, const Program &prog, const std::vector<ShOp>
     if (st.type == 0) {
       for (int me : S.local) {
         const int np = tile_plan_passes(st.plans[me]);
-        for (int p = first_taken[si] ? 1 : 0; p < (last_taken[si] ? np - 1 : np); p++) {
+        for (int p = first_taken[si]; p < np - last_taken[si]; p++) {
           ProfScope ps(S, S.sh[me], S.sh[me].st->stream, PR_PASS);
           launch_pass(S, S.sh[me], st, p, nullptr);
         }
@@ -811,8 +829,8 @@ static void run_program(Sharded &S, const Program &prog, const std::vector<ShOp>
     Shard &first = S.sh[S.local[0]];
     if (d.staged) {
       PassRef before, after;
-      if (d.use_before) { before.step = &prog.steps[si - 1]; before.last = true; }
-      if (d.use_after) { after.step = &prog.steps[si + 1]; after.last = false; }
+      if (d.n_before) { before.step = &prog.steps[si - 1]; before.last = true; before.count = d.n_before; }
+      if (d.n_after) { after.step = &prog.steps[si + 1]; after.last = false; after.count = d.n_after; }
       ProfScope ps(S, first, first.st->stream, PR_REGION);
       exchange_staged(S, x, before, after, d.slab_bits, d.nbuf);
     } else {
@@ -890,6 +908,7 @@ int b200sv_sharded_create(b200sv_sharded_handle *out, int num_qubits, int precis
     if (const char *e = getenv("B200SV_SHARD_SLAB_BITS")) S->want_slab_bits = std::max(0, std::min(4, atoi(e)));
     if (const char *e = getenv("B200SV_SHARD_STAGED")) S->allow_staged = atoi(e) != 0;
     if (const char *e = getenv("B200SV_SHARD_UNSTAGE")) S->unstage_dma = !strcmp(e, "dma");
+    if (const char *e = getenv("B200SV_SHARD_MAX_RIDE")) S->max_ride = std::max(0, std::min(4, atoi(e)));
     if (const char *e = getenv("B200SV_SHARD_PUSH_STREAMS")) S->push_streams = std::max(1, std::min(8, atoi(e)));
     S->min_run_bits = std::max(1, std::min(S->min_run_bits, std::max(S->nl - 1, 1)));
     const size_t slice_bytes = ((size_t)1 << S->nl) * S->amp_bytes();
@@ -1091,11 +1110,12 @@ int b200sv_sharded_plan_only(int num_qubits, int precision, int world, uint64_t 
     if (const char *e = getenv("B200SV_SHARD_MIN_RUN_BITS")) S.min_run_bits = atoi(e);
     if (const char *e = getenv("B200SV_SHARD_SLAB_BITS")) S.want_slab_bits = std::max(0, std::min(4, atoi(e)));
     if (const char *e = getenv("B200SV_SHARD_STAGED")) S.allow_staged = atoi(e) != 0;
+    if (const char *e = getenv("B200SV_SHARD_MAX_RIDE")) S.max_ride = std::max(0, std::min(4, atoi(e)));
     S.min_run_bits = std::max(1, std::min(S.min_run_bits, std::max(S.nl - 1, 1)));
     S.staging_bytes = world > 1 ? (size_t)staging_bytes : 0;
     std::vector<ShOp> ops = parse_ops(num_qubits, nops, kinds, op_off, op_qubits, data_off, data);
     std::unique_ptr<Program> prog = compile(S, ops);
-    std::vector<char> ft, lt;
+    std::vector<int> ft, lt;
     const std::vector<XSched> xs = schedule(S, *prog, ft, lt);
     double passes = 0, nx = 0, staged = 0, inplace = 0, taken = 0, fine = 0, coarse = 1e9, swaps = 0;
     for (size_t si = 0; si < prog->steps.size(); si++) {
@@ -1106,7 +1126,7 @@ int b200sv_sharded_plan_only(int num_qubits, int precision, int world, uint64_t 
       swaps += st.x.k;
       if (xs[si].staged) {
         staged++;
-        taken += (xs[si].use_before ? 1 : 0) + (xs[si].use_after ? 1 : 0);
+        taken += xs[si].n_before + xs[si].n_after;
         fine = std::max(fine, (double)(1u << xs[si].slab_bits.size()));
         coarse = std::min(coarse, (double)(1u << xs[si].slab_bits.size()));
       } else inplace++;

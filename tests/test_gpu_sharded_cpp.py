@@ -34,7 +34,7 @@ def _devices(world):
 def _make(n, world, staging, env=None, dtype=np.complex128):
     from qiskit_aer_b200 import sharded
     keys = ("B200SV_SHARD_MIN_RUN_BITS", "B200SV_SHARD_SLAB_BITS", "B200SV_SHARD_STAGED", "B200SV_SHARD_UNSTAGE",
-            "B200SV_SHARD_PUSH_STREAMS")
+            "B200SV_SHARD_PUSH_STREAMS", "B200SV_SHARD_MAX_RIDE")
     saved = {k: os.environ.get(k) for k in keys}
     for k in keys:
         os.environ.pop(k, None)
@@ -80,6 +80,20 @@ def test_qv_staged_pipelined_exchange(world, unstage, streams):
     stats = _check(st, n, ops)
     assert stats["exchanges"] > 0 and stats["staged"] == stats["exchanges"] and stats["inplace"] == 0
     assert stats["overlapped_passes"] > 0 and stats["copies"] > 0
+    st.close()
+
+
+@pytest.mark.parametrize("ride", [0, 1, 3])
+def test_overlap_window_sizes(ride):
+    """0, 1 or up to 3 passes on either side of an exchange run slab-wise under it."""
+    from qiskit_aer_b200 import circuits
+    n, world = 19, 4
+    ops = circuits.quantum_volume(n, 8, seed=50 + ride)
+    st = _make(n, world, staging=1 << 22, env={"B200SV_SHARD_MIN_RUN_BITS": "5", "B200SV_SHARD_SLAB_BITS": "2",
+                                               "B200SV_SHARD_MAX_RIDE": str(ride)})
+    stats = _check(st, n, ops, seed=21)
+    assert stats["staged"] == stats["exchanges"] > 0
+    assert (stats["overlapped_passes"] == 0) == (ride == 0)
     st.close()
 
 

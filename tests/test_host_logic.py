@@ -185,10 +185,10 @@ def test_sharded_plan_only_counts():
     ops = circuits.quantum_volume(36, 10, seed=1234)
     big = sharded.ShardedState.plan_only(36, 8, ops, 34 << 30)
     assert big["exchanges"] == 3 and big["qubit_swaps"] == 9 and big["staged"] == 3 and big["inplace"] == 0
-    assert big["passes"] <= 23 and big["passes_overlapped"] == 6 and big["slabs_min"] >= 4
+    assert big["passes"] <= 23 and big["passes_overlapped"] >= 6 and big["slabs_min"] >= 4
     # 112 GiB leave a shard per exchange: a 20 GiB staging area still pipelines (8 slabs, one buffer) ...
     mid = sharded.ShardedState.plan_only(36, 8, ops, 20 << 30)
-    assert mid["staged"] == 3 and mid["slabs_min"] == 8
+    assert mid["staged"] == 3 and mid["slabs_min"] >= 8
     # ... a 1 GiB one does not: in-place peer swaps
     small = sharded.ShardedState.plan_only(36, 8, ops, 1 << 30)
     assert small["staged"] == 0 and small["inplace"] == 3

@@ -822,16 +822,19 @@ struct MultiSwapParams {
 };
 template <typename T>
 __global__ void __launch_bounds__(256) multi_swap_kernel(cx<T> *__restrict__ mine, const __grid_constant__ MultiSwapParams p) {
-  const uint32_t l = p.lvals[blockIdx.y];
+  // classes (= partner shards) are interleaved over consecutive CTAs, so that all partners are served at the same
+  // rate from the first wave on (one class after the other would aim every shard at the same partner first)
+  const uint32_t ncls = (uint32_t)p.nl_classes;
+  const uint32_t l = p.lvals[blockIdx.x % ncls];
   uint64_t lmask = 0, gmask = 0;
   for (int b = 0; b < p.k; b++) {
     if ((l >> b) & 1) lmask |= 1ull << p.lq[b];
     if ((p.my_g >> b) & 1) gmask |= 1ull << p.lq[b];
   }
   cx<T> *peer = (cx<T> *)p.peer[l];
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t stride = (uint64_t)(gridDim.x / ncls) * blockDim.x;
   constexpr int U = 4;  // remote loads in flight per thread (NVLink latency ~2 us)
-  for (uint64_t j0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j0 < p.count; j0 += stride * U) {
+  for (uint64_t j0 = (uint64_t)(blockIdx.x / ncls) * blockDim.x + threadIdx.x; j0 < p.count; j0 += stride * U) {
     cx<T> a[U], b[U];
     uint64_t base[U];
 #pragma unroll
@@ -867,7 +870,7 @@ void launch_multi_swap_peer(State &s, int k, const int *local_q, uint32_t my_g, 
   }
   if (p.nl_classes == 0) return;
   int gx = (int)std::min<uint64_t>((p.count + 255) / 256, std::max<uint64_t>(1, (uint64_t)s.num_sms * 16 / p.nl_classes));
-  dim3 grid(std::max(gx, 1), p.nl_classes);
+  const unsigned grid = (unsigned)std::max(gx, 1) * (unsigned)p.nl_classes;
   if (s.precision == B200SV_F64) multi_swap_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, p);
   else multi_swap_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, p);
   B200_CUDA(cudaGetLastError());

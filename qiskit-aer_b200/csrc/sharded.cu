@@ -637,8 +637,13 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
   SlabSpec spec;
   spec.nbits = s;
   for (int b = 0; b < s; b++) spec.pos[b] = slab_bits[b];
-  // 1. the pass before the exchange, slab by slab; each slab's completion is handed to the copy stream
-  for (int i = 0; i < nslab; i++)
+  const uint64_t c0_pushed = S.seq[F_PUSHED], c0_unstaged = S.seq[F_UNSTAGED];
+  // Software pipeline over the slabs, `nbuf` slabs ahead on the sending side (the staging area holds nbuf slabs):
+  //   compute stream:  before(0) .. before(nbuf-1) | before(i+nbuf), unstage(i), after(i)   for i = 0, 1, ...
+  //   copy streams:    push(s) after before(s) and after the receivers have unstaged slab s - nbuf
+  // so the compute stream always has work that does not depend on the link (the "before" passes of a later slab)
+  // while slab i is still in flight.
+  auto issue_before = [&](int i) {  // the passes before the exchange on slab i; completion handed to the copy stream
     for (int me : S.local) {
       Shard &m = S.sh[me];
       for (int j = 0; before.valid() && j < before.count; j++) {
@@ -650,10 +655,9 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
       sel(m);
       B200_CUDA(cudaEventRecord(m.ev_pass[i % kEvRing], m.st->stream));
     }
-  const uint64_t c0_pushed = S.seq[F_PUSHED], c0_unstaged = S.seq[F_UNSTAGED];
-  for (int i = 0; i < nslab; i++) {
+  };
+  auto issue_push = [&](int i) {    // pushes of slab i (copy engines), once the receivers' buffer is free again
     const int b = i % nbuf;
-    // 2. pushes of slab i (copy engines), once the receivers' buffer b is free again
     for (int me : S.local) {
       Shard &m = S.sh[me];
       sel(m);
@@ -664,8 +668,9 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
       ProfScope ps_push(S, m, m.xs, PR_PUSH);
       B200_CUDA(cudaEventRecord(m.ev_fork, m.xs));
       for (int j = 0; j < S.push_streams; j++) B200_CUDA(cudaStreamWaitEvent(m.px[j], m.ev_fork, 0));
-      for (uint32_t v = 0; v < (1u << k); v++) {
-        if (v == my_g) continue;
+      // receivers in XOR order: at step d every shard g sends to g ^ d, a perfect matching
+      for (uint32_t dstep = 1; dstep < (1u << k); dstep++) {
+        const uint32_t v = my_g ^ dstep;
         const Shard &peer = S.sh[peer_of(x, me, v)];
         if (!peer.staging) throw Error("sharded: shard " + std::to_string(peer.rank) + " is not attached");
         const uint32_t slot = my_g < v ? my_g : my_g - 1;  // the receiver (id v) skips its own id
@@ -678,7 +683,9 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
       ps_push.end();
       signal(S, me, m.xs, F_PUSHED, c0_pushed + i + 1, group_of(x, me, true));
     }
-    // 3. unstage slab i and run the pass after the exchange on it
+  };
+  auto issue_unstage_after = [&](int i) {  // move slab i into place, then the passes after the exchange on it
+    const int b = i % nbuf;
     for (int me : S.local) {
       Shard &m = S.sh[me];
       sel(m);
@@ -725,6 +732,12 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
         if (i == 0) S.stat_overlapped_passes++;
       }
     }
+  };
+  for (int i = 0; i < std::min(nbuf, nslab); i++) { issue_before(i); issue_push(i); }
+  for (int i = 0; i < nslab; i++) {
+    if (i + nbuf < nslab) issue_before(i + nbuf);
+    issue_unstage_after(i);
+    if (i + nbuf < nslab) issue_push(i + nbuf);
   }
   S.seq[F_PUSHED] = c0_pushed + nslab;
   S.seq[F_UNSTAGED] = c0_unstaged + nslab;

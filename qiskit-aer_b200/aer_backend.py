@@ -52,10 +52,10 @@ def load():
 
 
 def build_circuit(cw, n, ops, shots, seed, expvals=(), save_statevector=False, measure=True, save_probs=None,
-                  save_density_matrix=False, expval_subtype="average"):
+                  save_density_matrix=False, expval_subtype="average", num_memory=None):
     c = cw.AerCircuit()
     c.num_qubits = n
-    c.num_memory = n if (shots and measure) else 0
+    c.num_memory = int(num_memory) if num_memory is not None else (n if (shots and measure) else 0)
     c.shots = max(shots, 1)
     c.seed = seed
     for op in ops:

@@ -196,6 +196,12 @@ int b200sv_fuse_block_matrix(int k, const int *block_qubits, int ngates, const i
  * own modulus", for measurements of every qubit).  One launch for all states. */
 int b200sv_collapse(b200sv_handle h, const uint64_t *qubits, int k, const uint64_t *outcomes, const double *scales,
                     const uint8_t *active);
+/* Per-state matrices in ONE launch: state s applies the column-major 2^k x 2^k matrix mats[index[s]] times scale[s]
+ * (index[s] < 0: state s is left alone).  Batched Kraus channels (apply_batched_kraus + MatrixMultNxN_conditional,
+ * qubitvector_thrust.hpp:2996-3177: index = the operator each shot's draw selected, scale = 1/sqrt(p)) and
+ * per-parameter matrices of bound circuits (apply_batched_matrix, :1578-1611). */
+int b200sv_apply_batched_matrix(b200sv_handle h, const uint64_t *qubits, int k, const double *mats, int nmats,
+                                const int *index, const double *scale);
 /* A handle onto states [first_state, first_state + num_states) of a batched container, sharing its memory
  * and stream (per-shot fallbacks of the batched executor, batch_shots_executor.hpp:594-603; per-parameter
  * matrices, apply_batched_matrix qubitvector_thrust.hpp:1578-1611).  Destroy it before the parent. */

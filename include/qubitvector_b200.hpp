@@ -619,12 +619,18 @@ public:
     const size_t S = batch_->nstates;
     std::vector<uint8_t> active = take_conditional();
     batch_->queue.flush(batch_->h);
-    std::vector<double> r(S), accum(S, 0.0), p(S);
+    std::vector<double> r(S), accum(S, 0.0), p(S), scale(S, 1.0);
     std::vector<int> chosen(S, -1);
     for (size_t s = 0; s < S; s++) r[s] = rng[s].rand(0., 1.);
+    const size_t msz = (size_t)1 << (2 * qubits.size());
+    cvector_t<double> table(msz * kmats.size());
     for (size_t j = 0; j < kmats.size(); j++) {
       cvector_t<double> vmat = Utils::vectorize_matrix(kmats[j]);
+      std::copy(vmat.begin(), vmat.end(), table.begin() + j * msz);
       const bool last = j + 1 == kmats.size();
+      bool undecided = false;
+      for (size_t s = 0; s < S && !undecided; s++) undecided = active[s] && chosen[s] < 0;
+      if (!undecided) continue;  // every shot has its operator: no need to evaluate the remaining probabilities
       if (!last) ck(b200sv_norm_matrix(batch_->h, qubits.data(), (int)qubits.size(), (const double *)vmat.data(), p.data()));
       for (size_t s = 0; s < S; s++) {
         if (!active[s] || chosen[s] >= 0) continue;
@@ -632,27 +638,28 @@ public:
         accum[s] += pj;
         if (last || accum[s] > r[s]) {
           chosen[s] = (int)j;
-          const double renorm = 1.0 / std::sqrt(pj);
-          cvector_t<double> scaled = vmat;
-          for (auto &x : scaled) x *= renorm;
-          ck(b200sv_apply_matrix(state_view(s), qubits.data(), (int)qubits.size(), (const double *)scaled.data()));
+          scale[s] = 1.0 / std::sqrt(pj);
         }
       }
     }
+    // one launch: every shot applies the operator its draw selected, renormalised
+    ck(b200sv_apply_batched_matrix(batch_->h, qubits.data(), (int)qubits.size(), (const double *)table.data(),
+                                   (int)kmats.size(), chosen.data(), scale.data()));
   }
   // per-parameter matrices (runtime parameter binding): apply_batched_matrix (qubitvector_thrust.hpp:1578-1611)
   void apply_batched_matrix(const reg_t &qubits, const cvector_t<double> &mat, const uint_t num_matrices,
                             const uint_t num_shots_per_matrix) {
     if (!batch_ || idle()) return;
     batch_->queue.flush(batch_->h);
-    const size_t msize = 1ull << (2 * qubits.size());
-    for (uint_t m = 0; m < num_matrices; m++) {
-      b200sv_handle v = nullptr;
-      ck(b200sv_create_view(&v, batch_->h, (int64_t)(m * num_shots_per_matrix), (int64_t)num_shots_per_matrix));
-      const int rc = b200sv_apply_matrix(v, qubits.data(), (int)qubits.size(), (const double *)(mat.data() + m * msize));
-      b200sv_destroy(v);
-      ck(rc);
+    const size_t S = batch_->nstates;
+    std::vector<int> index(S, -1);
+    std::vector<double> scale(S, 1.0);
+    for (size_t s = 0; s < S; s++) {
+      const uint_t m = s / num_shots_per_matrix;
+      if (m < num_matrices) index[s] = (int)m;
     }
+    ck(b200sv_apply_batched_matrix(batch_->h, qubits.data(), (int)qubits.size(), (const double *)mat.data(),
+                                   (int)num_matrices, index.data(), scale.data()));
   }
   void apply_batched_diagonal_matrix(const reg_t &qubits, const cvector_t<double> &mat, const uint_t num_matrices,
                                      const uint_t num_shots_per_matrix) {

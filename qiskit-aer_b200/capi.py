@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200sv_selftest_op_sequence": [C.c_int, C.c_int64, C.c_int, _vp, C.c_int, C.POINTER(C.c_int), _u64p, _f64p,
                                     C.POINTER(C.c_int), C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int)],
     "b200sv_collapse": [_vp, _u64p, C.c_int, _u64p, _f64p, C.POINTER(C.c_uint8)],
+    "b200sv_apply_batched_matrix": [_vp, _u64p, C.c_int, _f64p, C.c_int, C.POINTER(C.c_int), _f64p],
     "b200sv_create_view": [C.POINTER(_vp), _vp, C.c_int64, C.c_int64],
     "b200sv_norm": [_vp, _f64p],
     "b200sv_norm_matrix": [_vp, _u64p, C.c_int, _f64p, _f64p],

@@ -720,6 +720,35 @@ int b200sv_collapse(b200sv_handle h, const uint64_t *qubits, int k, const uint64
   });
 }
 
+int b200sv_apply_batched_matrix(b200sv_handle h, const uint64_t *qubits, int k, const double *mats, int nmats,
+                                const int *index, const double *scale) {
+  return guard([&] {
+    select(H);
+    auto q = checked_qubits(*H, qubits, k);
+    if (!mats || !index || !scale || nmats < 1) throw Error("apply_batched_matrix: bad arguments");
+    for (int64_t st = 0; st < H->nstates; st++)
+      if (index[st] >= nmats) throw Error("apply_batched_matrix: matrix index out of range");
+    if (k >= 1 && k <= 3) {
+      for_state_slabs(H, [&](State &v, int64_t s0) { launch_batched_matrix(v, q.data(), k, mats, nmats, index + s0, scale + s0); });
+      return;
+    }
+    // wider blocks: one launch per state through a view (rare: Kraus channels act on 1-2 qubits)
+    const size_t msz = (size_t)2 << (2 * k);
+    std::vector<double> scaled(msz);
+    for (int64_t st = 0; st < H->nstates; st++) {
+      if (index[st] < 0) continue;
+      State v = *H;
+      v.nstates = 1;
+      v.data = (char *)H->data + ((uint64_t)st << H->nq) * H->amp_bytes();
+      v.owns_data = false;
+      for (size_t i = 0; i < msz; i++) scaled[i] = mats[(size_t)index[st] * msz + i] * scale[st];
+      if (k <= kMaxRegQubits) launch_dense(v, q.data(), k, nullptr, 0, scaled.data());
+      else launch_dense_generic(v, q.data(), k, scaled.data());
+      H->scratch = v.scratch; H->scratch_bytes = v.scratch_bytes; H->pinned = v.pinned; H->pinned_bytes = v.pinned_bytes;
+    }
+  });
+}
+
 int b200sv_create_view(b200sv_handle *out, b200sv_handle parent, int64_t first_state, int64_t num_states) {
   return guard([&] {
     State *P = (State *)parent;

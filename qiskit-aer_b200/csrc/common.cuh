@@ -138,6 +138,8 @@ void launch_pauli(State &s, uint64_t x_mask, uint64_t z_mask, int x_max, double 
 void launch_batched_pauli(State &s, const uint64_t *masks4_host);
 void launch_collapse(State &s, const int *qubits, int k, const uint64_t *outcomes, const double *scales,
                      const uint8_t *active);
+void launch_batched_matrix(State &s, const int *qubits, int k, const double *mats, int nmats, const int *index,
+                           const double *scale);
 void launch_gather_line(State &s, int row_bits, uint64_t xor_mask, void *host_out);
 void launch_init(State &s, bool ket0);
 void launch_init_component(State &s, const int *qubits, int k, const double *state);

@@ -622,6 +622,88 @@ void launch_collapse(State &s, const int *qubits, int k, const uint64_t *outcome
   B200_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------ per-state matrices in one launch
+// State s of a batched container applies matrix index[s] of a table (or nothing when index[s] < 0), multiplied by
+// scale[s].  One launch for all shots replaces the reference's conditional-kernel loops: batched Kraus
+// (MatrixMultNxN_conditional + apply_batched_kraus, qubitvector_thrust.hpp:2996-3177: every shot applies the Kraus
+// operator its random draw selected, renormalised by 1/sqrt(p)) and per-parameter matrices of a bound circuit
+// (apply_batched_matrix, :1578-1611).  K <= 3; the table (<= a few KiB) is read through L1/L2.
+struct BatchedMatParams {
+  uint64_t off[8];
+  InsertList ins;
+  uint64_t groups_per_state;
+  int nq;
+};
+template <typename T, int K>
+__global__ void __launch_bounds__(256)
+batched_matrix_kernel(cx<T> *__restrict__ psi, const double2 *__restrict__ table, const int *__restrict__ index,
+                      const double *__restrict__ scale, const __grid_constant__ BatchedMatParams p) {
+  constexpr int DIM = 1 << K;
+  const uint64_t st = blockIdx.y;
+  const int mi = index[st];
+  if (mi < 0) return;
+  const double sc = scale[st];
+  const double2 *m = table + (size_t)mi * DIM * DIM;  // column major like apply_matrix: m[i + DIM * j]
+  cx<T> *base_ptr = psi + (st << p.nq);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.groups_per_state; g += stride) {
+    const uint64_t base = insert_zeros(g, p.ins);
+    cx<T> in[DIM];
+#pragma unroll
+    for (int e = 0; e < DIM; e++) in[e] = base_ptr[base + p.off[e]];
+#pragma unroll
+    for (int i = 0; i < DIM; i++) {
+      cx<T> acc = mk<T>(0, 0);
+#pragma unroll
+      for (int j = 0; j < DIM; j++) {
+        const double2 e = m[i + DIM * j];
+        cfma(acc, mk<T>((T)(e.x * sc), (T)(e.y * sc)), in[j]);
+      }
+      base_ptr[base + p.off[i]] = acc;
+    }
+  }
+}
+void launch_batched_matrix(State &s, const int *qubits, int k, const double *mats, int nmats, const int *index,
+                           const double *scale) {
+  if (k < 1 || k > 3) throw Error("batched matrix: 1..3 qubits");
+  if (s.nstates > 65535) throw Error("batched matrix: more than 65535 states per container");
+  const size_t S = (size_t)s.nstates, msz = ((size_t)1 << (2 * k)) * 16 * (size_t)nmats;
+  const size_t b_idx = (msz + 15) & ~(size_t)15, b_sc = b_idx + ((S * 4 + 15) & ~(size_t)15), total = b_sc + S * 8;
+  char *hm = (char *)s.ensure_pinned(total);
+  char *dm = (char *)s.ensure_scratch(total);
+  B200_CUDA(cudaStreamSynchronize(s.stream));
+  memcpy(hm, mats, msz);
+  memcpy(hm + b_idx, index, S * 4);
+  memcpy(hm + b_sc, scale, S * 8);
+  B200_CUDA(cudaMemcpyAsync(dm, hm, total, cudaMemcpyHostToDevice, s.stream));
+  BatchedMatParams p;
+  p.nq = s.nq;
+  std::vector<int> sorted(qubits, qubits + k);
+  for (int e = 0; e < (1 << k); e++) {
+    uint64_t o = 0;
+    for (int b = 0; b < k; b++)
+      if ((e >> b) & 1) o |= 1ull << qubits[b];
+    p.off[e] = o;
+  }
+  std::sort(sorted.begin(), sorted.end());
+  p.ins.n = k;
+  for (int i = 0; i < k; i++) p.ins.pos[i] = (uint8_t)sorted[i];
+  p.groups_per_state = s.amps_per_state() >> k;
+  int gx = (int)std::min<uint64_t>((p.groups_per_state + 255) / 256, std::max<uint64_t>(1, (uint64_t)s.num_sms * 16 / S));
+  dim3 grid(std::max(gx, 1), (unsigned)S);
+  const double2 *tb = (const double2 *)dm;
+  const int *ix = (const int *)(dm + b_idx);
+  const double *sc = (const double *)(dm + b_sc);
+#define BM(K)                                                                                                     \
+  case K:                                                                                                         \
+    if (s.precision == B200SV_F64) batched_matrix_kernel<double, K><<<grid, 256, 0, s.stream>>>((double2 *)s.data, tb, ix, sc, p); \
+    else batched_matrix_kernel<float, K><<<grid, 256, 0, s.stream>>>((float2 *)s.data, tb, ix, sc, p);             \
+    break;
+  switch (k) { BM(1) BM(2) BM(3) }
+#undef BM
+  B200_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------ density-matrix line gather
 template <typename T>
 __global__ void __launch_bounds__(256) gather_line_kernel(const cx<T> *__restrict__ psi, cx<T> *__restrict__ out,

@@ -229,6 +229,19 @@ class QubitVectorB200:
             raise ValueError("need 4 words per state")
         capi.check(self._lib.b200sv_apply_batched_pauli(self.h, a.ctypes.data_as(_u64p)))
 
+    def apply_batched_matrix(self, qubits, mats, index, scale=None):
+        """State s applies the column-major matrix mats[index[s]] * scale[s] (index < 0: untouched) -- one launch
+        (batched Kraus / per-parameter matrices, qubitvector_thrust.hpp:1578-1611,2996-3177)."""
+        qa, qp, k = _q(qubits)
+        m = np.ascontiguousarray(np.asarray(mats, dtype=np.complex128).reshape(-1))
+        nm = m.size >> (2 * k)
+        ix = np.ascontiguousarray(index, dtype=np.int32)
+        sc = np.ascontiguousarray(np.ones(self.num_states) if scale is None else scale, dtype=np.float64)
+        if ix.size != self.num_states or sc.size != self.num_states:
+            raise ValueError("need one index / scale per state")
+        capi.check(self._lib.b200sv_apply_batched_matrix(self.h, qp, k, m.ctypes.data_as(_f64p), int(nm),
+                                                         ix.ctypes.data_as(C.POINTER(C.c_int)), sc.ctypes.data_as(_f64p)))
+
     # ---- reductions ----------------------------------------------------------
     def _ret(self, out):
         return float(out[0]) if self.num_states == 1 else out

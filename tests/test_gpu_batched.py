@@ -108,3 +108,46 @@ def test_reference_noisy_per_shot_path_on_b200_vector():
     cpu = aer_backend.run_circuit(n, ops, device="CPU", **kw)
     assert gpu["metadata"]["device"] == "GPU"
     assert gpu["data"]["counts"] == cpu["data"]["counts"]
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.complex128, 1e-12), (np.complex64, 5e-6)])
+@pytest.mark.parametrize("k", [1, 2, 3, 4])
+def test_per_state_matrices_in_one_launch(dtype, tol, k):
+    """b200sv_apply_batched_matrix: every state applies its own (scaled) matrix of a table, or none."""
+    import qiskit_aer_b200 as q
+    n, S, nm = 7, 37, 5
+    rng = np.random.default_rng(40 + k)
+    mats = [opgen.colmajor(opgen.haar_unitary(rng, 1 << k) * rng.uniform(0.5, 1.5)) for _ in range(nm)]
+    index = rng.integers(-1, nm, size=S)
+    scale = rng.uniform(0.5, 2.0, size=S)
+    qubits = opgen.pick(rng, n, k)
+    gpu = q.QubitVectorB200(n, dtype, num_states=S)
+    states = [opgen.random_state(rng, n, dtype) for _ in range(S)]
+    gpu.set_state(np.concatenate(states))
+    gpu.apply_batched_matrix(qubits, np.concatenate(mats), index, scale)
+    got = gpu.vector().reshape(S, -1)
+    for s in range(S):
+        ora = OracleQV(n)
+        ora.set_state(states[s].astype(np.complex128))
+        if index[s] >= 0:
+            ora.apply_matrix(qubits, mats[index[s]] * scale[s])
+        assert np.max(np.abs(got[s] - ora.vector())) < tol * 4, (s, index[s])
+
+
+@pytest.mark.parametrize("nq,S", [(5, 10), (6, 11), (7, 3), (5, 100)])
+def test_five_qubit_block_on_a_batch_whose_group_count_is_not_a_multiple_of_8(nq, S):
+    """The DMMA kernel walks batches of 8 groups: containers with a ragged group count take the register kernel."""
+    import qiskit_aer_b200 as q
+    rng = np.random.default_rng(nq * 100 + S)
+    U = opgen.colmajor(opgen.haar_unitary(rng, 32))
+    qubits = opgen.pick(rng, nq, 5)
+    gpu = q.QubitVectorB200(nq, np.complex128, num_states=S)
+    states = [opgen.random_state(rng, nq) for _ in range(S)]
+    gpu.set_state(np.concatenate(states))
+    gpu.apply_matrix(qubits, U)
+    got = gpu.vector().reshape(S, -1)
+    for s in range(S):
+        ora = OracleQV(nq)
+        ora.set_state(states[s])
+        ora.apply_matrix(qubits, U)
+        assert np.max(np.abs(got[s] - ora.vector())) < 1e-12, s

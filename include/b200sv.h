@@ -101,6 +101,14 @@ int b200sv_download(b200sv_handle h, void *host, uint64_t offset, uint64_t count
  * diagonal used by probability()/probabilities()/sample_measure (densitymatrix.hpp:590-593) and the other
  * masks are the lines DensityMatrix::expval_pauli walks (:470-520). */
 int b200sv_download_line(b200sv_handle h, int row_bits, uint64_t xor_mask, void *host_out);
+/* Density-matrix reductions on the device (state = vec(rho), as above): DensityMatrix::expval_pauli
+ * (densitymatrix.hpp:455-520; GPU twin density_expval_pauli_func, densitymatrix_thrust.hpp:1011-1188) =
+ * sum_i Re(phase * rho[i ^ x, i]) (-1)^popcount(i & z) with the Pauli given like b200sv_expval_pauli (qubits < row_bits;
+ * the identity string returns the trace), and the marginal probabilities of k <= 12 qubits from the diagonal
+ * (densitymatrix.hpp:590-593 -> qubitvector.hpp:2108; out has 2^k entries). */
+int b200sv_dm_expval_pauli(b200sv_handle h, int row_bits, const uint64_t *qubits, int k, const char *pauli, double pre,
+                           double pim, double *out);
+int b200sv_dm_probabilities(b200sv_handle h, int row_bits, const uint64_t *qubits, int k, double *out);
 /* initialize_component(qubits, state) (qubitvector.hpp:879-900) */
 int b200sv_initialize_component(b200sv_handle h, const uint64_t *qubits, int k, const double *state);
 /* checkpoint()/revert(keep)/inner_product() (qubitvector.hpp:995-1041) -- device-resident copy */

@@ -5,9 +5,10 @@
 // (src/simulators/density_matrix/densitymatrix_state.hpp): rho is stored as the 2n-qubit vector vec(rho)
 // (index = row + col * 2^n), every channel is a vector operation on the doubled register -- U (x) conj(U) as a
 // superoperator matrix or as two passes (densitymatrix.hpp:292-330), X / CX / SWAP / Toffoli as permutations
-// (:338-450), phases as diagonals -- forwarded to QubitVectorB200 and from there to the C ABI.  Measurement
-// statistics, Pauli expectation values and the trace only need one 2^n-entry line of the matrix
-// (b200sv_download_line) and are finished on the host.
+// (:338-450), phases as diagonals -- forwarded to QubitVectorB200 and from there to the C ABI.  Pauli expectation
+// values, the trace and marginal probabilities are device reductions over one 2^n-entry line of the matrix
+// (b200sv_dm_expval_pauli / b200sv_dm_probabilities); sampling draws from the diagonal (b200sv_download_line) with a
+// prefix sum + binary search on the host.
 #ifndef _qv_density_matrix_b200_hpp_
 #define _qv_density_matrix_b200_hpp_
 
@@ -47,9 +48,9 @@ public:
   }
   matrix<std::complex<data_t>> move_to_matrix() { return copy_to_matrix(); }
   std::complex<double> trace() const {
-    auto d = line(0);
-    std::complex<double> t = 0;
-    for (auto &x : d) t += std::complex<double>(x);
+    double t = 0;
+    BaseVector::flush();
+    b200detail::ck(b200sv_dm_expval_pauli(this->Hs(), (int)num_qubits_, nullptr, 0, "", 1.0, 0.0, &t));
     return t;
   }
   template <typename T> void initialize_from_matrix(const matrix<std::complex<T>> &mat) {
@@ -182,6 +183,12 @@ public:
     return p;
   }
   virtual std::vector<double> probabilities(const reg_t &qubits) const override {  // qubitvector.hpp:2108-2143 on the diagonal
+    if (qubits.size() <= 12) {  // one strided pass over the diagonal on the device
+      std::vector<double> p(1ull << qubits.size(), 0.0);
+      BaseVector::flush();
+      b200detail::ck(b200sv_dm_probabilities(this->Hs(), (int)num_qubits(), qubits.data(), (int)qubits.size(), p.data()));
+      return p;
+    }
     const auto diag = probabilities();
     std::vector<double> p(1ull << qubits.size(), 0.0);
     for (size_t i = 0; i < diag.size(); i++) {
@@ -193,15 +200,14 @@ public:
   }
   virtual reg_t sample_measure(const std::vector<double> &rnds) const override {  // qubitvector.hpp:2149-2228
     const auto diag = probabilities();
-    const int_t END = (int_t)diag.size();
+    const size_t END = diag.size();
+    std::vector<double> cum(END);  // inclusive prefix sums in index order, as the reference's running sum
+    double p = 0;
+    for (size_t i = 0; i < END; i++) { p += diag[i]; cum[i] = p; }
     reg_t samples(rnds.size(), 0);
     for (size_t s = 0; s < rnds.size(); s++) {
-      double p = 0;
-      int_t sample = 0;
-      for (; sample < END - 1; ++sample) {
-        p += diag[sample];
-        if (rnds[s] < p) break;
-      }
+      // first index with rnd < cumulative probability, at most END - 1
+      const size_t sample = std::upper_bound(cum.begin(), cum.end() - 1, rnds[s]) - cum.begin();
       samples[s] = sample;
     }
     return samples;
@@ -210,16 +216,11 @@ public:
     uint_t x_mask, z_mask, num_y, x_max;
     std::tie(x_mask, z_mask, num_y, x_max) = pauli_masks_and_phase(qubits, pauli);
     if (x_mask + z_mask == 0) return std::real(BaseMatrix::trace());  // densitymatrix.hpp:463-466
-    auto phase = std::complex<double>(initial_phase);
-    add_y_phase(num_y, phase);
-    // sum_i phase * rho[i ^ x, i] * (-1)^popcount(i & z)   (densitymatrix.hpp:470-520; Z-only: phase is unused)
-    auto l = BaseMatrix::line(x_mask);
+    // sum_i Re(phase * rho[i ^ x, i]) * (-1)^popcount(i & z)   (densitymatrix.hpp:470-520): device reduction
     double val = 0;
-    for (size_t i = 0; i < l.size(); i++) {
-      double v = x_mask ? std::real(phase * std::complex<double>(l[i])) : std::real(std::complex<double>(l[i]));
-      if (z_mask && (AER::Utils::popcount(i & z_mask) & 1)) v = -v;
-      val += v;
-    }
+    BaseVector::flush();
+    b200detail::ck(b200sv_dm_expval_pauli(this->Hs(), (int)num_qubits(), qubits.data(), (int)qubits.size(), pauli.c_str(),
+                                          initial_phase.real(), initial_phase.imag(), &val));
     return val;
   }
   double expval_pauli_non_diagonal_chunk(const reg_t &qubits, const std::string &pauli, const complex_t initial_phase = 1.0) const {

@@ -28,6 +28,8 @@ SIGNATURES = {
     "b200sv_upload": [_vp, _vp, C.c_uint64, C.c_uint64],
     "b200sv_download": [_vp, _vp, C.c_uint64, C.c_uint64],
     "b200sv_download_line": [_vp, C.c_int, C.c_uint64, _vp],
+    "b200sv_dm_expval_pauli": [_vp, C.c_int, _u64p, C.c_int, C.c_char_p, C.c_double, C.c_double, _f64p],
+    "b200sv_dm_probabilities": [_vp, C.c_int, _u64p, C.c_int, _f64p],
     "b200sv_initialize_component": [_vp, _u64p, C.c_int, _f64p],
     "b200sv_checkpoint": [_vp],
     "b200sv_revert": [_vp, C.c_int],

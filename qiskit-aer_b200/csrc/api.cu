@@ -407,6 +407,36 @@ int b200sv_download_line(b200sv_handle h, int row_bits, uint64_t xor_mask, void 
   });
 }
 
+int b200sv_dm_expval_pauli(b200sv_handle h, int row_bits, const uint64_t *qubits, int k, const char *pauli, double pre,
+                           double pim, double *out) {
+  return guard([&] {
+    select(H);
+    if (2 * row_bits != H->nq || H->nstates != 1) throw Error("dm_expval_pauli: the state is not a 2^m x 2^m matrix");
+    std::vector<int> q(k);
+    for (int i = 0; i < k; i++) {
+      if (qubits[i] >= (uint64_t)row_bits) throw Error("qubit index " + std::to_string(qubits[i]) + " out of range");
+      q[i] = (int)qubits[i];
+    }
+    PauliMasks m = pauli_masks(q, pauli);
+    add_y_phase(m.num_y, pre, pim);
+    reduce_dm_expval(*H, row_bits, m.x, m.z, pre, pim, out);  // identity string: the trace (densitymatrix.hpp:463-466)
+  });
+}
+int b200sv_dm_probabilities(b200sv_handle h, int row_bits, const uint64_t *qubits, int k, double *out) {
+  return guard([&] {
+    select(H);
+    if (2 * row_bits != H->nq || H->nstates != 1) throw Error("dm_probabilities: the state is not a 2^m x 2^m matrix");
+    std::vector<int> q(k);
+    for (int i = 0; i < k; i++) {
+      if (qubits[i] >= (uint64_t)row_bits) throw Error("qubit index " + std::to_string(qubits[i]) + " out of range");
+      q[i] = (int)qubits[i];
+      for (int j = 0; j < i; j++)
+        if (q[j] == q[i]) throw Error("duplicate qubit " + std::to_string(q[i]));
+    }
+    reduce_dm_probabilities(*H, row_bits, q.data(), k, out);
+  });
+}
+
 int b200sv_initialize_component(b200sv_handle h, const uint64_t *qubits, int k, const double *state) {
   return guard([&] {
     select(H);

@@ -178,5 +178,7 @@ void reduce_expval_pauli(State &s, uint64_t x_mask, uint64_t z_mask, int x_max, 
                          const void *pair, uint64_t zc, uint64_t zcp, double *out);
 void reduce_inner_product(State &s, const void *other, double *re, double *im);
 void sample_measure(State &s, const double *rnds, int64_t shots, uint64_t *out);
+void reduce_dm_expval(State &s, int m, uint64_t x_mask, uint64_t z_mask, double pre, double pim, double *out);
+void reduce_dm_probabilities(State &s, int m, const int *qubits, int k, double *out);
 
 }  // namespace b200sv

@@ -381,6 +381,71 @@ void reduce_probabilities(State &s, const int *qubits, int k, double *out) {
   memcpy(out, pin, nres * sizeof(double));
 }
 
+// ------------------------------------------------------------------ density-matrix reductions
+// The state is vec(rho) of a 2^m x 2^m matrix (index = row + col * 2^m, densitymatrix.hpp:292-343).  Pauli
+// expectation values and marginal probabilities only touch one 2^m-entry line rho[i ^ x, i]
+// (densitymatrix.hpp:470-520, :590-593; GPU twins density_expval_pauli_func / probability functors,
+// densitymatrix_thrust.hpp:1011-1188): one strided pass on the device, fixed-order finish, no line on the host.
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads)
+dm_expval_kernel(const cx<T> *__restrict__ rho, int m, uint64_t x_mask, uint64_t z_mask, double pre, double pim,
+                 double *__restrict__ partial) {
+  const uint64_t n = 1ull << m, stride = (uint64_t)gridDim.x * blockDim.x;
+  double acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const cx<T> v = rho[(i ^ x_mask) + (i << m)];
+    double t = x_mask ? pre * (double)v.x - pim * (double)v.y : (double)v.x;  // Re(phase * rho[i ^ x, i])
+    if (__popcll(i & z_mask) & 1) t = -t;
+    acc += t;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+void reduce_dm_expval(State &s, int m, uint64_t x_mask, uint64_t z_mask, double pre, double pim, double *out) {
+  NvtxRange nvtx("b200sv density-matrix expval_pauli");
+  const int nb = (int)std::max<uint64_t>(1, std::min<uint64_t>(((1ull << m) + kRedThreads - 1) / kRedThreads, (uint64_t)s.num_sms * 4));
+  run_reduction(s, nb, 1, out, [&](double *partial) {
+    if (s.precision == B200SV_F64) dm_expval_kernel<double><<<nb, kRedThreads, 0, s.stream>>>((const double2 *)s.data, m, x_mask, z_mask, pre, pim, partial);
+    else dm_expval_kernel<float><<<nb, kRedThreads, 0, s.stream>>>((const float2 *)s.data, m, x_mask, z_mask, pre, pim, partial);
+  });
+}
+// marginal probabilities of k measured qubits from the diagonal: every block owns a contiguous slice of the
+// diagonal and 2^k bins in shared memory; the bins of all blocks are summed in a fixed order
+struct DmProbParams {
+  uint8_t q[16];
+  int k, m;
+};
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads)
+dm_prob_kernel(const cx<T> *__restrict__ rho, const __grid_constant__ DmProbParams p, double *__restrict__ partial) {
+  extern __shared__ double bins[];
+  const int nb = 1 << p.k;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) bins[b] = 0.0;
+  __syncthreads();
+  const uint64_t n = 1ull << p.m, per = (n + gridDim.x - 1) / gridDim.x;
+  const uint64_t i0 = per * blockIdx.x, i1 = i0 + per < n ? i0 + per : n;
+  for (uint64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+    uint32_t o = 0;
+    for (int j = 0; j < p.k; j++) o |= (uint32_t)((i >> p.q[j]) & 1ull) << j;
+    atomicAdd(&bins[o], (double)rho[i + (i << p.m)].x);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) partial[(size_t)blockIdx.x * nb + b] = bins[b];
+}
+void reduce_dm_probabilities(State &s, int m, const int *qubits, int k, double *out) {
+  NvtxRange nvtx("b200sv density-matrix probabilities");
+  if (k > 12) throw Error("density-matrix probabilities: more than 12 measured qubits at once");
+  DmProbParams p;
+  p.k = k; p.m = m;
+  for (int j = 0; j < k; j++) p.q[j] = (uint8_t)qubits[j];
+  const int nb = (int)std::max<uint64_t>(1, std::min<uint64_t>(((1ull << m) + 4 * kRedThreads - 1) / (4 * kRedThreads), (uint64_t)s.num_sms * 2));
+  run_reduction(s, nb, 1 << k, out, [&](double *partial) {
+    const size_t smem = sizeof(double) << k;
+    if (s.precision == B200SV_F64) dm_prob_kernel<double><<<nb, kRedThreads, smem, s.stream>>>((const double2 *)s.data, p, partial);
+    else dm_prob_kernel<float><<<nb, kRedThreads, smem, s.stream>>>((const float2 *)s.data, p, partial);
+  });
+}
+
 // ------------------------------------------------------------------ sampler (non-destructive, no 2^n temporary)
 // level 1: sums of contiguous blocks of 2^B amplitudes (one pass over the state)
 // level 2: exclusive scan of the 2^(n-B) block sums (one CTA, fixed order)

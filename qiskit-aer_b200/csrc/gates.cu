@@ -54,6 +54,38 @@ dense_kernel(cx<T> *__restrict__ psi, const __grid_constant__ DenseParams<T, K> 
   }
 }
 
+// Variant for blocks that contain global qubit 0 (the host makes it matrix bit 0): elements 2j and 2j + 1 of a group
+// are neighbours in memory, so every access is one 256-bit load / store = a whole 32-byte sector per lane.  With
+// 128-bit accesses a group whose targets all sit in the low bits costs every sector twice (two instructions, each
+// using half of it): 0.50-0.58 of the HBM peak for K = 3, 4 before (profiles/r01_sweep_n30_v1.txt).
+template <int K>
+__global__ void __launch_bounds__(256, (K == 3 || K == 4) ? 2 : 1)
+dense_pair0_kernel(double2 *__restrict__ psi, const __grid_constant__ DenseParams<double, K> p) {
+  constexpr int DIM = 1 << K;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.ngroups; g += stride) {
+    const uint64_t base = insert_zeros(g, p.ins) | p.ctrl_mask;
+    double2 in[DIM];
+#pragma unroll
+    for (int e = 0; e < DIM; e += 2)
+      asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];"
+                   : "=d"(in[e].x), "=d"(in[e].y), "=d"(in[e + 1].x), "=d"(in[e + 1].y)
+                   : "l"(psi + base + p.off[e]));
+#pragma unroll
+    for (int i = 0; i < DIM; i += 2) {
+      double2 a0 = mk<double>(0, 0), a1 = mk<double>(0, 0);
+#pragma unroll
+      for (int j = 0; j < DIM; j++) {
+        cfma(a0, p.m[i * DIM + j], in[j]);
+        cfma(a1, p.m[(i + 1) * DIM + j], in[j]);
+      }
+      asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(psi + base + p.off[i]), "d"(a0.x), "d"(a0.y), "d"(a1.x),
+                   "d"(a1.y)
+                   : "memory");
+    }
+  }
+}
+
 // ------------------------------------------------------------------ dense k = 5 on the FP64 tensor path (DMMA)
 // A 5-qubit block is 128 DFMA per amplitude: FP64 bound, and in the register kernel above also issue bound (every
 // complex matrix entry feeds one complex FMA per thread: one LDCU per two DFMA).  Here the block is a real 64x64
@@ -130,13 +162,31 @@ template <typename T, int K>
 static void launch_dense_t(State &s, const int *targets, const int *controls, int nc, const double *mat) {
   constexpr int DIM = 1 << K;
   static thread_local DenseParams<T, K> p;  // large: keep off the stack; thread_local because Aer calls from OpenMP threads
+  // matrix bit order: as given, except that global qubit 0 (if it is a target) becomes matrix bit 0 for the
+  // 256-bit-access variant (double precision, K = 2..4): bit b0 <-> bit 0 of the matrix indices
+  int tq[K];
+  for (int b = 0; b < K; b++) tq[b] = targets[b];
+  int b0 = -1;
+  if constexpr (std::is_same<T, double>::value && K >= 2 && K <= 4) {
+    for (int b = 0; b < K; b++)
+      if (targets[b] == 0) b0 = b;
+    if (((uintptr_t)s.data & 31) != 0) b0 = -1;
+    if (b0 > 0) std::swap(tq[0], tq[b0]);
+  }
+  auto perm = [&](int i) {  // index in the caller's bit order of index i in ours
+    if (b0 <= 0) return i;
+    const int lo = i & 1, hi = (i >> b0) & 1;
+    return (i & ~(1 | (1 << b0))) | (hi) | (lo << b0);
+  };
   for (int i = 0; i < DIM; i++)
-    for (int j = 0; j < DIM; j++)
-      p.m[i * DIM + j] = mk<T>((T)mat[2 * (i + DIM * j)], (T)mat[2 * (i + DIM * j) + 1]);
+    for (int j = 0; j < DIM; j++) {
+      const int si = perm(i), sj = perm(j);
+      p.m[i * DIM + j] = mk<T>((T)mat[2 * (si + DIM * sj)], (T)mat[2 * (si + DIM * sj) + 1]);
+    }
   for (int e = 0; e < DIM; e++) {
     uint64_t o = 0;
     for (int b = 0; b < K; b++)
-      if ((e >> b) & 1) o |= 1ull << targets[b];
+      if ((e >> b) & 1) o |= 1ull << tq[b];
     p.off[e] = o;
   }
   std::vector<int> all(targets, targets + K);
@@ -163,6 +213,14 @@ static void launch_dense_t(State &s, const int *targets, const int *controls, in
   }
   const int threads = K >= 5 ? 128 : 256;
   const int grid = grid_for(s, p.ngroups, threads, K >= 5 ? 12 : 16);
+  if constexpr (std::is_same<T, double>::value && K >= 2 && K <= 4) {
+    static const int env_pair0 = [] { const char *e = getenv("B200SV_DENSE_PAIR0"); return e ? atoi(e) : 1; }();
+    if (b0 >= 0 && env_pair0) {
+      dense_pair0_kernel<K><<<grid, threads, 0, s.stream>>>((double2 *)s.data, p);
+      B200_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   dense_kernel<T, K><<<grid, threads, 0, s.stream>>>((cx<T> *)s.data, p);
   B200_CUDA(cudaGetLastError());
 }
@@ -378,16 +436,28 @@ __global__ void __launch_bounds__(256) mcphase_kernel(cx<T> *__restrict__ psi, c
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) pair_perm_kernel(cx<T> *__restrict__ psi, const __grid_constant__ CubeParams p) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < p.ngroups; g += stride) {
-    const uint64_t base = insert_zeros(g, p.ins);
-    const uint64_t i0 = base | p.mask0, i1 = base | p.mask1;
-    const cx<T> a = psi[i0], b = psi[i1];
-    if (MODE == 0) {
-      psi[i0] = b;
-      psi[i1] = a;
-    } else {
-      psi[i0] = mk<T>(b.y, -b.x);
-      psi[i1] = mk<T>(-a.y, a.x);
+  constexpr int U = 4;  // pairs in flight per thread: 8 independent 16-byte loads before the first store
+  for (uint64_t g0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g0 < p.ngroups; g0 += stride * U) {
+    cx<T> a[U], b[U];
+    uint64_t i0[U], i1[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const uint64_t g = g0 + u * stride;
+      const uint64_t base = insert_zeros(g < p.ngroups ? g : 0, p.ins);
+      i0[u] = base | p.mask0;
+      i1[u] = base | p.mask1;
+      if (g < p.ngroups) { a[u] = psi[i0[u]]; b[u] = psi[i1[u]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (g0 + u * stride >= p.ngroups) continue;
+      if (MODE == 0) {
+        psi[i0[u]] = b[u];
+        psi[i1[u]] = a[u];
+      } else {
+        psi[i0[u]] = mk<T>(b[u].y, -b[u].x);
+        psi[i1[u]] = mk<T>(-a[u].y, a[u].x);
+      }
     }
   }
 }

@@ -225,7 +225,7 @@ __device__ __forceinline__ void apply_pre_paulis(double2 *__restrict__ tile, con
 // runs out of uniform registers and demotes the generic path's matrix operands to vector registers.
 // LASTSYNC = false: no barrier after the final round (the caller hands the tile over through an mbarrier that every
 // thread arrives on, so the warps of a group may drift apart across tiles).
-template <int GROUPED, int kLoBits, int MODE, bool LASTSYNC = true>
+template <int GROUPED, int kLoBits, int MODE, bool LASTSYNC = true, int GT = 256>
 __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int tid, const uint64_t t,
                                            const TilePassParams &p, const int grp, const bool valid,
                                            const uint8_t *scodes = nullptr) {
@@ -327,8 +327,17 @@ __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int
     }
     if (R.sync && (LASTSYNC || r + 1 < p.nrounds)) {
       if (GROUPED) {
-        if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
-        else asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (GT == 256) {
+          if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
+          else asm volatile("bar.sync 1, 256;" ::: "memory");
+        } else {
+          switch (grp) {  // constant barrier ids (a register id makes ptxas reserve all 16 barriers)
+          case 0: asm volatile("bar.sync 1, %0;" ::"n"(GT) : "memory"); break;
+          case 1: asm volatile("bar.sync 2, %0;" ::"n"(GT) : "memory"); break;
+          case 2: asm volatile("bar.sync 3, %0;" ::"n"(GT) : "memory"); break;
+          default: asm volatile("bar.sync 4, %0;" ::"n"(GT) : "memory"); break;
+          }
+        }
       } else __syncthreads();
     }
     else __syncwarp();
@@ -570,17 +579,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 
 // MODE 1: double precision, fast rounds; MODE 3: single precision (psi = the state as 16-byte slots)
-template <int MODE>
+// TB = 11: 2^11-amplitude tiles (32 KiB), FOUR compute groups of 128 threads and six buffers: every scheduler of the SM
+// then holds one warp of each group, four independent phases (shared-memory reads / DFMA block / writes / barrier)
+// instead of two pairs in lock step.  The smaller tile carries fewer gates per pass, which is affordable: the passes
+// are FP64 bound, their time follows the gate count, not the pass count (B200SV_TILE_PIPE=3).
+template <int MODE, int TB = 12>
 __global__ void __maxnreg__(96) tile_pipe2_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassParams p) {
-  constexpr int kLoBits = 8;
+  constexpr int kLoBits = TB - 4, kTile = 1 << TB, kGT = 1 << (TB - 4), kGroups = 512 / kGT, kBufs = TB == 12 ? kPipeBufs : 6;
+  constexpr int kMemIters = kTile / 128;
   extern __shared__ __align__(16) double2 tiles[];
-  uint64_t *full = reinterpret_cast<uint64_t *>(tiles + kPipeBufs * 4096);
-  uint64_t *done = full + kPipeBufs;
-  uint8_t *scodes = reinterpret_cast<uint8_t *>(done + kPipeBufs);  // MODE 4: [grp][2][kMaxRounds + 16] Pauli codes
+  uint64_t *full = reinterpret_cast<uint64_t *>(tiles + kBufs * kTile);
+  uint64_t *done = full + kBufs;
+  uint8_t *scodes = reinterpret_cast<uint8_t *>(done + kBufs);  // MODE 4: [grp][2][kMaxRounds + 16] Pauli codes
   // lane-0 broadcasts: warp-uniform role / group ids the compiler can see (uniform branches, uniform datapath)
   const int wid = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (threadIdx.x == 0)
-    for (int b = 0; b < kPipeBufs; b++) { mbar_init(&full[b], 128); mbar_init(&done[b], 256); }
+    for (int b = 0; b < kBufs; b++) { mbar_init(&full[b], 128); mbar_init(&done[b], kGT); }
   __syncthreads();
   const int K = (int)((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);  // tiles of this CTA
   if (wid >= 16) {
@@ -591,38 +605,39 @@ __global__ void __maxnreg__(96) tile_pipe2_kernel(double2 *__restrict__ psi, con
     for (int u = 0; u < 7; u++)
       if ((mt >> u) & 1) glo |= p.goff_lo[u];
     const uint32_t slo = phys_slot((uint32_t)mt);
-    auto goff = [&](int i) { return ((i & 1) ? p.goff_lo[7] : 0) | p.goff_hi[i >> 1]; };
-    auto soff = [&](int i) { return phys_slot((uint32_t)(i & 1) << 7) ^ (uint32_t)p.soff_hi[i >> 1]; };
+    // tile-local bit 7 belongs to the staging-low bits for 2^12 tiles (kLoBits = 8) and to the high index for 2^11 ones
+    auto goff = [&](int i) { return TB == 12 ? (((i & 1) ? p.goff_lo[7] : 0) | p.goff_hi[i >> 1]) : p.goff_hi[i]; };
+    auto soff = [&](int i) { return TB == 12 ? (phys_slot((uint32_t)(i & 1) << 7) ^ (uint32_t)p.soff_hi[i >> 1]) : (uint32_t)p.soff_hi[i]; };
     auto load = [&](int k) {
-      double2 *buf = tiles + (k % kPipeBufs) * 4096;
+      double2 *buf = tiles + (k % kBufs) * kTile;
       const double2 *gt = psi + (insert_zeros(blockIdx.x + (uint64_t)k * gridDim.x, p.ins) | glo);
 #pragma unroll 16
-      for (int i = 0; i < 32; i++) cp_async16_ordered(&buf[slo ^ soff(i)], gt + goff(i));
-      mbar_arrive_cp_async(&full[k % kPipeBufs]);
+      for (int i = 0; i < kMemIters; i++) cp_async16_ordered(&buf[slo ^ soff(i)], gt + goff(i));
+      mbar_arrive_cp_async(&full[k % kBufs]);
     };
-    for (int k = 0; k < kPipeBufs && k < K; k++) load(k);
+    for (int k = 0; k < kBufs && k < K; k++) load(k);
     for (int k = 0; k < K; k++) {
-      mbar_wait(&done[k % kPipeBufs], (uint32_t)((k / kPipeBufs) & 1));
-      double2 *buf = tiles + (k % kPipeBufs) * 4096;
+      mbar_wait(&done[k % kBufs], (uint32_t)((k / kBufs) & 1));
+      double2 *buf = tiles + (k % kBufs) * kTile;
       double2 *gt = psi + (insert_zeros(blockIdx.x + (uint64_t)k * gridDim.x, p.ins) | glo);
 #pragma unroll 16
-      for (int i = 0; i < 32; i++) gt[goff(i)] = buf[slo ^ soff(i)];
-      if (k + kPipeBufs < K) load(k + kPipeBufs);
+      for (int i = 0; i < kMemIters; i++) gt[goff(i)] = buf[slo ^ soff(i)];
+      if (k + kBufs < K) load(k + kBufs);
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     return;
   }
   // ---- compute groups
-  const int grp = wid >> 3, tid = threadIdx.x & 255;
-  for (int kk = 0; 2 * kk < K; kk++) {
-    const int k = 2 * kk + grp;
+  const int grp = wid >> (TB - 9), tid = threadIdx.x & (kGT - 1);
+  for (int kk = 0; kGroups * kk < K; kk++) {
+    const int k = kGroups * kk + grp;
     const bool valid = k < K;
     const uint64_t t = blockIdx.x + (uint64_t)k * gridDim.x;
-    double2 *tile = tiles + (k % kPipeBufs) * 4096;
+    double2 *tile = tiles + (k % kBufs) * kTile;
     if (valid) {
       // order the parity tests: tile k - 3 (other group) left this buffer => full[] is in tile k's phase or past it
-      if (k >= kPipeBufs) mbar_wait(&done[k % kPipeBufs], (uint32_t)(((k - kPipeBufs) / kPipeBufs) & 1));
-      mbar_wait(&full[k % kPipeBufs], (uint32_t)((k / kPipeBufs) & 1));
+      if (k >= kBufs) mbar_wait(&done[k % kBufs], (uint32_t)(((k - kBufs) / kBufs) & 1));
+      mbar_wait(&full[k % kBufs], (uint32_t)((k / kBufs) & 1));
     }
     // MODE 4: Pauli codes of this tile's state, staged by the group's first warp (see tile_pipe_kernel).  Two copies per
     // group, alternating by tile: there is no barrier at the end of a tile here, so the first warp may already be staging
@@ -640,8 +655,8 @@ __global__ void __maxnreg__(96) tile_pipe2_kernel(double2 *__restrict__ psi, con
       else asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if (MODE == 3) run_rounds_f32(tile, tid, p, grp, valid);
-    else run_rounds<1, kLoBits, MODE == 3 ? 1 : MODE, false>(tile, tid, t, p, grp, valid, sc);
-    if (valid) mbar_arrive(&done[k % kPipeBufs]);  // release: this thread's shared-memory writes are visible to the waiter
+    else run_rounds<1, kLoBits, MODE == 3 ? 1 : MODE, false, kGT>(tile, tid, t, p, grp, valid, sc);
+    if (valid) mbar_arrive(&done[k % kBufs]);  // release: this thread's shared-memory writes are visible to the waiter
   }
 }
 
@@ -1085,7 +1100,7 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
 // zero-insertion list, the fixed bit values become a pointer offset, the tile count shrinks -- so the kernels are
 // unchanged.  Slabs are what lets the sharded executor overlap a global-qubit exchange with the passes next to it.
 enum TileVariant { TV_PIPE2_PAULI, TV_PIPE_PAULI, TV_PIPE2_FAST, TV_PIPE_FAST, TV_PIPE_GENERIC, TV_PASS12, TV_PASS11,
-                   TV_PIPE2_F32, TV_DENSE };
+                   TV_PIPE2_F32, TV_DENSE, TV_PIPE3_FAST };
 struct TilePlannedPass {
   TileVariant variant;
   TilePassParams p;        // unused for TV_DENSE
@@ -1112,6 +1127,7 @@ static void launch_tile_variant(State &s, const TilePassParams &p, TileVariant v
     B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pauli));
     B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pipe));
     B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pipe));
+    B200_CUDA(cudaFuncSetAttribute(tile_pipe2_kernel<1, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * (16 << 11) + 128));
     attr_set = true;
   }
   const uint64_t sms = (uint64_t)std::max(1, grid_cap > 0 ? std::min(grid_cap, s.num_sms) : s.num_sms);
@@ -1123,6 +1139,7 @@ static void launch_tile_variant(State &s, const TilePassParams &p, TileVariant v
   case TV_PIPE_FAST: tile_pipe_kernel<1><<<grid, 512, smem_pipe, s.stream>>>(psi, p); break;
   case TV_PIPE_GENERIC: tile_pipe_kernel<2><<<grid, 512, smem_pipe, s.stream>>>(psi, p); break;
   case TV_PIPE2_F32: tile_pipe2_kernel<3><<<grid, 640, smem_pipe, s.stream>>>(psi, p); break;
+  case TV_PIPE3_FAST: tile_pipe2_kernel<1, 11><<<grid, 640, 6 * (16 << 11) + 128, s.stream>>>(psi, p); break;
   case TV_PASS12:
     tile_pass_kernel<12><<<(int)std::min<uint64_t>(p.ntiles, sms * 2), 256, 16 << 12, s.stream>>>(psi, p);
     break;
@@ -1300,6 +1317,7 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
   if (slot_pauli) v = env_pipe == 2 ? TV_PIPE2_PAULI : TV_PIPE_PAULI;   // fast rounds + sampled-noise Paulis
   else if (kTB == 12 && env_pipe == 2 && all_fast) v = TV_PIPE2_FAST;   // memory-warp variant: fast-only code fits its register budget
   else if (kTB == 12 && env_pipe) v = all_fast ? TV_PIPE_FAST : TV_PIPE_GENERIC;
+  else if (kTB == 11 && env_pipe == 3 && all_fast) v = TV_PIPE3_FAST;
   else v = kTB == 12 ? TV_PASS12 : TV_PASS11;
   emit_tile_pass(s, p, v);
   return leftover;
@@ -1651,7 +1669,8 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
   }
   // B200SV_TILE_BITS = 11 | 12 selects the tile size (default 12)
   static const int env_tb = [] { const char *e = getenv("B200SV_TILE_BITS"); return e ? atoi(e) : 0; }();
-  const int kTB = (env_tb == 11 && !s.selftest_host) ? 11 : 12;
+  static const int env_pipe3 = [] { const char *e = getenv("B200SV_TILE_PIPE"); return e ? atoi(e) == 3 : false; }();
+  const int kTB = ((env_tb == 11 || env_pipe3) && !s.selftest_host) ? 11 : 12;
   static const int env_f32 = [] { const char *e = getenv("B200SV_TILE_F32"); return e ? atoi(e) : 1; }();
   if (s.precision == B200SV_F32 && s.nq >= 13 && !any_pauli && env_f32) return apply_gate_sequence_f32(s, gates);
   const bool tiled = s.precision == B200SV_F64 && s.nq >= kTB;

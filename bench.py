@@ -258,7 +258,7 @@ def b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    class_of = lambda op: "%s_k%d" % ("dense" if op[0] == "unitary" else op[0], len(op[1]))  # noqa: E731
+    class_of = lambda op: "diag_layer" if op[0] == "diag_layer" else "%s_k%d" % ("dense" if op[0] == "unitary" else op[0], len(op[1]))  # noqa: E731
     per_class = {}
     launches = [0]
     tile = args.engine == "tile"
@@ -327,7 +327,7 @@ def b200_arm(args):
                     launches[0] += 1
                 if timed:
                     e1.record(stream)
-                    evs.append((class_of(op) if op[0] in ("unitary", "diagonal") else op[0], e0, e1, 1))
+                    evs.append((class_of(op) if op[0] in ("unitary", "diagonal", "diag_layer") else op[0], e0, e1, 1))
         if runner is not None:
             runner.phys = list(final_phys)
         return evs
@@ -450,7 +450,7 @@ def b200_arm(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        dom = max((c for c in per_class if c.startswith(("dense", "diagonal", "tile"))), key=lambda c: per_class[c][1])
+        dom = max((c for c in per_class if c.startswith(("dense", "diag", "tile"))), key=lambda c: per_class[c][1])
         cnt, tot = per_class[dom]
         avg_ms = tot / cnt
         bytes_per_launch = 2 * AMP_BYTES * 2.0 ** n_local
@@ -524,12 +524,17 @@ def extra_qft30(local_rank):
     n = 30
     ops = circuits.qft(n)
     amps = circuits.amplitudes_written(ops, n)
-    fused = fusion.fuse(ops, max_qubit=4, max_diag_qubit=16)
+    # commutation-aware fusion: dense blocks <= 4 qubits, diagonal tables <= 16 qubits, wider sets of commuting
+    # controlled phases as ONE streaming pass each (b200sv_apply_diagonal_layer)
+    fused = fusion.fuse(ops, max_qubit=4, max_diag_qubit=40, max_table_qubit=16)
     stream = torch.cuda.Stream()
     with torch.cuda.stream(stream):
         buf = torch.empty((1 << n) * 2, dtype=torch.float64, device="cuda:%d" % local_rank)
     qv = q.QubitVectorB200(n, np.complex128, device=local_rank, external_ptr=buf.data_ptr(), stream=stream.cuda_stream)
-    cls = lambda op: "%s_k%d" % ("dense" if op[0] == "unitary" else op[0], len(op[1])) if op[0] in ("unitary", "diagonal") else op[1]  # noqa: E731
+    def cls(op):
+        if op[0] == "diag_layer":
+            return "diag_layer"
+        return "%s_k%d" % ("dense" if op[0] == "unitary" else op[0], len(op[1])) if op[0] in ("unitary", "diagonal") else op[1]
     per = {}
     walls = []
     for rep in range(4):
@@ -875,7 +880,8 @@ def main():
     ap.add_argument("--qubits", type=int, default=0, help="override the total qubit count (default 33 + log2 N)")
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--fusion-max-qubit", type=int, default=4)
-    ap.add_argument("--max-diag-qubit", type=int, default=16, help="widest fused diagonal block (table in L2 above 10)")
+    ap.add_argument("--max-diag-qubit", type=int, default=40,
+                    help="widest fused diagonal block (2^k table up to 16 qubits, one-pass diagonal layer above)")
     ap.add_argument("--engine", default="tile", choices=["tile", "dense"],
                     help="tile: multi-gate shared-memory passes (default); dense: one fused dense block per pass")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],

@@ -121,6 +121,12 @@ int b200sv_inner_product(b200sv_handle h, double *re, double *im);
 int b200sv_apply_matrix(b200sv_handle h, const uint64_t *qubits, int k, const double *mat);
 /* apply_diagonal_matrix (qubitvector.hpp:1343 -> transformer.hpp:235) */
 int b200sv_apply_diagonal(b200sv_handle h, const uint64_t *qubits, int k, const double *diag);
+/* A LAYER of commuting diagonal 1-/2-qubit gates (cp, cz, rz, p, rzz, ... on any qubits) in one streaming pass, with no
+ * 2^k table: nq[g] in {1, 2}, qubits = 2 entries per gate, diags = 4 complex<double> per gate (index = bit(q0) +
+ * 2 bit(q1); 1-qubit gates use the first two).  Same result as one apply_diagonal_matrix per gate
+ * (qubitvector.hpp:1343; DiagonalMult*, thrust_kernels.hpp:1318-1444); entries must be non-zero (projectors go through
+ * apply_diagonal_matrix). */
+int b200sv_apply_diagonal_layer(b200sv_handle h, int ngates, const int *nq, const uint64_t *qubits, const double *diags);
 /* apply_multiplexer (qubitvector.hpp:1305) */
 int b200sv_apply_multiplexer(b200sv_handle h, const uint64_t *ctrl, int nc, const uint64_t *tgt, int nt,
                              const double *mat);

@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200sv_inner_product": [_vp, _f64p, _f64p],
     "b200sv_apply_matrix": [_vp, _u64p, C.c_int, _f64p],
     "b200sv_apply_diagonal": [_vp, _u64p, C.c_int, _f64p],
+    "b200sv_apply_diagonal_layer": [_vp, C.c_int, C.POINTER(C.c_int), _u64p, _f64p],
     "b200sv_apply_multiplexer": [_vp, _u64p, C.c_int, _u64p, C.c_int, _f64p],
     "b200sv_apply_permutation": [_vp, _u64p, C.c_int, _u64p, C.c_int],
     "b200sv_apply_mcx": [_vp, _u64p, C.c_int],

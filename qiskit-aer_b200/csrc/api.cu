@@ -519,6 +519,29 @@ int b200sv_apply_diagonal(b200sv_handle h, const uint64_t *qubits, int k, const 
   });
 }
 
+int b200sv_apply_diagonal_layer(b200sv_handle h, int ngates, const int *nq, const uint64_t *qubits, const double *diags) {
+  return guard([&] {
+    select(H);
+    if (ngates < 0 || (ngates > 0 && (!nq || !qubits || !diags))) throw Error("apply_diagonal_layer: bad arguments");
+    if (H->global_nq > H->nq) throw Error("apply_diagonal_layer: not available on a chunk of a sharded register");
+    for (int g = 0; g < ngates; g++) {
+      if (nq[g] != 1 && nq[g] != 2) throw Error("apply_diagonal_layer: gates must act on 1 or 2 qubits");
+      for (int j = 0; j < nq[g]; j++)
+        if (qubits[2 * g + j] >= (uint64_t)H->nq) throw Error("qubit index " + std::to_string(qubits[2 * g + j]) + " out of range");
+      if (nq[g] == 2 && qubits[2 * g] == qubits[2 * g + 1]) throw Error("duplicate qubit " + std::to_string(qubits[2 * g]));
+    }
+    if (ngates == 0) return;
+    if (H->nq < 4) {  // tiny registers: gate by gate
+      for (int g = 0; g < ngates; g++) {
+        int q[2] = {(int)qubits[2 * g], (int)qubits[2 * g + 1]};
+        launch_diagonal(*H, q, nq[g], diags + 8 * (size_t)g);
+      }
+      return;
+    }
+    launch_diag_layer(*H, ngates, nq, qubits, diags);
+  });
+}
+
 int b200sv_apply_multiplexer(b200sv_handle h, const uint64_t *ctrl, int nc, const uint64_t *tgt, int nt,
                              const double *mat) {
   return guard([&] {
@@ -715,7 +738,7 @@ int b200sv_fuse_assign(int nops, const int *op_off, const int *op_qubits, const 
                        int window, int max_diag_qubit, int *block_of_op, int *nblocks) {
   return guard([&] {
     if (nops < 0 || !nblocks || (nops > 0 && (!op_off || !op_qubits || !op_is_diag || !block_of_op)) || max_qubit < 1 ||
-        max_qubit > 10 || max_diag_qubit < 1 || max_diag_qubit > 28 || window < 1)
+        max_qubit > 10 || max_diag_qubit < 1 || max_diag_qubit > 62 || window < 1)
       throw Error("fuse_assign: bad arguments");
     for (int k = 0; k < (nops ? op_off[nops] : 0); k++)
       if (op_qubits[k] < 0 || op_qubits[k] > 62) throw Error("fuse_assign: qubit out of range");

@@ -129,6 +129,7 @@ std::vector<int> checked_qubits(const State &s, const uint64_t *qubits, int k, b
 void launch_dense(State &s, const int *targets, int k, const int *controls, int nc, const double *mat_colmajor);
 void launch_dense_generic(State &s, const int *targets, int k, const double *mat_colmajor);
 void launch_diagonal(State &s, const int *qubits, int k, const double *diag);
+void launch_diag_layer(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *diags);
 void launch_mcphase(State &s, const int *qubits, int k, double re, double im);
 void launch_mcx(State &s, const int *controls, int nc, int target);
 void launch_mcy(State &s, const int *controls, int nc, int target);

@@ -13,6 +13,8 @@
 //     device_chunk_container.hpp:566-594) and feed DFMA directly.
 // Index algebra: base = insert_zeros(g, sorted(targets U controls)) | ctrl_mask,
 // element e at base + off[e]  (indexes.hpp:212-250).
+#include <complex>
+
 #include "common.cuh"
 
 namespace b200sv {
@@ -1025,6 +1027,183 @@ void launch_multi_swap_peer(State &s, int k, const int *local_q, uint32_t my_g, 
   const unsigned grid = (unsigned)std::max(gx, 1) * (unsigned)p.nl_classes;
   if (s.precision == B200SV_F64) multi_swap_kernel<double><<<grid, 256, 0, s.stream>>>((double2 *)s.data, p);
   else multi_swap_kernel<float><<<grid, 256, 0, s.stream>>>((float2 *)s.data, p);
+  B200_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------ wide diagonal layers
+// ANY number of commuting diagonal 1-/2-qubit gates (cp, cz, rz, p, rzz ... over all qubits of the register) in ONE
+// streaming pass, without a 2^k table: with every gate written as d(ba, bb) = c * A_a^ba * A_b^bb * G_ab^(ba bb) the
+// whole layer is   phase(i) = C * prod_{a set} A_a * prod_{a<b both set} G_ab,
+// a quadratic form in the index bits.  A CTA walks chunks of 2^12 consecutive amplitudes: per chunk the high bits are
+// fixed, so S(hi) and the twelve low-bit multipliers M_u(hi) = A_u * prod_{b high, set} G_ub are computed once (by 44
+// threads), each thread then builds the factor of its 8 thread-id bits (<= 36 predicated complex multiplies) and the 16
+// phases of its 16 amplitudes by doubling: ~6 complex multiplies per amplitude, far below the ~22 a pass can afford at
+// HBM speed.  Replaces chains of DiagonalMult* launches / 2^k-entry tables (thrust_kernels.hpp:1318-1444) for layers
+// wider than a table can be (QFT: all controlled phases between two groups of Hadamards).
+struct DiagLayerParams {
+  const double2 *A;   // [nq]
+  const double2 *G;   // [nq][nq], G[a * nq + b] for a != b (symmetric), 1 elsewhere
+  double2 C;
+  int nq;
+};
+__device__ __forceinline__ double2 cmulz(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <typename T>
+__global__ void __launch_bounds__(288) diag_layer_kernel(cx<T> *__restrict__ psi, const __grid_constant__ DiagLayerParams p,
+                                                         uint64_t nchunks, int lo_bits) {
+  extern __shared__ double2 sTab[];            // A[nq], then G[nq][nq]: staged once per CTA
+  __shared__ double2 sMbuf[2][12], sSbuf[2];   // per-chunk factors, double buffered
+  const int tid = threadIdx.x, nq = p.nq;
+  double2 *sA = sTab, *sG = sTab + nq;
+  for (int e = tid; e < nq + nq * nq; e += blockDim.x) sTab[e] = p.A[e];  // A and G are contiguous in device memory
+  __syncthreads();
+  // warp 8 (threads 256..287) is the producer: it computes the factors of the NEXT chunk while warps 0..7 apply the
+  // current one; one barrier per chunk hands the buffers over
+  auto produce = [&](uint64_t hi, int buf) {
+    const int lane = tid - 256;
+    double2 part = make_double2(1.0, 0.0);  // S(hi) = C * prod_{a high, set} (A_a * prod_{b > a, set} G_ab): one a per lane
+    for (int a = lo_bits + lane; a < nq; a += 32) {
+      if (!((hi >> (a - lo_bits)) & 1)) continue;
+      part = cmulz(part, sA[a]);
+      for (int b = a + 1; b < nq; b++)
+        if ((hi >> (b - lo_bits)) & 1) part = cmulz(part, sG[a * nq + b]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double2 other = make_double2(__shfl_xor_sync(0xffffffffu, part.x, o), __shfl_xor_sync(0xffffffffu, part.y, o));
+      part = cmulz(part, other);
+    }
+    if (lane == 0) sSbuf[buf] = cmulz(p.C, part);
+    if (lane < 12) {  // M_u(hi) = A_u * prod_{b high, set} G_ub
+      double2 m = make_double2(1.0, 0.0);
+      if (lane < lo_bits) {
+        m = sA[lane];
+        for (int b = lo_bits; b < nq; b++)
+          if ((hi >> (b - lo_bits)) & 1) m = cmulz(m, sG[lane * nq + b]);
+      }
+      sMbuf[buf][lane] = m;
+    }
+  };
+  if (tid >= 256 && blockIdx.x < nchunks) produce(blockIdx.x, 0);
+  __syncthreads();
+  int it = 0;
+  for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x, it++) {
+    const double2 *sM = sMbuf[it & 1];
+    const double2 sS = sSbuf[it & 1];
+    if (tid >= 256) {
+      if (c + gridDim.x < nchunks) produce(c + gridDim.x, (it + 1) & 1);
+      __syncthreads();
+      continue;
+    }
+    // ---- thread id = chunk-local bits 0..7 (consecutive threads touch consecutive amplitudes: coalesced), the 16
+    // amplitudes of a thread differ in chunk-local bits 8..11.  Thread factor over its id bits, then the 16 phases by doubling.
+    const bool active = lo_bits == 12 || (lo_bits >= 8 ? true : tid < (1 << lo_bits));
+    const int ebits = lo_bits >= 8 ? lo_bits - 8 : 0;   // element bits that exist in this chunk (4 for full chunks)
+    if (active) {
+      double2 f = sS;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        if (!((tid >> u) & 1)) continue;
+        f = cmulz(f, sM[u]);
+#pragma unroll
+        for (int v = u + 1; v < 8; v++)
+          if ((tid >> v) & 1) f = cmulz(f, sG[u * nq + v]);
+      }
+      double2 w[4];  // multiplier of element bit e (position 8 + e) given this thread's id bits
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        double2 m = make_double2(1.0, 0.0);
+        if (e < ebits) {
+          m = sM[8 + e];
+#pragma unroll
+          for (int u = 0; u < 8; u++)
+            if ((tid >> u) & 1) m = cmulz(m, sG[(8 + e) * nq + u]);
+        }
+        w[e] = m;
+      }
+      double2 ph[16];
+      ph[0] = f;
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+#pragma unroll
+        for (int j = 0; j < (1 << e); j++) {
+          double2 m = cmulz(ph[j], w[e]);
+          if (e < ebits) {
+#pragma unroll
+            for (int x = 0; x < e; x++)
+              if ((j >> x) & 1) m = cmulz(m, sG[(8 + x) * nq + 8 + e]);
+          }
+          ph[j | (1 << e)] = m;
+        }
+      cx<T> *base = psi + (c << lo_bits) + (uint64_t)tid;
+      cx<T> v[16];
+#pragma unroll
+      for (int e = 0; e < 16; e++)
+        if (e < (1 << ebits)) v[e] = base[(uint64_t)e << 8];
+#pragma unroll
+      for (int e = 0; e < 16; e++)
+        if (e < (1 << ebits))
+          base[(uint64_t)e << 8] = mk<T>((T)(ph[e].x * (double)v[e].x - ph[e].y * (double)v[e].y),
+                                         (T)(ph[e].x * (double)v[e].y + ph[e].y * (double)v[e].x));
+    }
+    __syncthreads();
+  }
+}
+void launch_diag_layer(State &s, int ngates, const int *nq, const uint64_t *qubits, const double *diags) {
+  typedef std::complex<double> cd;
+  if (s.nq < 4) throw Error("diagonal layer: needs at least 4 qubits");
+  const int n = s.nq;
+  std::vector<cd> A((size_t)n, cd(1.0)), G((size_t)n * n, cd(1.0));
+  cd Cc(1.0);
+  for (int g = 0; g < ngates; g++) {
+    const cd *d = reinterpret_cast<const cd *>(diags + 8 * (size_t)g);
+    const int a = (int)qubits[2 * g];
+    if (nq[g] == 1) {
+      if (d[0] == cd(0.0)) throw Error("diagonal layer: zero entry (use apply_diagonal_matrix)");
+      Cc *= d[0];
+      A[a] *= d[1] / d[0];
+    } else {
+      const int b = (int)qubits[2 * g + 1];
+      if (d[0] == cd(0.0) || d[1] == cd(0.0) || d[2] == cd(0.0)) throw Error("diagonal layer: zero entry (use apply_diagonal_matrix)");
+      Cc *= d[0];
+      A[a] *= d[1] / d[0];     // index = ba + 2 bb
+      A[b] *= d[2] / d[0];
+      const cd gab = d[3] * d[0] / (d[1] * d[2]);
+      G[(size_t)a * n + b] *= gab;
+      G[(size_t)b * n + a] *= gab;
+    }
+  }
+  const size_t bytes = ((size_t)n + (size_t)n * n) * 16;
+  char *hm = (char *)s.ensure_pinned(bytes);
+  char *dm = (char *)s.ensure_scratch(bytes);
+  B200_CUDA(cudaStreamSynchronize(s.stream));
+  memcpy(hm, A.data(), (size_t)n * 16);
+  memcpy(hm + (size_t)n * 16, G.data(), (size_t)n * n * 16);
+  B200_CUDA(cudaMemcpyAsync(dm, hm, bytes, cudaMemcpyHostToDevice, s.stream));
+  DiagLayerParams p;
+  p.A = (const double2 *)dm;
+  p.G = (const double2 *)(dm + (size_t)n * 16);
+  p.C = make_double2(Cc.real(), Cc.imag());
+  p.nq = n;
+  const int lo_bits = std::min(12, n);
+  const size_t smem = ((size_t)n + (size_t)n * n) * 16;  // <= 26 KiB at 40 qubits
+  // batched containers: every state is its own run of chunks with the same layer (hi wraps per state)
+  const uint64_t chunks_per_state = 1ull << (n - lo_bits);
+  if (s.nstates != 1 && chunks_per_state != 1) {
+    for (int64_t st = 0; st < s.nstates; st++) {
+      State v = s;
+      v.nstates = 1;
+      v.data = (char *)s.data + ((uint64_t)st << n) * s.amp_bytes();
+      const int grid = (int)std::min<uint64_t>(chunks_per_state, (uint64_t)s.num_sms * 8);
+      if (s.precision == B200SV_F64) diag_layer_kernel<double><<<grid, 288, smem, s.stream>>>((double2 *)v.data, p, chunks_per_state, lo_bits);
+      else diag_layer_kernel<float><<<grid, 288, smem, s.stream>>>((float2 *)v.data, p, chunks_per_state, lo_bits);
+    }
+    B200_CUDA(cudaGetLastError());
+    return;
+  }
+  const uint64_t nchunks = s.nstates == 1 ? chunks_per_state : (uint64_t)s.nstates;
+  const int grid = (int)std::min<uint64_t>(nchunks, (uint64_t)s.num_sms * 8);
+  if (s.precision == B200SV_F64) diag_layer_kernel<double><<<grid, 288, smem, s.stream>>>((double2 *)s.data, p, nchunks, lo_bits);
+  else diag_layer_kernel<float><<<grid, 288, smem, s.stream>>>((float2 *)s.data, p, nchunks, lo_bits);
   B200_CUDA(cudaGetLastError());
 }
 

@@ -17,6 +17,12 @@ def apply_op(qv, op):
         qv.apply_matrix(op[1], colmajor(op[2]))
     elif kind == "diagonal":
         qv.apply_diagonal_matrix(op[1], op[2])
+    elif kind == "diag_layer":  # commuting diagonal 1-/2-qubit gates: one pass on the engine, gate by gate elsewhere
+        if hasattr(qv, "apply_diagonal_layer"):
+            qv.apply_diagonal_layer(op[1])
+        else:
+            for q, d in op[1]:
+                qv.apply_diagonal_matrix(q, d)
     elif kind == "gate":
         name, qubits, params = op[1], op[2], op[3]
         if name == "h":      # apply_mcu(u4(pi/2,0,pi,0)), statevector_state.hpp:809-811
@@ -52,6 +58,8 @@ def op_h2d_bytes(op):
         return 16 * np.asarray(op[2]).size
     if op[0] == "diagonal":
         return 16 * len(op[2])
+    if op[0] == "diag_layer":
+        return 64 * len(op[1])
     return 64
 
 

@@ -91,7 +91,7 @@ def _is_diag(U):
     return np.count_nonzero(U - np.diag(np.diag(U))) == 0
 
 
-def fuse(ops, max_qubit=5, window=64, max_diag_qubit=10):
+def fuse(ops, max_qubit=5, window=64, max_diag_qubit=10, max_table_qubit=16):
     """Returns a list of ("unitary", qubits, U) / ("diagonal", qubits, d) ops equivalent to `ops`.
     The block assignment and the block matrix products run in the library (b200sv_fuse_assign /
     b200sv_fuse_block_matrix, csrc/planner.cu); `_fuse_py` below is the same algorithm in numpy, kept as the
@@ -125,6 +125,12 @@ def fuse(ops, max_qubit=5, window=64, max_diag_qubit=10):
                 if x not in bq:
                     bq.append(x)
         diag = all(isd[i] for i in ms)
+        if diag and len(bq) > max_table_qubit:
+            # wider than a 2^k table can be: keep the gate list, the engine applies the whole layer in one pass
+            # (b200sv_apply_diagonal_layer); gates on more than two qubits do not occur here (they were tables already)
+            if all(len(mats[i][0]) <= 2 and np.all(np.diag(mats[i][1]) != 0) for i in ms):
+                out.append(("diag_layer", [(list(mats[i][0]), np.diag(mats[i][1]).copy()) for i in ms]))
+                continue
         goff = np.zeros(len(ms) + 1, dtype=np.int32)
         moff = np.zeros(len(ms), dtype=np.int64)
         flat, gq, pos = [], [], 0

@@ -229,6 +229,19 @@ class QubitVectorB200:
             raise ValueError("need 4 words per state")
         capi.check(self._lib.b200sv_apply_batched_pauli(self.h, a.ctypes.data_as(_u64p)))
 
+    def apply_diagonal_layer(self, gates):
+        """gates: [(qubits (1 or 2), diagonal (2 or 4 complex))] -- commuting diagonal gates, one streaming pass."""
+        ng = len(gates)
+        nq = np.zeros(ng, dtype=np.int32)
+        qs = np.zeros(2 * ng, dtype=np.uint64)
+        dg = np.zeros((ng, 4), dtype=np.complex128)
+        for i, (q, d) in enumerate(gates):
+            nq[i] = len(q)
+            qs[2 * i:2 * i + len(q)] = q
+            dg[i, :1 << len(q)] = np.asarray(d, dtype=np.complex128).reshape(-1)
+        capi.check(self._lib.b200sv_apply_diagonal_layer(self.h, ng, nq.ctypes.data_as(C.POINTER(C.c_int)),
+                                                         qs.ctypes.data_as(_u64p), dg.ctypes.data_as(_f64p)))
+
     def apply_batched_matrix(self, qubits, mats, index, scale=None):
         """State s applies the column-major matrix mats[index[s]] * scale[s] (index < 0: untouched) -- one launch
         (batched Kraus / per-parameter matrices, qubitvector_thrust.hpp:1578-1611,2996-3177)."""

@@ -553,3 +553,60 @@ def test_full_size_qv33_round_trip_across_engines():
     s = gpu.sample_measure(np.array([0.5]))
     assert int(s[0]) == 1 << (n - 1)
     gpu.close()
+
+
+@pytest.mark.parametrize("n,dtype", [(4, np.complex128), (9, np.complex128), (13, np.complex128), (17, np.complex128),
+                                     (15, np.complex64)])
+def test_wide_diagonal_layer(n, dtype):
+    """b200sv_apply_diagonal_layer: many commuting diagonal 1-/2-qubit gates over all qubits in one pass == the gates
+    applied one by one (apply_diagonal_matrix, qubitvector.hpp:1343)."""
+    dtype = np.dtype(dtype)
+    rng = np.random.default_rng(n)
+    psi0 = opgen.random_state(rng, n, dtype)
+    ora, gpu = OracleQV(n, dtype), gpu_qv(n, dtype)
+    ora.set_state(psi0)
+    gpu.set_state(psi0)
+    gates = []
+    for _ in range(6 * n):
+        k = int(rng.integers(1, 3))
+        qs = opgen.pick(rng, n, k)
+        d = np.exp(1j * rng.uniform(0, 2 * np.pi, 1 << k)) * rng.uniform(0.9, 1.1, 1 << k)
+        gates.append((qs, d))
+    gpu.apply_diagonal_layer(gates)
+    for qs, d in gates:
+        ora.apply_diagonal_matrix(qs, d)
+    a, b = ora.vector(), gpu.vector()
+    scale = np.max(np.abs(a))
+    assert np.max(np.abs(a - b)) < (1e-11 if dtype == np.complex128 else 2e-5) * scale
+
+
+def test_wide_diagonal_layer_on_a_batch_and_qft_front_end():
+    import qiskit_aer_b200 as q
+    from qiskit_aer_b200 import circuits, executor, fusion
+    # batched container: every state gets the same layer
+    n, S = 13, 5
+    rng = np.random.default_rng(3)
+    states = [opgen.random_state(rng, n) for _ in range(S)]
+    gpu = q.QubitVectorB200(n, np.complex128, num_states=S)
+    gpu.set_state(np.concatenate(states))
+    gates = [(opgen.pick(rng, n, 2), np.exp(1j * rng.uniform(0, 6.28, 4))) for _ in range(40)]
+    gpu.apply_diagonal_layer(gates)
+    got = gpu.vector().reshape(S, -1)
+    for s in range(S):
+        ora = OracleQV(n)
+        ora.set_state(states[s])
+        for qs, d in gates:
+            ora.apply_diagonal_matrix(qs, d)
+        assert np.max(np.abs(got[s] - ora.vector())) < 1e-12
+    # QFT through the fusion front end with wide diagonal layers
+    n = 16
+    ops = circuits.qft(n)
+    fused = fusion.fuse(ops, max_qubit=4, max_diag_qubit=40, max_table_qubit=6)
+    assert any(op[0] == "diag_layer" for op in fused)
+    g, o = q.QubitVectorB200(n), OracleQV(n)
+    psi0 = opgen.random_state(rng, n)
+    g.set_state(psi0)
+    o.set_state(psi0)
+    executor.apply_ops(g, fused)
+    executor.apply_ops(o, ops)
+    assert opgen.fidelity_gap(o.vector(), g.vector()) < 1e-10

@@ -114,6 +114,7 @@ struct State {
   bool plan_only = false;  // selftest without a host array: count the passes only
   const uint8_t *selftest_codes = nullptr;
   TilePlan *capture = nullptr;  // set while tile_plan_build runs: passes are recorded instead of launched
+  bool in_layer_split = false;  // apply_gate_sequence is running the dense part of a diagonal-layer split
 
   uint64_t amps_per_state() const { return 1ull << nq; }
   uint64_t total_amps() const { return (uint64_t)nstates << nq; }

@@ -1662,6 +1662,83 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
       any_pauli = true;
     }
   }
+  // Circuits rich in commuting diagonal gates (QFT's controlled phases, cz / rz layers): the engine's fusion pass
+  // (planner.cu, commutation aware) regroups the queue into small dense blocks and WIDE diagonal blocks; a wide
+  // diagonal block is one streaming pass (gates.cu: diag_layer_kernel) instead of one tile-round slot per gate, the
+  // dense blocks in between go through the tile passes as before.  The role Fusion::optimize_circuit's diagonal
+  // fusion plays in the reference (src/transpile/fusion.hpp:816-821), without its 2^k table limit.
+  static const int env_layers = [] { const char *e = getenv("B200SV_QUEUE_DIAG_LAYERS"); return e ? atoi(e) : 1; }();
+  if (env_layers && !s.in_layer_split && !any_pauli && !s.selftest_host && !s.capture && s.nstates == 1 && s.nq >= 16 &&
+      s.global_nq <= s.nq) {
+    int ndiag2 = 0;
+    std::vector<uint8_t> isd(ngates);
+    bool layer_ok = true;
+    for (int i = 0; i < ngates; i++) {
+      isd[i] = is_diag(gates[i]) ? 1 : 0;
+      if (isd[i] && gates[i].nq == 2) ndiag2++;
+      if (isd[i]) {
+        const int dim = 1 << gates[i].nq;
+        for (int d = 0; d < dim; d++)
+          if (gates[i].mat[2 * (d + dim * d)] == 0.0 && gates[i].mat[2 * (d + dim * d) + 1] == 0.0) layer_ok = false;  // projector
+      }
+    }
+    if (layer_ok && ndiag2 >= 24 && 3 * ndiag2 >= ngates) {
+      std::vector<int> off(ngates + 1, 0), qs, blk(ngates);
+      for (int i = 0; i < ngates; i++) {
+        for (int j = 0; j < gates[i].nq; j++) qs.push_back(gates[i].q[j]);
+        off[i + 1] = (int)qs.size();
+      }
+      int nblocks = 0;
+      fuse_assign(ngates, off.data(), qs.data(), isd.data(), 4, 64, 62, blk.data(), &nblocks);
+      std::vector<std::vector<int>> members(nblocks);
+      for (int i = 0; i < ngates; i++) members[blk[i]].push_back(i);
+      int passes = 0;
+      std::vector<int> seq_nq;
+      std::vector<uint64_t> seq_q;
+      std::vector<double> seq_m;
+      auto flush_seq = [&] {
+        if (seq_nq.empty()) return;
+        s.in_layer_split = true;
+        try {
+          passes += apply_gate_sequence(s, (int)seq_nq.size(), seq_nq.data(), seq_q.data(), seq_m.data(), low_bits);
+        } catch (...) { s.in_layer_split = false; throw; }
+        s.in_layer_split = false;
+        seq_nq.clear(); seq_q.clear(); seq_m.clear();
+      };
+      for (int b = 0; b < nblocks; b++) {
+        bool all_diag = true;
+        for (int i : members[b]) all_diag = all_diag && isd[i];
+        if (all_diag && members[b].size() >= 6) {
+          flush_seq();
+          std::vector<int> lnq;
+          std::vector<uint64_t> lq;
+          std::vector<double> ld;
+          for (int i : members[b]) {
+            const QGate &g = gates[i];
+            const int dim = 1 << g.nq;
+            lnq.push_back(g.nq);
+            lq.push_back((uint64_t)g.q[0]);
+            lq.push_back(g.nq == 2 ? (uint64_t)g.q[1] : 0);
+            for (int d = 0; d < 4; d++) {
+              ld.push_back(d < dim ? g.mat[2 * (d + dim * d)] : 0.0);
+              ld.push_back(d < dim ? g.mat[2 * (d + dim * d) + 1] : 0.0);
+            }
+          }
+          launch_diag_layer(s, (int)lnq.size(), lnq.data(), lq.data(), ld.data());
+          passes++;
+          continue;
+        }
+        for (int i : members[b]) {
+          seq_nq.push_back(gates[i].nq);
+          seq_q.push_back((uint64_t)gates[i].q[0]);
+          seq_q.push_back(gates[i].nq == 2 ? (uint64_t)gates[i].q[1] : 0);
+          seq_m.insert(seq_m.end(), gates[i].mat, gates[i].mat + 32);
+        }
+      }
+      flush_seq();
+      return passes;
+    }
+  }
   std::vector<std::array<double, 32>> merged;
   if ((s.precision == B200SV_F64 && s.nq >= 12) || (s.precision == B200SV_F32 && s.nq >= 13)) {
     absorb_one_qubit_gates(gates, s.nq, merged);

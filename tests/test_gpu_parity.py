@@ -610,3 +610,26 @@ def test_wide_diagonal_layer_on_a_batch_and_qft_front_end():
     executor.apply_ops(g, fused)
     executor.apply_ops(o, ops)
     assert opgen.fidelity_gap(o.vector(), g.vector()) < 1e-10
+
+
+def test_gate_queue_splits_wide_diagonal_layers_out():
+    """A queue rich in commuting controlled phases (QFT): the flush regroups it into tile passes for the dense gates and
+    one-pass diagonal layers (b200sv_apply_gate_sequence -> fuse_assign -> diag_layer_kernel); result == gate by gate."""
+    from qiskit_aer_b200 import circuits, executor, fusion
+    n = 17
+    rng = np.random.default_rng(5)
+    psi0 = opgen.random_state(rng, n)
+    ops = circuits.qft(n) + circuits.random_noisy_circuit(n, 2, seed=3)
+    seq = []
+    for op in ops:
+        qs, U = fusion.op_matrix(op)
+        seq.append((list(qs), executor.colmajor(U)))
+    ora, gpu = OracleQV(n), gpu_qv(n)
+    ora.set_state(psi0)
+    gpu.set_state(psi0)
+    passes = gpu.apply_gate_sequence(seq)
+    for qs, m in seq:
+        ora.apply_matrix(qs, m)
+    assert opgen.fidelity_gap(ora.vector(), gpu.vector()) < 1e-10
+    assert np.max(np.abs(ora.vector() - gpu.vector())) < 1e-11
+    assert passes < len(seq) // 4

@@ -317,6 +317,14 @@ int b200sv_sharded_apply_ops(b200sv_sharded_handle h, int nops, const int *kinds
 int b200sv_sharded_plan_only(int num_qubits, int precision, int world, uint64_t staging_bytes, int nops, const int *kinds,
                              const int *op_off, const int *op_qubits, const int64_t *data_off, const double *data,
                              double *out8);
+/* Executor self-test -- TEST INFRASTRUCTURE, no device: the register lives in host_state (2^n amplitudes of the given
+ * precision, shard r = the r-th contiguous slice); the program is compiled and scheduled as apply_ops does and then
+ * interpreted on the host in issue order (tile-pass parameter blocks whole and slab-patched, pushes / unstages as the
+ * same strided copies, in-place exchanges as swaps), and the qubit order is restored.  out8 as b200sv_sharded_stats.
+ * Lets the CPU-only test-suite cover the slab / staging / exchange-group index algebra and the pipeline's issue order. */
+int b200sv_sharded_selftest(int num_qubits, int precision, int world, uint64_t staging_bytes, int nops, const int *kinds,
+                            const int *op_off, const int *op_qubits, const int64_t *data_off, const double *data,
+                            void *host_state, double *out8);
 /* of the last apply_ops: {tile passes, exchanges, staged, in place, kernel launches, DMA copies, bytes sent per shard,
  * passes that ran slab-wise next to an exchange} */
 int b200sv_sharded_stats(b200sv_sharded_handle h, double *out8);

@@ -93,6 +93,8 @@ SIGNATURES = {
                                  C.POINTER(C.c_int64), _f64p],
     "b200sv_sharded_plan_only": [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                  C.POINTER(C.c_int), C.POINTER(C.c_int64), _f64p, _f64p],
+    "b200sv_sharded_selftest": [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int), C.POINTER(C.c_int64), _f64p, _vp, _f64p],
     "b200sv_sharded_stats": [_vp, _f64p],
     "b200sv_sharded_profile": [_vp, C.c_int],
     "b200sv_sharded_profile_read": [_vp, _f64p],

@@ -154,6 +154,7 @@ struct Sharded {
   int push_streams = 4;
   int max_ride = 2;           // passes per side of an exchange that may run slab-wise under it
   bool profile = false;
+  bool emulate = false;       // executor self-test: shards are host arrays, work is interpreted in issue order
   // statistics of the last run
   int64_t stat_passes = 0, stat_exchanges = 0, stat_staged = 0, stat_inplace = 0, stat_launches = 0, stat_copies = 0;
   int64_t stat_overlapped_passes = 0;
@@ -162,7 +163,10 @@ struct Sharded {
   bool multi_process() const { return (int)local.size() < world; }
 };
 
-static void sel(const Shard &s) { B200_CUDA(cudaSetDevice(s.st->device)); }
+static void sel(const Shard &s) {
+  if (s.st->selftest_host) return;  // emulated shard: no device
+  B200_CUDA(cudaSetDevice(s.st->device));
+}
 
 // profiling scope: records an event pair on `stream` around a piece of work of the first local shard
 struct ProfScope {
@@ -201,6 +205,7 @@ struct ProfScope {
 // (kind, >= seq).  Shards of this process are ordered with events (the host issues their work in dependency order),
 // shards of other processes with flag words.
 static void signal(Sharded &S, int me, cudaStream_t stream, int kind, uint64_t seq, const std::vector<int> &to) {
+  if (S.emulate) return;  // the emulation executes in issue order, which is a valid serialisation of the partial order
   Shard &m = S.sh[me];
   sel(m);
   B200_CUDA(cudaEventRecord(m.ev[kind][seq % kEvRing], stream));
@@ -219,7 +224,7 @@ static void signal(Sharded &S, int me, cudaStream_t stream, int kind, uint64_t s
   }
 }
 static void wait(Sharded &S, int me, cudaStream_t stream, int kind, uint64_t seq, const std::vector<int> &from) {
-  if (seq == 0) return;
+  if (seq == 0 || S.emulate) return;
   Shard &m = S.sh[me];
   sel(m);
   WaitParams p;
@@ -304,6 +309,16 @@ static void push_subblock(Sharded &S, Shard &m, const std::vector<int> &fixed_po
     const uint64_t idx = insert_zeros(r << f0, ins) | fixed_mask;
     char *strided = m.data + idx * ab;
     char *packed = compact + (r << f0) * ab;
+    if (S.emulate) {
+      for (uint64_t g = 0; g < in_group; g++) {
+        char *sp = strided + g * 2 * run_bytes, *pp = packed + g * run_bytes;
+        if (scatter) memcpy(sp, pp, run_bytes);
+        else memcpy(pp, sp, run_bytes);
+      }
+      S.stat_copies++;
+      r += in_group;
+      continue;
+    }
     cudaStream_t st = only ? only : m.px[m.push_rr++ % nstreams];
     if (use_2d && in_group > 1) {
       if (scatter) B200_CUDA(cudaMemcpy2DAsync(strided, 2 * run_bytes, packed, run_bytes, run_bytes, in_group, cudaMemcpyDeviceToDevice, st));
@@ -447,6 +462,7 @@ static int enqueue_op(const Sharded &S, const ShOp &op, const std::vector<int> &
 }
 
 static void run_direct(Sharded &S, Shard &m, const ShOp &op, const std::vector<int> &pq) {
+  if (S.emulate) throw Error("sharded self-test: ops that need their own kernel are not emulated");
   std::vector<uint64_t> q(pq.begin(), pq.end());
   b200sv_handle h = (b200sv_handle)m.st;
   int rc = 0;
@@ -576,8 +592,43 @@ static void launch_pass(Sharded &S, Shard &m, const Step &st, int pass, const Sl
   S.stat_launches++;
 }
 
+// host version of the in-place all-to-all (self-test): amplitude with exchange positions l on the shard whose global
+// bits read g trades places with the amplitude whose positions read g on the shard whose bits read l
+template <typename C> static void emulate_inplace(Sharded &S, const Exchange &x) {
+  std::vector<int> pos(x.lpos, x.lpos + x.k);
+  std::sort(pos.begin(), pos.end());
+  InsertList ins;
+  ins.n = x.k;
+  for (int i = 0; i < x.k; i++) ins.pos[i] = (uint8_t)pos[i];
+  auto lmask = [&](uint32_t v) {
+    uint64_t m = 0;
+    for (int i = 0; i < x.k; i++)
+      if ((v >> i) & 1) m |= 1ull << x.lpos[i];
+    return m;
+  };
+  const uint64_t count = 1ull << (S.nl - x.k);
+  for (int me = 0; me < S.world; me++) {
+    const uint32_t g = gval_of(x, me);
+    for (uint32_t l = 0; l < (1u << x.k); l++) {
+      const int peer = peer_of(x, me, l);
+      if (peer <= me) continue;  // each unordered pair of sub-blocks once
+      C *a = reinterpret_cast<C *>(S.sh[me].data), *b = reinterpret_cast<C *>(S.sh[peer].data);
+      for (uint64_t j = 0; j < count; j++) {
+        const uint64_t base = insert_zeros(j, ins);
+        std::swap(a[base | lmask(l)], b[base | lmask(g)]);
+      }
+    }
+  }
+}
+
 static void exchange_inplace(Sharded &S, const Exchange &x) {
   NvtxRange nvtx("b200sv exchange (in place)");
+  if (S.emulate) {
+    if (S.precision == B200SV_F64) emulate_inplace<std::complex<double>>(S, x);
+    else emulate_inplace<std::complex<float>>(S, x);
+    S.stat_inplace++;
+    return;
+  }
   const uint64_t s_ready = ++S.seq[F_READY], s_done = ++S.seq[F_DONE];
   for (int me : S.local) signal(S, me, S.sh[me].st->stream, F_READY, s_ready, group_of(x, me, false));
   for (int me : S.local) {
@@ -653,7 +704,7 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
         if (i == 0) S.stat_overlapped_passes++;
       }
       sel(m);
-      B200_CUDA(cudaEventRecord(m.ev_pass[i % kEvRing], m.st->stream));
+      if (!S.emulate) B200_CUDA(cudaEventRecord(m.ev_pass[i % kEvRing], m.st->stream));
     }
   };
   auto issue_push = [&](int i) {    // pushes of slab i (copy engines), once the receivers' buffer is free again
@@ -661,13 +712,15 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
     for (int me : S.local) {
       Shard &m = S.sh[me];
       sel(m);
-      B200_CUDA(cudaStreamWaitEvent(m.xs, m.ev_pass[i % kEvRing], 0));
+      if (!S.emulate) B200_CUDA(cudaStreamWaitEvent(m.xs, m.ev_pass[i % kEvRing], 0));
       const uint64_t need_unstaged = c0_unstaged + (uint64_t)std::max(0, i - nbuf + 1);
       wait(S, me, m.xs, F_UNSTAGED, need_unstaged, group_of(x, me, false));
       const uint32_t my_g = gval_of(x, me);
       ProfScope ps_push(S, m, m.xs, PR_PUSH);
-      B200_CUDA(cudaEventRecord(m.ev_fork, m.xs));
-      for (int j = 0; j < S.push_streams; j++) B200_CUDA(cudaStreamWaitEvent(m.px[j], m.ev_fork, 0));
+      if (!S.emulate) {
+        B200_CUDA(cudaEventRecord(m.ev_fork, m.xs));
+        for (int j = 0; j < S.push_streams; j++) B200_CUDA(cudaStreamWaitEvent(m.px[j], m.ev_fork, 0));
+      }
       // receivers in XOR order: at step d every shard g sends to g ^ d, a perfect matching
       for (uint32_t dstep = 1; dstep < (1u << k); dstep++) {
         const uint32_t v = my_g ^ dstep;
@@ -676,7 +729,7 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
         const uint32_t slot = my_g < v ? my_g : my_g - 1;  // the receiver (id v) skips its own id
         push_subblock(S, m, fixed_pos, fixed_mask(v, i), peer.staging + (size_t)b * buf_bytes + (size_t)slot * slot_bytes);
       }
-      for (int j = 0; j < S.push_streams; j++) {
+      for (int j = 0; j < S.push_streams && !S.emulate; j++) {
         B200_CUDA(cudaEventRecord(m.ev_join[j], m.px[j]));
         B200_CUDA(cudaStreamWaitEvent(m.xs, m.ev_join[j], 0));
       }
@@ -691,8 +744,9 @@ static void exchange_staged(Sharded &S, const Exchange &x, const PassRef &before
       sel(m);
       const uint32_t my_g = gval_of(x, me);
       const char *src = m.staging + (size_t)b * buf_bytes;
-      if (S.unstage_dma) {
-        // copy engines again (unstage stream): the compute stream only waits for the result
+      if (S.unstage_dma || S.emulate) {
+        // copy engines again (unstage stream): the compute stream only waits for the result (the self-test takes
+        // this branch too: the same strided copies, as memcpy)
         wait(S, me, m.us, F_PUSHED, c0_pushed + i + 1, group_of(x, me, true));
         ProfScope ps_un(S, m, m.us, PR_UNSTAGE);
         for (uint32_t u = 0, slot = 0; u < (1u << k); u++) {
@@ -884,6 +938,67 @@ static void destroy(Sharded *S) {
   }
   cudaGetLastError();
   delete S;
+}
+
+static void restore_order_impl(Sharded &S) {
+  const int n = S.n, nl = S.nl;
+  std::vector<int> phys = S.phys, inv(n);
+  auto reinv = [&] { for (int q = 0; q < n; q++) inv[phys[q]] = q; };
+  Program prog;
+  std::vector<ShOp> ops;
+  auto add_x = [&](int lpos, int gbit) {
+    Step st;
+    st.type = 2;
+    st.x.k = 1;
+    st.x.lpos[0] = lpos;
+    st.x.gbit[0] = gbit;
+    prog.steps.push_back(std::move(st));
+  };
+  for (int g = nl; g < n; g++) {
+    reinv();
+    if (inv[g] == g) continue;
+    int p = phys[g];  // where logical qubit g lives now
+    if (p >= nl) {    // on another global position: pull it to a local one first
+      const int lpos = nl - 1, victim = inv[lpos];
+      add_x(lpos, p - nl);
+      phys[victim] = p;
+      phys[g] = lpos;
+      p = lpos;
+      reinv();
+    }
+    const int occupant = inv[g];
+    add_x(p, g - nl);
+    phys[occupant] = p;
+    phys[g] = g;
+  }
+  // the local permutation as SWAP gates riding tile passes (~9 transpositions per HBM pass instead of one mcswap
+  // pass each; 0/1 matrices: the amplitudes move bit-exactly)
+  std::vector<RankQueue> Q(S.world);
+  static const cd SWAPM[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
+  for (int q = 0; q < nl; q++) {
+    const int p = phys[q];
+    if (p == q) continue;
+    reinv();
+    const int other = inv[q];
+    const int pq[2] = {p, q};
+    for (int r = 0; r < S.world; r++) Q[r].push(2, pq, SWAPM);
+    phys[q] = q;
+    phys[other] = p;
+  }
+  if (!Q[0].nq.empty()) {
+    State proto;
+    proto.nq = S.nl;
+    proto.nstates = 1;
+    proto.precision = S.precision;
+    Step st;
+    st.type = 0;
+    st.plans.resize(S.world, nullptr);
+    for (int r = 0; r < S.world; r++)
+      st.plans[r] = tile_plan_build(proto, (int)Q[r].nq.size(), Q[r].nq.data(), Q[r].qubits.data(), Q[r].mats.data());
+    prog.steps.push_back(std::move(st));
+  }
+  run_program(S, prog, ops);
+  S.phys = phys;
 }
 
 }  // namespace b200sv
@@ -1149,6 +1264,67 @@ int b200sv_sharded_plan_only(int num_qubits, int precision, int world, uint64_t 
   });
 }
 
+// Executor self-test -- TEST INFRASTRUCTURE, no device involved: the register lives in `host_state` (2^n amplitudes,
+// shard r = the r-th contiguous slice), the program is compiled and scheduled exactly as apply_ops does and then
+// INTERPRETED in issue order: tile-pass parameter blocks (whole and slab-patched) by the tile engine's host
+// interpreter, pushes / unstages as the same strided copies with memcpy, in-place exchanges as host swaps; finally the
+// qubit order is restored (exchanges + SWAP passes).  Covers, on the CPU test tier, the index algebra of slabs, staging
+// slots and exchange groups and the issue order of the pipeline (a buffer reused too early shows up as wrong data).
+int b200sv_sharded_selftest(int num_qubits, int precision, int world, uint64_t staging_bytes, int nops, const int *kinds,
+                            const int *op_off, const int *op_qubits, const int64_t *data_off, const double *data,
+                            void *host_state, double *out8) {
+  return sguard([&] {
+    if (world < 1 || world > kMaxWorld || (world & (world - 1)) || !host_state) throw Error("sharded_selftest: bad arguments");
+    Sharded S;
+    int g = 0;
+    while ((1 << g) < world) g++;
+    S.n = num_qubits; S.gbits = g; S.nl = num_qubits - g; S.world = world; S.precision = precision;
+    if (S.nl < 4 || S.nl > 26) throw Error("sharded_selftest: 4..26 qubits per shard");
+    S.emulate = true;
+    S.sh.resize(world);
+    S.phys.resize(num_qubits);
+    for (int q = 0; q < num_qubits; q++) S.phys[q] = q;
+    if (const char *e = getenv("B200SV_SHARD_MIN_RUN_BITS")) S.min_run_bits = atoi(e);
+    if (const char *e = getenv("B200SV_SHARD_SLAB_BITS")) S.want_slab_bits = std::max(0, std::min(4, atoi(e)));
+    if (const char *e = getenv("B200SV_SHARD_STAGED")) S.allow_staged = atoi(e) != 0;
+    if (const char *e = getenv("B200SV_SHARD_MAX_RIDE")) S.max_ride = std::max(0, std::min(4, atoi(e)));
+    S.min_run_bits = std::max(1, std::min(S.min_run_bits, std::max(S.nl - 1, 1)));
+    S.staging_bytes = world > 1 ? (size_t)staging_bytes : 0;
+    const size_t slice_bytes = ((size_t)1 << S.nl) * S.amp_bytes();
+    std::vector<State> states(world);
+    std::vector<std::vector<char>> staging(world);
+    for (int r = 0; r < world; r++) {
+      Shard &m = S.sh[r];
+      m.rank = r;
+      m.local = true;
+      states[r].nq = S.nl;
+      states[r].precision = precision;
+      states[r].global_nq = num_qubits;
+      states[r].chunk_index = (uint64_t)r;
+      states[r].selftest_host = (char *)host_state + (size_t)r * slice_bytes;
+      m.st = &states[r];
+      m.data = (char *)states[r].selftest_host;
+      staging[r].resize(S.staging_bytes + 16);
+      m.staging = staging[r].data();
+      S.local.push_back(r);
+    }
+    std::vector<ShOp> ops = parse_ops(num_qubits, nops, kinds, op_off, op_qubits, data_off, data);
+    {
+      std::unique_ptr<Program> prog = compile(S, ops);
+      run_program(S, *prog, ops);
+    }
+    if (out8) {
+      out8[0] = (double)S.stat_passes; out8[1] = (double)S.stat_exchanges; out8[2] = (double)S.stat_staged;
+      out8[3] = (double)S.stat_inplace; out8[4] = 0; out8[5] = (double)S.stat_copies; out8[6] = S.stat_bytes_exchanged;
+      out8[7] = (double)S.stat_overlapped_passes;
+    }
+    // restore the qubit order with the same machinery (what b200sv_sharded_restore_order does on a handle)
+    restore_order_impl(S);
+    for (int r = 0; r < world; r++) S.sh[r].st = nullptr;  // the States are stack objects
+    S.sh.clear();
+  });
+}
+
 int b200sv_sharded_stats(b200sv_sharded_handle h, double *out8) {
   return sguard([&] {
     out8[0] = (double)SH->stat_passes;
@@ -1215,67 +1391,7 @@ int b200sv_sharded_elapsed_ms(b200sv_sharded_handle h, double *ms) {
 // test_chunk.py:31-168 asserts exact equality): global positions first (pairwise exchanges), then the local
 // permutation by transpositions (mcswap passes).
 int b200sv_sharded_restore_order(b200sv_sharded_handle h) {
-  return sguard([&] {
-    Sharded &S = *SH;
-    const int n = S.n, nl = S.nl;
-    std::vector<int> phys = S.phys, inv(n);
-    auto reinv = [&] { for (int q = 0; q < n; q++) inv[phys[q]] = q; };
-    Program prog;
-    std::vector<ShOp> ops;
-    auto add_x = [&](int lpos, int gbit) {
-      Step st;
-      st.type = 2;
-      st.x.k = 1;
-      st.x.lpos[0] = lpos;
-      st.x.gbit[0] = gbit;
-      prog.steps.push_back(std::move(st));
-    };
-    for (int g = nl; g < n; g++) {
-      reinv();
-      if (inv[g] == g) continue;
-      int p = phys[g];  // where logical qubit g lives now
-      if (p >= nl) {    // on another global position: pull it to a local one first
-        const int lpos = nl - 1, victim = inv[lpos];
-        add_x(lpos, p - nl);
-        phys[victim] = p;
-        phys[g] = lpos;
-        p = lpos;
-        reinv();
-      }
-      const int occupant = inv[g];
-      add_x(p, g - nl);
-      phys[occupant] = p;
-      phys[g] = g;
-    }
-    // the local permutation as SWAP gates riding tile passes (~9 transpositions per HBM pass instead of one mcswap
-    // pass each; 0/1 matrices: the amplitudes move bit-exactly)
-    std::vector<RankQueue> Q(S.world);
-    static const cd SWAPM[16] = {1, 0, 0, 0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 1};
-    for (int q = 0; q < nl; q++) {
-      const int p = phys[q];
-      if (p == q) continue;
-      reinv();
-      const int other = inv[q];
-      const int pq[2] = {p, q};
-      for (int r = 0; r < S.world; r++) Q[r].push(2, pq, SWAPM);
-      phys[q] = q;
-      phys[other] = p;
-    }
-    if (!Q[0].nq.empty()) {
-      State proto;
-      proto.nq = S.nl;
-      proto.nstates = 1;
-      proto.precision = S.precision;
-      Step st;
-      st.type = 0;
-      st.plans.resize(S.world, nullptr);
-      for (int r = 0; r < S.world; r++)
-        st.plans[r] = tile_plan_build(proto, (int)Q[r].nq.size(), Q[r].nq.data(), Q[r].qubits.data(), Q[r].mats.data());
-      prog.steps.push_back(std::move(st));
-    }
-    run_program(S, prog, ops);
-    S.phys = phys;
-  });
+  return sguard([&] { restore_order_impl(*SH); });
 }
 
 // per-shard squared norms (entries of shards hosted elsewhere stay 0: sum / gather over processes)

@@ -1868,37 +1868,76 @@ uint64_t tile_plan_pass_mask(const TilePlan *plan, int i) {
   if (shift) m |= 1ull;
   return m;
 }
+// host evaluation of a captured small-state pass (scheduler / executor self-tests only)
+template <typename T>
+static void emulate_dense_gate(void *host, int nq, const TilePlannedPass &pp) {
+  typedef std::complex<T> C;
+  C *psi = reinterpret_cast<C *>(host);
+  const cd_t *M = reinterpret_cast<const cd_t *>(pp.dmat);  // column major
+  const int k = pp.dnq, dim = 1 << k;
+  for (uint64_t i = 0; i < (1ull << nq); i++) {
+    bool lead = true;
+    for (int b = 0; b < k; b++) lead = lead && !((i >> pp.dq[b]) & 1);
+    if (!lead) continue;
+    cd_t x[4], y[4];
+    uint64_t idx[4];
+    for (int e = 0; e < dim; e++) {
+      idx[e] = i;
+      for (int b = 0; b < k; b++)
+        if ((e >> b) & 1) idx[e] |= 1ull << pp.dq[b];
+      x[e] = cd_t(psi[idx[e]]);
+    }
+    for (int r = 0; r < dim; r++) {
+      y[r] = 0;
+      for (int c = 0; c < dim; c++) y[r] += M[r + dim * c] * x[c];
+    }
+    for (int e = 0; e < dim; e++) psi[idx[e]] = C(y[e]);
+  }
+}
+
 void tile_plan_launch(State &s, const TilePlan *plan, int i, const SlabSpec *slab) {
   const TilePlannedPass &pp = plan->passes.at(i);
   const bool has_slab = slab && slab->nbits > 0;
   if (pp.variant == TV_DENSE) {
     if (has_slab) throw Error("tile plan: this pass cannot be restricted to a slab");
+    if (s.selftest_host) {
+      if (s.precision == B200SV_F64) emulate_dense_gate<double>(s.selftest_host, s.nq, pp);
+      else emulate_dense_gate<float>(s.selftest_host, s.nq, pp);
+      return;
+    }
     launch_dense(s, pp.dq, pp.dnq, nullptr, 0, pp.dmat);
     return;
   }
-  if (!has_slab) {
-    launch_tile_variant(s, pp.p, pp.variant, (double2 *)s.data, slab ? slab->sm_limit : 0);
+  const TilePassParams *use = &pp.p;
+  uint64_t offset = 0;  // in amplitudes
+  static thread_local TilePassParams q;
+  if (has_slab) {
+    q = pp.p;
+    const int shift = pp.variant == TV_PIPE2_F32 ? 1 : 0;
+    std::vector<int> pos(q.ins.pos, q.ins.pos + q.ins.n);
+    for (int b = 0; b < slab->nbits; b++) {
+      const int sp = slab->pos[b];
+      if (sp < shift || sp >= s.nq) throw Error("tile plan: slab bit out of range");
+      if (std::find(pos.begin(), pos.end(), sp - shift) != pos.end()) throw Error("tile plan: slab bit lies inside the pass's tile");
+      pos.push_back(sp - shift);
+      if ((slab->value >> b) & 1u) offset |= 1ull << sp;
+    }
+    std::sort(pos.begin(), pos.end());
+    if ((int)pos.size() > kMaxInsert) throw Error("tile plan: too many fixed bits");
+    q.ins.n = (int)pos.size();
+    for (size_t u = 0; u < pos.size(); u++) q.ins.pos[u] = (uint8_t)pos[u];
+    q.ntiles = pp.p.ntiles >> slab->nbits;
+    use = &q;
+  }
+  if (s.selftest_host) {  // executor self-test: interpret the (slab-patched) parameter block on the host slice
+    char *hb = (char *)s.selftest_host + offset * s.amp_bytes();
+    if (pp.variant == TV_PIPE2_F32) emulate_tile_pass<float>(*use, hb, nullptr, true);
+    else if (pp.variant == TV_PASS11 || pp.variant == TV_PIPE3_FAST) throw Error("tile plan: 2^11 tiles are not emulated");
+    else emulate_tile_pass<double>(*use, hb, nullptr, false);
     return;
   }
-  static thread_local TilePassParams q;
-  q = pp.p;
-  const int shift = pp.variant == TV_PIPE2_F32 ? 1 : 0;
-  uint64_t offset = 0;  // in amplitudes
-  std::vector<int> pos(q.ins.pos, q.ins.pos + q.ins.n);
-  for (int b = 0; b < slab->nbits; b++) {
-    const int sp = slab->pos[b];
-    if (sp < shift || sp >= s.nq) throw Error("tile plan: slab bit out of range");
-    if (std::find(pos.begin(), pos.end(), sp - shift) != pos.end()) throw Error("tile plan: slab bit lies inside the pass's tile");
-    pos.push_back(sp - shift);
-    if ((slab->value >> b) & 1u) offset |= 1ull << sp;
-  }
-  std::sort(pos.begin(), pos.end());
-  if ((int)pos.size() > kMaxInsert) throw Error("tile plan: too many fixed bits");
-  q.ins.n = (int)pos.size();
-  for (size_t u = 0; u < pos.size(); u++) q.ins.pos[u] = (uint8_t)pos[u];
-  q.ntiles = pp.p.ntiles >> slab->nbits;
   char *base = (char *)s.data + offset * s.amp_bytes();
-  launch_tile_variant(s, q, pp.variant, (double2 *)base, slab->sm_limit);
+  launch_tile_variant(s, *use, pp.variant, (double2 *)base, slab ? slab->sm_limit : 0);
 }
 
 #ifdef B200SV_TILE_PROFILE

@@ -575,6 +575,26 @@ class ShardedState:
         keys = ("passes", "exchanges", "staged", "inplace", "passes_overlapped", "slabs_max", "slabs_min", "qubit_swaps")
         return {k: int(v) for k, v in zip(keys, out)}
 
+    @classmethod
+    def selftest(cls, n, world, ops, staging_bytes, host_state):
+        """Host-only interpretation of what apply_ops + restore_order would do (no device): `host_state` (2^n complex,
+        logical order) is transformed in place; returns the run's statistics."""
+        import ctypes as C
+        from . import capi
+        kinds, off, qs, doff, data = cls.encode(ops)
+        if not host_state.flags["C_CONTIGUOUS"] or host_state.size != 1 << n:
+            raise ValueError("host_state must be a contiguous array of 2^n amplitudes")
+        prec = 64 if host_state.dtype == np.complex128 else 32
+        out = np.zeros(8)
+        capi.check(capi.lib().b200sv_sharded_selftest(
+            int(n), prec, int(world), C.c_uint64(int(staging_bytes)), int(kinds.size),
+            kinds.ctypes.data_as(C.POINTER(C.c_int)), off.ctypes.data_as(C.POINTER(C.c_int)),
+            qs.ctypes.data_as(C.POINTER(C.c_int)), doff.ctypes.data_as(C.POINTER(C.c_int64)),
+            data.ctypes.data_as(C.POINTER(C.c_double)), host_state.ctypes.data_as(C.c_void_p),
+            out.ctypes.data_as(C.POINTER(C.c_double))))
+        keys = ("passes", "exchanges", "staged", "inplace", "launches", "copies", "bytes_sent_per_shard", "overlapped_passes")
+        return {k: (float(v) if k.startswith("bytes") else int(v)) for k, v in zip(keys, out)}
+
     # ---- execution
     def initialize(self):
         self._capi.check(self._lib.b200sv_sharded_initialize(self.h))

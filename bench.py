@@ -33,8 +33,9 @@ def host_cores():
 
 # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU legs (reference arm, cpu_baseline) are meant to use every
 # host core, and libgomp reads the variable when it is loaded -- so fix it before anything OpenMP-linked is imported.
-if "reference" in sys.argv or os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
-    os.environ["OMP_NUM_THREADS"] = str(host_cores())
+if "reference" in sys.argv or int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    if os.environ.get("OMP_NUM_THREADS", "") in ("", "1"):
+        os.environ["OMP_NUM_THREADS"] = str(host_cores())
 
 import numpy as np  # noqa: E402
 

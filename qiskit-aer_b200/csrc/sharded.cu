@@ -954,6 +954,29 @@ static void restore_order_impl(Sharded &S) {
     st.x.gbit[0] = gbit;
     prog.steps.push_back(std::move(st));
   };
+  // global positions: when every logical qubit that belongs on a global position currently sits on a LOCAL one, a single
+  // k-qubit all-to-all brings them all home ((1 - 2^-k) of the slice crosses the links once instead of k half-slice
+  // exchanges); otherwise one pairwise exchange per position
+  {
+    std::vector<int> want;
+    bool all_local = true;
+    for (int g = nl; g < n; g++)
+      if (phys[g] != g) { want.push_back(g); all_local = all_local && phys[g] < nl; }
+    if (want.size() >= 2 && want.size() <= 4 && all_local) {
+      reinv();
+      Step st;
+      st.type = 2;
+      st.x.k = (int)want.size();
+      for (size_t i = 0; i < want.size(); i++) {
+        const int g = want[i], lpos = phys[g], occupant = inv[g];
+        st.x.lpos[i] = lpos;
+        st.x.gbit[i] = g - nl;
+        phys[occupant] = lpos;
+        phys[g] = g;
+      }
+      prog.steps.push_back(std::move(st));
+    }
+  }
   for (int g = nl; g < n; g++) {
     reinv();
     if (inv[g] == g) continue;

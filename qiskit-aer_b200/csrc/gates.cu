@@ -1089,14 +1089,10 @@ __global__ void __launch_bounds__(288) diag_layer_kernel(cx<T> *__restrict__ psi
   for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x, it++) {
     const double2 *sM = sMbuf[it & 1];
     const double2 sS = sSbuf[it & 1];
-    if (tid >= 256) {
-      if (c + gridDim.x < nchunks) produce(c + gridDim.x, (it + 1) & 1);
-      __syncthreads();
-      continue;
-    }
+    if (tid >= 256 && c + gridDim.x < nchunks) produce(c + gridDim.x, (it + 1) & 1);
     // ---- thread id = chunk-local bits 0..7 (consecutive threads touch consecutive amplitudes: coalesced), the 16
     // amplitudes of a thread differ in chunk-local bits 8..11.  Thread factor over its id bits, then the 16 phases by doubling.
-    const bool active = lo_bits == 12 || (lo_bits >= 8 ? true : tid < (1 << lo_bits));
+    const bool active = tid < 256 && (lo_bits >= 8 || tid < (1 << lo_bits));
     const int ebits = lo_bits >= 8 ? lo_bits - 8 : 0;   // element bits that exist in this chunk (4 for full chunks)
     if (active) {
       double2 f = sS;

@@ -1047,11 +1047,12 @@ struct DiagLayerParams {
   int nq;
 };
 __device__ __forceinline__ double2 cmulz(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-template <typename T>
-__global__ void __launch_bounds__(288) diag_layer_kernel(cx<T> *__restrict__ psi, const __grid_constant__ DiagLayerParams p,
+template <typename T, int LB>
+__global__ void __launch_bounds__(288, LB == 12 ? 1 : 2) diag_layer_kernel(cx<T> *__restrict__ psi, const __grid_constant__ DiagLayerParams p,
                                                          uint64_t nchunks, int lo_bits) {
   extern __shared__ double2 sTab[];            // A[nq], then G[nq][nq]: staged once per CTA
   __shared__ double2 sMbuf[2][12], sSbuf[2];   // per-chunk factors, double buffered
+  constexpr int EB = LB - 8, NE = 1 << EB;     // element bits / amplitudes per thread (chunk = 2^LB amplitudes)
   const int tid = threadIdx.x, nq = p.nq;
   double2 *sA = sTab, *sG = sTab + nq;
   for (int e = tid; e < nq + nq * nq; e += blockDim.x) sTab[e] = p.A[e];  // A and G are contiguous in device memory
@@ -1093,8 +1094,14 @@ __global__ void __launch_bounds__(288) diag_layer_kernel(cx<T> *__restrict__ psi
     // ---- thread id = chunk-local bits 0..7 (consecutive threads touch consecutive amplitudes: coalesced), the 16
     // amplitudes of a thread differ in chunk-local bits 8..11.  Thread factor over its id bits, then the 16 phases by doubling.
     const bool active = tid < 256 && (lo_bits >= 8 || tid < (1 << lo_bits));
-    const int ebits = lo_bits >= 8 ? lo_bits - 8 : 0;   // element bits that exist in this chunk (4 for full chunks)
+    const int ebits = lo_bits >= 8 ? lo_bits - 8 : 0;   // element bits that exist in this chunk (EB for full chunks)
     if (active) {
+      // loads first: their latency runs under the phase arithmetic below
+      cx<T> *base = psi + (c << lo_bits) + (uint64_t)tid;
+      cx<T> v[NE];
+#pragma unroll
+      for (int e = 0; e < NE; e++)
+        if (e < (1 << ebits)) v[e] = base[(uint64_t)e << 8];
       double2 f = sS;
 #pragma unroll
       for (int u = 0; u < 8; u++) {
@@ -1104,9 +1111,9 @@ __global__ void __launch_bounds__(288) diag_layer_kernel(cx<T> *__restrict__ psi
         for (int v = u + 1; v < 8; v++)
           if ((tid >> v) & 1) f = cmulz(f, sG[u * nq + v]);
       }
-      double2 w[4];  // multiplier of element bit e (position 8 + e) given this thread's id bits
+      double2 w[EB];  // multiplier of element bit e (position 8 + e) given this thread's id bits
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
+      for (int e = 0; e < EB; e++) {
         double2 m = make_double2(1.0, 0.0);
         if (e < ebits) {
           m = sM[8 + e];
@@ -1116,10 +1123,10 @@ __global__ void __launch_bounds__(288) diag_layer_kernel(cx<T> *__restrict__ psi
         }
         w[e] = m;
       }
-      double2 ph[16];
+      double2 ph[NE];
       ph[0] = f;
 #pragma unroll
-      for (int e = 0; e < 4; e++)
+      for (int e = 0; e < EB; e++)
 #pragma unroll
         for (int j = 0; j < (1 << e); j++) {
           double2 m = cmulz(ph[j], w[e]);
@@ -1130,13 +1137,8 @@ __global__ void __launch_bounds__(288) diag_layer_kernel(cx<T> *__restrict__ psi
           }
           ph[j | (1 << e)] = m;
         }
-      cx<T> *base = psi + (c << lo_bits) + (uint64_t)tid;
-      cx<T> v[16];
 #pragma unroll
-      for (int e = 0; e < 16; e++)
-        if (e < (1 << ebits)) v[e] = base[(uint64_t)e << 8];
-#pragma unroll
-      for (int e = 0; e < 16; e++)
+      for (int e = 0; e < NE; e++)
         if (e < (1 << ebits))
           base[(uint64_t)e << 8] = mk<T>((T)(ph[e].x * (double)v[e].x - ph[e].y * (double)v[e].y),
                                          (T)(ph[e].x * (double)v[e].y + ph[e].y * (double)v[e].x));
@@ -1180,8 +1182,21 @@ void launch_diag_layer(State &s, int ngates, const int *nq, const uint64_t *qubi
   p.G = (const double2 *)(dm + (size_t)n * 16);
   p.C = make_double2(Cc.real(), Cc.imag());
   p.nq = n;
-  const int lo_bits = std::min(12, n);
+  // chunk = 2^11 amplitudes (8 per thread, two CTAs per SM: one CTA's loads run under the other's arithmetic) for double,
+  // B200SV_DIAG_LAYER_CHUNK_BITS = 12 selects the 16-per-thread form
+  static const int env_lb = [] { const char *e = getenv("B200SV_DIAG_LAYER_CHUNK_BITS"); return e ? atoi(e) : 11; }();
+  const int LB = env_lb == 12 ? 12 : 11;
+  const int lo_bits = std::min(LB, n);
   const size_t smem = ((size_t)n + (size_t)n * n) * 16;  // <= 26 KiB at 40 qubits
+  auto launch = [&](void *data, int grid, uint64_t nchunks) {
+    if (s.precision == B200SV_F64) {
+      if (LB == 12) diag_layer_kernel<double, 12><<<grid, 288, smem, s.stream>>>((double2 *)data, p, nchunks, lo_bits);
+      else diag_layer_kernel<double, 11><<<grid, 288, smem, s.stream>>>((double2 *)data, p, nchunks, lo_bits);
+    } else {
+      if (LB == 12) diag_layer_kernel<float, 12><<<grid, 288, smem, s.stream>>>((float2 *)data, p, nchunks, lo_bits);
+      else diag_layer_kernel<float, 11><<<grid, 288, smem, s.stream>>>((float2 *)data, p, nchunks, lo_bits);
+    }
+  };
   // batched containers: every state is its own run of chunks with the same layer (hi wraps per state)
   const uint64_t chunks_per_state = 1ull << (n - lo_bits);
   if (s.nstates != 1 && chunks_per_state != 1) {
@@ -1190,16 +1205,14 @@ void launch_diag_layer(State &s, int ngates, const int *nq, const uint64_t *qubi
       v.nstates = 1;
       v.data = (char *)s.data + ((uint64_t)st << n) * s.amp_bytes();
       const int grid = (int)std::min<uint64_t>(chunks_per_state, (uint64_t)s.num_sms * 8);
-      if (s.precision == B200SV_F64) diag_layer_kernel<double><<<grid, 288, smem, s.stream>>>((double2 *)v.data, p, chunks_per_state, lo_bits);
-      else diag_layer_kernel<float><<<grid, 288, smem, s.stream>>>((float2 *)v.data, p, chunks_per_state, lo_bits);
+      launch(v.data, grid, chunks_per_state);
     }
     B200_CUDA(cudaGetLastError());
     return;
   }
   const uint64_t nchunks = s.nstates == 1 ? chunks_per_state : (uint64_t)s.nstates;
   const int grid = (int)std::min<uint64_t>(nchunks, (uint64_t)s.num_sms * 8);
-  if (s.precision == B200SV_F64) diag_layer_kernel<double><<<grid, 288, smem, s.stream>>>((double2 *)s.data, p, nchunks, lo_bits);
-  else diag_layer_kernel<float><<<grid, 288, smem, s.stream>>>((float2 *)s.data, p, nchunks, lo_bits);
+  launch(s.data, grid, nchunks);
   B200_CUDA(cudaGetLastError());
 }
 

@@ -61,6 +61,8 @@ __host__ __device__ inline uint32_t phys_slot(uint32_t j) {
 
 struct TileRound {
   uint16_t eoff[16];            // phys(sum_i bit_i(e) << pos[i]) for the 16 elements of a sub-block
+  uint16_t eoff_ld[16];         // slot rounds of noisy passes load through this copy: eoff with the round's bare cx
+                                // gates folded in as a permutation of the elements (== eoff without cx slots)
   uint16_t gbit[8];             // phys(1 << tpos[i]): contribution of group-id bit i
   uint8_t ngates;
   uint8_t npre;                 // number of valid entries in pre[]
@@ -187,6 +189,17 @@ __device__ __forceinline__ void apply_pauli_reg(double2 (&a)[16], int code) {
   }
 }
 
+// Bare cx gates in slot rounds (batched noisy passes).  Noisy circuits keep their cx gates bare -- the sampled Paulis
+// around them stop the host from absorbing neighbouring 1-qubit gates -- and a cx only permutes the 16 amplitudes of a
+// register block: the host folds that permutation into the round's LOAD offsets (TileRound::eoff_ld), the kernel just
+// skips the slot's arithmetic.  Half of a noisy pass's gate slots then cost no DFMA and no instruction at all.
+// kSlotCxLo / kSlotCxHi = cx controlled by the slot's lower / upper round bit; other forms = dense 4x4.
+constexpr int kSlotCxLo = 24, kSlotCxHi = 25;
+template <int P0, int P1>
+__device__ __forceinline__ void slot_gate(double2 (&a)[16], const int form, const double2 *__restrict__ m) {
+  if (form < kSlotCxLo) apply2<P0, P1>(a, m);  // `form` comes from the parameter block: uniform branch
+}
+
 // Sampled noise folded into a gate round: the Pauli codes (staged per tile in shared memory) of the ops that precede
 // the round's gates on its four bits.  Identity draws (99 %) cost four shared-memory bytes and a vote; a hit takes the
 // block through registers once more (same thread, same slots: no synchronisation) before the straight-line gate code,
@@ -242,9 +255,14 @@ __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int
       if (fast == 2) {
         double2 a[16];
 #pragma unroll
-        for (int e = 0; e < 16; e++) a[e] = tile[base ^ R.eoff[e]];
-        apply2<0, 1>(a, p.mats[R.gate[0]]);
-        apply2<2, 3>(a, p.mats[R.gate[1]]);
+        for (int e = 0; e < 16; e++) a[e] = tile[base ^ (MODE == 4 ? R.eoff_ld[e] : R.eoff[e])];
+        if (MODE == 4) {
+          slot_gate<0, 1>(a, R.form[0], p.mats[R.gate[0]]);
+          slot_gate<2, 3>(a, R.form[1], p.mats[R.gate[1]]);
+        } else {
+          apply2<0, 1>(a, p.mats[R.gate[0]]);
+          apply2<2, 3>(a, p.mats[R.gate[1]]);
+        }
 #pragma unroll
         for (int e = 0; e < 16; e++)
           if (valid) tile[base ^ R.eoff[e]] = a[e];
@@ -271,8 +289,9 @@ __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int
       } else if (MODE == 1 || MODE == 4 || fast == 1) {
         double2 a[16];
 #pragma unroll
-        for (int e = 0; e < 16; e++) a[e] = tile[base ^ R.eoff[e]];
-        apply2<0, 1>(a, p.mats[R.gate[0]]);
+        for (int e = 0; e < 16; e++) a[e] = tile[base ^ (MODE == 4 ? R.eoff_ld[e] : R.eoff[e])];
+        if (MODE == 4) slot_gate<0, 1>(a, R.form[0], p.mats[R.gate[0]]);
+        else apply2<0, 1>(a, p.mats[R.gate[0]]);
 #pragma unroll
         for (int e = 0; e < 16; e++)
           if (valid) tile[base ^ R.eoff[e]] = a[e];
@@ -775,6 +794,19 @@ static void emulate_tile_pass(const TilePassParams &p, void *host, const uint8_t
               }
             }
           }
+          if (R.fast == 1 || R.fast == 2) {
+            // the kernels of noisy passes load the block through eoff_ld (bare cx slots folded in as a permutation of the
+            // elements) AFTER the pre-Paulis went through shared memory: replay exactly that table
+            C b[16];
+            for (int e = 0; e < 16; e++) {
+              int src = -1;
+              for (int x = 0; x < 16; x++)
+                if (R.eoff[x] == R.eoff_ld[e]) src = x;
+              if (src < 0) throw Error("selftest: eoff_ld is not a permutation of eoff");
+              b[e] = a[src];
+            }
+            std::copy(b, b + 16, a);
+          }
           if (R.fast == 5) {
             const int code = codes[(size_t)p.pauli_slot[R.gate[0]] * p.nstates + (t >> p.state_shift)];
             for (int i = 0; i < na && code; i++) {
@@ -787,6 +819,7 @@ static void emulate_tile_pass(const TilePassParams &p, void *host, const uint8_t
             }
           }
           for (int k = 0; k < (R.fast == 5 ? 0 : R.ngates); k++) {
+            if (R.fast && R.form[k] >= kSlotCxLo) continue;  // bare cx slot: already applied by the permuted load
             const int form = R.fast ? (k == 0 ? 0 : 5) : R.form[k];
             C M[16];
             const double2 *m = p.mats[R.gate[k]];
@@ -853,7 +886,7 @@ static std::vector<int> build_round(TileRound &R, const std::vector<int> &round_
     uint32_t j = 0;
     for (int i = 0; i < 4; i++)
       if ((e >> i) & 1) j |= 1u << pos[i];
-    R.eoff[e] = (uint16_t)phys_slot(j);
+    R.eoff[e] = R.eoff_ld[e] = (uint16_t)phys_slot(j);
   }
   std::vector<int> free_pos;
   for (int u = 0; u < kTB; u++)
@@ -940,9 +973,30 @@ static void plan_segments(const std::vector<std::vector<int>> &round_pos, int kT
 // qubits, which the host multiplies into one 4x4 (v x u: the same 16 DFMA per amplitude as the two gates apart, but no
 // form dispatch).  Per-state Pauli ops (sampled noise) get rounds of their own, which cost a byte load unless the state
 // drew a non-identity Pauli.  Fills p.rounds / p.mats / p.nrounds; returns true when the pass contains Pauli rounds.
+// 0, or kSlotCxLo / kSlotCxHi when g is exactly CX controlled by its first / second qubit (column-major 4x4, index =
+// bit(q[0]) + 2 bit(q[1]))
+static int bare_cx_form(const QGate &g) {
+  if (!g.mat || g.nq != 2) return 0;
+  static const int lo[4] = {0, 3, 2, 1}, hi[4] = {0, 1, 3, 2};  // row holding the 1 of column c
+  bool is_lo = true, is_hi = true;
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++) {
+      const double re = g.mat[2 * (r + 4 * c)], im = g.mat[2 * (r + 4 * c) + 1];
+      if (im != 0.0 || re != (r == lo[c] ? 1.0 : 0.0)) is_lo = false;
+      if (im != 0.0 || re != (r == hi[c] ? 1.0 : 0.0)) is_hi = false;
+    }
+  return is_lo ? kSlotCxLo : is_hi ? kSlotCxHi : 0;
+}
 static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates, const std::vector<int> &sel,
                               const std::vector<int> &tile_bits, std::vector<int> &leftover) {
   constexpr int kTB = 12;
+  // bare cx gates as register renamings: only in passes that carry sampled noise (they run the MODE 4 kernels, the
+  // only ones that read the slot forms)
+  static const int env_cx = [] { const char *e = getenv("B200SV_TILE_CX_SLOTS"); return e ? atoi(e) : 1; }();
+  bool allow_cx = false, any_cx = false;
+  for (int gi : sel) allow_cx = allow_cx || !gates[gi].mat;
+  allow_cx = allow_cx && env_cx;
+  auto slot_form = [&](const std::vector<int> &sl) { return allow_cx && !sl.empty() ? bare_cx_form(gates[sl[0]]) : 0; };
   auto tile_pos = [&](int q) {
     for (int u = 0; u < kTB; u++)
       if (tile_bits[u] == q) return u;
@@ -1015,7 +1069,8 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
     std::vector<int> rp;
     for (int q = 0; q < 64; q++)
       if ((rq >> q) & 1) rp.push_back(tile_pos(q));
-    nmat += sr.kind == 5 ? 0 : sr.kind;
+    if (sr.kind != 5)
+      for (int k = 0; k < sr.kind; k++) nmat += slot_form(sr.slot[k]) ? 0 : 1;
     npaul += sr.kind == 5 ? 1 : (int)sr.pre.size();
     rounds.push_back(sr);
     round_pos.push_back(rp);
@@ -1080,6 +1135,17 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
         any_pauli = true;
       }
       for (int k = 0; k < sr.kind; k++) {
+        if (const int cxf = slot_form(sr.slot[k])) {  // no matrix, no arithmetic: output e = input e ^ (ctl(e) << tgt)
+          R.form[k] = (uint8_t)cxf;
+          R.gate[k] = 0;
+          any_cx = true;
+          const int ctl = 2 * k + (cxf == kSlotCxLo ? 0 : 1), tgt = 2 * k + (cxf == kSlotCxLo ? 1 : 0);
+          uint16_t ld[16];
+          for (int e = 0; e < 16; e++) ld[e] = R.eoff_ld[e ^ (((e >> ctl) & 1) << tgt)];
+          std::copy(ld, ld + 16, R.eoff_ld);
+          continue;
+        }
+        if (nm >= kMaxTileGates) throw Error("tile pass: matrix slots exhausted");
         double2 *M = p.mats[nm];
         for (int i = 0; i < 4; i++)
           for (int j = 0; j < 4; j++) M[i * 4 + j] = mk<double>(M4[k][i + 4 * j].real(), M4[k][i + 4 * j].imag());
@@ -1089,7 +1155,7 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
     }
     R.sync = (r == seg_end[r] - 1);
   }
-  return any_pauli;
+  return any_pauli || any_cx;
 }
 
 // ------------------------------------------------------------------------------------------ planned passes
@@ -1336,7 +1402,25 @@ struct PassPacker {
   std::vector<int> pending;  // undone predecessors
   std::vector<char> done;
   int ndone = 0;
+  bool noisy = false;  // the sequence carries sampled-noise Paulis: slot rounds with bare-cx slots (build_slot_rounds)
+  // matrix-slot cost of an op in half slots: two 1-qubit gates share a 4x4, a bare cx of a noisy pass needs none
+  int half_slots(const QGate &g) const {
+    if (!g.mat) return 0;
+    if (!noisy) return 2;
+    return g.nq == 1 ? 1 : (bare_cx_form(g) ? 0 : 2);
+  }
   explicit PassPacker(const std::vector<QGate> &g) : gates(g), succ(g.size()), pending(g.size(), 0), done(g.size(), 0) {
+    static const int env_cx = [] { const char *e = getenv("B200SV_TILE_CX_SLOTS"); return e ? atoi(e) : 1; }();
+    bool any_diag2 = false;  // diagonal 2-qubit gates send their pass to the generic rounds: one matrix per gate there
+    for (const QGate &x : g) {
+      noisy = noisy || (!x.mat && env_cx);
+      any_diag2 = any_diag2 || (x.mat && x.nq == 2 && is_diag(x));
+    }
+    static const bool slot_rounds = [] {  // the debugging knobs that turn slot rounds off (run_tile_pass)
+      const char *a = getenv("B200SV_TILE_SLOTS"), *b = getenv("B200SV_TILE_PIPE");
+      return (a ? atoi(a) : 1) != 0 && (b ? atoi(b) : 2) != 0;
+    }();
+    noisy = noisy && !any_diag2 && slot_rounds;
     int last[64];
     std::fill(last, last + 64, -1);
     for (int i = 0; i < (int)g.size(); i++)
@@ -1359,7 +1443,7 @@ struct PassPacker {
       for (size_t c = 0; c < cand.size(); c++) {
         const int i = cand[c];
         const uint64_t m = qmask(gates[i]);
-        if (gates[i].mat && ndense >= max_dense) continue;
+        if (gates[i].mat && ndense + half_slots(gates[i]) > 2 * max_dense) continue;
         if (__builtin_popcountll(Q | m) > cap) continue;
         const int nw = __builtin_popcountll(m & ~Q);
         int sc = 0;
@@ -1373,7 +1457,7 @@ struct PassPacker {
       cand.erase(cand.begin() + best_at);
       sel.push_back(best);
       Q |= qmask(gates[best]);
-      ndense += gates[best].mat != nullptr;
+      ndense += half_slots(gates[best]);
       for (int sx : succ[best])
         if (--pp[sx] == 0) cand.push_back(sx);
     }
@@ -1689,7 +1773,8 @@ int apply_gate_sequence(State &s, int ngates, const int *nq, const uint64_t *qub
         off[i + 1] = (int)qs.size();
       }
       int nblocks = 0;
-      fuse_assign(ngates, off.data(), qs.data(), isd.data(), 4, 64, 62, blk.data(), &nblocks);
+      static const int env_dense = [] { const char *e = getenv("B200SV_LAYER_DENSE_QUBITS"); return e ? std::min(12, std::max(2, atoi(e))) : 5; }();
+      fuse_assign(ngates, off.data(), qs.data(), isd.data(), env_dense, 64, 62, blk.data(), &nblocks);
       std::vector<std::vector<int>> members(nblocks);
       for (int i = 0; i < ngates; i++) members[blk[i]].push_back(i);
       int passes = 0;

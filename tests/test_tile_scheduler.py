@@ -195,6 +195,46 @@ def test_scheduler_folds_noise_paulis_into_the_next_gate_round():
         assert np.max(np.abs(got[s_i] - o.vector())) < 1e-12
 
 
+_PAULI = [np.eye(2), np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1, -1])]
+_CX_FIRST_CONTROLS = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=np.complex128)   # index = bit(q0) + 2 bit(q1)
+_CX_SECOND_CONTROLS = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=np.complex128)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_bare_cx_gates_of_noisy_passes_become_load_permutations(seed):
+    """The config-5 pattern: layers of 1-qubit gates and cx gates (either qubit as the control), a sampled Pauli after
+    every gate on each of its qubits.  In passes that carry Paulis a bare cx takes no matrix slot and no arithmetic: it is
+    folded into the load offsets of its round (TileRound::eoff_ld).  Must equal the oracle; and because matrix slots are
+    what limits a noisy pass, the circuit must fit in fewer passes than one per 16 gates."""
+    n, S = 14, 3
+    rng = np.random.default_rng(900 + seed)
+    states = [opgen.random_state(rng, n) for _ in range(S)]
+    ops, nslots, ngates = [], 0, 0
+    for layer in range(6):
+        for q in range(n):
+            ops.append((1, [q], opgen.colmajor(opgen.haar_unitary(rng, 2))))
+            ops.append((3, [q], nslots)); nslots += 1
+            ngates += 1
+        perm = rng.permutation(n)
+        for i in range(n // 2):
+            a, b = int(perm[2 * i]), int(perm[2 * i + 1])
+            ops.append((2, [a, b], opgen.colmajor(_CX_FIRST_CONTROLS if rng.random() < 0.5 else _CX_SECOND_CONTROLS)))
+            ngates += 1
+            for q in (a, b):
+                ops.append((3, [q], nslots)); nslots += 1
+    codes = rng.choice(4, size=(nslots, S), p=[0.85, 0.05, 0.05, 0.05]).astype(np.uint8)
+    state = np.concatenate(states).astype(np.complex128)
+    passes = selftest(n, state, ops, num_states=S, codes=codes)
+    assert passes <= ngates // 16
+    got = state.reshape(S, -1)
+    for s_i, st in enumerate(states):
+        o = OracleQV(n)
+        o.set_state(st)
+        for k, qs, m in ops:
+            o.apply_matrix(qs, opgen.colmajor(_PAULI[int(codes[m, s_i])].astype(np.complex128)) if k == 3 else m)
+        assert np.max(np.abs(got[s_i] - o.vector())) < 1e-12
+
+
 def _plan_only_passes(n, ops):
     lib = capi.lib()
     nops = len(ops)
@@ -223,9 +263,6 @@ def test_pass_packing_quality_on_the_headline_circuit():
         assert 14 <= passes <= 18, (seed, passes)
 
 
-_PAULI = [np.eye(2), np.array([[0, 1], [1, 0]]), np.array([[0, -1j], [1j, 0]]), np.diag([1, -1])]
-
-
 @pytest.mark.parametrize("block", range(4))
 def test_scheduler_randomized_op_mixes(block):
     """Random mixes of dense / diagonal 1- and 2-qubit gates and per-state Paulis (densities from none to 80 %, optionally
@@ -247,6 +284,8 @@ def test_scheduler_randomized_op_mixes(block):
             k = 1 if rng.random() < p1q else 2
             qs = [int(q) for q in rng.choice(pool, size=k, replace=False)]
             m = np.diag(np.exp(1j * rng.uniform(0, 6.28, 1 << k))) if rng.random() < pdiag else opgen.haar_unitary(rng, 1 << k)
+            if k == 2 and seed % 2 and rng.random() < 0.4:  # odd seeds: bare cx gates (load permutations in noisy passes)
+                m = _CX_FIRST_CONTROLS if rng.random() < 0.5 else _CX_SECOND_CONTROLS
             ops.append((k, qs, opgen.colmajor(m)))
         if all(o[0] == 3 for o in ops):
             ops.append((1, [0], opgen.colmajor(opgen.haar_unitary(rng, 2))))

@@ -151,3 +151,54 @@ def test_five_qubit_block_on_a_batch_whose_group_count_is_not_a_multiple_of_8(nq
         ora.set_state(states[s])
         ora.apply_matrix(qubits, U)
         assert np.max(np.abs(got[s] - ora.vector())) < 1e-12, s
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_noisy_pass_slot_forms(seed):
+    """Slot rounds of noisy passes on the device: bare cx gates (either control) folded into the load offsets,
+    1-qubit gates by kind (dense / diagonal / real / unpaired), sampled Paulis before and between them -- against the
+    oracle replaying every state's own Pauli draws."""
+    import qiskit_aer_b200 as q
+    n, S = 14, 5
+    rng = np.random.default_rng(300 + seed)
+    cx_first = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 0, 0]], dtype=np.complex128)
+    cx_second = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=np.complex128)
+    ops, nslots = [], 0
+    for layer in range(6):
+        for qb in range(n):
+            kind = int(rng.integers(4))
+            if kind == 1:
+                u = np.diag(np.exp(1j * rng.uniform(0, 6.28, 2)))
+            elif kind == 2:
+                th = rng.uniform(0, 6.28)
+                u = np.array([[1, 1], [1, -1]]) / np.sqrt(2) if rng.random() < 0.5 else np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+            else:
+                u = opgen.haar_unitary(rng, 2)
+            if layer == 4 and qb % 3 == 0:
+                continue
+            ops.append(("dense", [qb], opgen.colmajor(np.asarray(u, dtype=np.complex128))))
+            ops.append(("pauli", qb, nslots)); nslots += 1
+        perm = rng.permutation(n)
+        for i in range(n // 2):
+            a, b = int(perm[2 * i]), int(perm[2 * i + 1])
+            ops.append(("dense", [a, b], opgen.colmajor(cx_first if rng.random() < 0.5 else cx_second)))
+            for qb in (a, b):
+                ops.append(("pauli", qb, nslots)); nslots += 1
+    codes = rng.choice(4, size=(nslots, S), p=[0.8, 0.07, 0.07, 0.06]).astype(np.uint8)
+    states = [opgen.random_state(rng, n) for _ in range(S)]
+    qv = q.QubitVectorB200(n, np.complex128, num_states=S)
+    qv.initialize_from_vector(np.concatenate(states))
+    ngates = sum(1 for o in ops if o[0] == "dense")
+    passes = qv.apply_op_sequence(ops, codes)
+    assert passes <= ngates // 16
+    got = qv.vector().reshape(S, -1)
+    for si, st in enumerate(states):
+        o = OracleQV(n)
+        o.set_state(st)
+        for op in ops:
+            if op[0] == "dense":
+                o.apply_matrix(op[1], op[2])
+            elif codes[op[2], si]:
+                o.apply_pauli([op[1]], "IXYZ"[int(codes[op[2], si])])
+        assert np.max(np.abs(got[si] - o.vector())) < 1e-12
+    qv.close()

@@ -204,7 +204,8 @@ _CX_SECOND_CONTROLS = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0,
 def test_bare_cx_gates_of_noisy_passes_become_load_permutations(seed):
     """The config-5 pattern: layers of 1-qubit gates and cx gates (either qubit as the control), a sampled Pauli after
     every gate on each of its qubits.  In passes that carry Paulis a bare cx takes no matrix slot and no arithmetic: it is
-    folded into the load offsets of its round (TileRound::eoff_ld).  Must equal the oracle; and because matrix slots are
+    folded into the load offsets of its round (TileRound::eoff_ld); 1-qubit gates that are diagonal or real take the
+    cheaper per-kind forms of a pair slot.  Must equal the oracle; and because matrix slots are
     what limits a noisy pass, the circuit must fit in fewer passes than one per 16 gates."""
     n, S = 14, 3
     rng = np.random.default_rng(900 + seed)
@@ -212,7 +213,17 @@ def test_bare_cx_gates_of_noisy_passes_become_load_permutations(seed):
     ops, nslots, ngates = [], 0, 0
     for layer in range(6):
         for q in range(n):
-            ops.append((1, [q], opgen.colmajor(opgen.haar_unitary(rng, 2))))
+            kind = int(rng.integers(4))  # dense, diagonal (rz), real (h / ry), dense again: slots pair them by kind
+            if kind == 1:
+                u = np.diag(np.exp(1j * rng.uniform(0, 6.28, 2)))
+            elif kind == 2:
+                th = rng.uniform(0, 6.28)
+                u = np.array([[1, 1], [1, -1]]) / np.sqrt(2) if rng.random() < 0.5 else np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+            else:
+                u = opgen.haar_unitary(rng, 2)
+            if layer == 4 and q % 3 == 0:
+                continue  # unpaired 1-qubit gates (an absent partner)
+            ops.append((1, [q], opgen.colmajor(np.asarray(u, dtype=np.complex128))))
             ops.append((3, [q], nslots)); nslots += 1
             ngates += 1
         perm = rng.permutation(n)

@@ -195,39 +195,9 @@ __device__ __forceinline__ void apply_pauli_reg(double2 (&a)[16], int code) {
 // skips the slot's arithmetic.  Half of a noisy pass's gate slots then cost no DFMA and no instruction at all.
 // kSlotCxLo / kSlotCxHi = cx controlled by the slot's lower / upper round bit; other forms = dense 4x4.
 constexpr int kSlotCxLo = 24, kSlotCxHi = 25;
-// A slot holding two 1-qubit gates that are not both dense (noise keeps 1-qubit gates apart from their neighbours, so
-// rz / h / p ... arrive one by one): form = kSlotPair + ku + 4 kv, u on the slot's lower round bit (matrix entries
-// 0..3), v on the upper one (entries 4..7); kind 0 = dense (8 DFMA per amplitude), 1 = diagonal (4), 2 = real matrix
-// (4), 3 = absent.  The host keeps the 4x4 product form (16 DFMA per amplitude) when both are dense.
-constexpr int kSlotPair = 32;
-enum { K1_DENSE = 0, K1_DIAG = 1, K1_REAL = 2, K1_NONE = 3 };
-template <int P>
-__device__ __forceinline__ void apply1_real(double2 (&a)[16], const double2 *__restrict__ m) {
-  const double m00 = m[0].x, m01 = m[1].x, m10 = m[2].x, m11 = m[3].x;
-#pragma unroll
-  for (int i = 0; i < 16; i++) {
-    if (i & (1 << P)) continue;
-    const double2 x0 = a[i], x1 = a[i | (1 << P)];
-    a[i] = mk<double>(fma(m01, x1.x, m00 * x0.x), fma(m01, x1.y, m00 * x0.y));
-    a[i | (1 << P)] = mk<double>(fma(m11, x1.x, m10 * x0.x), fma(m11, x1.y, m10 * x0.y));
-  }
-}
-template <int P>
-__device__ __forceinline__ void gate1(double2 (&a)[16], const int kind, const double2 *__restrict__ m) {
-  if (kind == K1_DENSE) apply1<P>(a, m);
-  else if (kind == K1_DIAG) {
-    const double2 d[2] = {m[0], m[3]};
-    apply_diag1<P>(a, d);
-  } else if (kind == K1_REAL) apply1_real<P>(a, m);
-}
 template <int P0, int P1>
 __device__ __forceinline__ void slot_gate(double2 (&a)[16], const int form, const double2 *__restrict__ m) {
-  // `form` comes from the parameter block: uniform branches
-  if (form < kSlotCxLo) apply2<P0, P1>(a, m);
-  else if (form >= kSlotPair) {
-    gate1<P0>(a, (form - kSlotPair) & 3, m);
-    gate1<P1>(a, (form - kSlotPair) >> 2, m + 4);
-  }
+  if (form < kSlotCxLo) apply2<P0, P1>(a, m);  // `form` comes from the parameter block: uniform branch
 }
 
 // Sampled noise folded into a gate round: the Pauli codes (staged per tile in shared memory) of the ops that precede
@@ -849,25 +819,6 @@ static void emulate_tile_pass(const TilePassParams &p, void *host, const uint8_t
             }
           }
           for (int k = 0; k < (R.fast == 5 ? 0 : R.ngates); k++) {
-            if (R.fast && R.form[k] >= kSlotPair) {  // two 1-qubit gates by kind (noisy passes)
-              const double2 *mm = p.mats[R.gate[k]];
-              for (int w = 0; w < 2; w++) {
-                const int kind = ((R.form[k] - kSlotPair) >> (2 * w)) & 3, P = (k == 0 ? 0 : 2) + w;
-                if (kind == K1_NONE) continue;
-                C U[4];
-                for (int i = 0; i < 4; i++) U[i] = C((T)mm[4 * w + i].x, (T)mm[4 * w + i].y);
-                if (kind == K1_DIAG && (U[1] != C(0) || U[2] != C(0))) throw Error("selftest: diagonal kind with off-diagonal entries");
-                if (kind == K1_REAL && (U[0].imag() != 0 || U[1].imag() != 0 || U[2].imag() != 0 || U[3].imag() != 0))
-                  throw Error("selftest: real kind with imaginary entries");
-                for (int i = 0; i < na; i++) {
-                  if (i & (1 << P)) continue;
-                  const C x0 = a[i], x1 = a[i | (1 << P)];
-                  a[i] = U[0] * x0 + U[1] * x1;
-                  a[i | (1 << P)] = U[2] * x0 + U[3] * x1;
-                }
-              }
-              continue;
-            }
             if (R.fast && R.form[k] >= kSlotCxLo) continue;  // bare cx slot: already applied by the permuted load
             const int form = R.fast ? (k == 0 ? 0 : 5) : R.form[k];
             C M[16];
@@ -1036,13 +987,6 @@ static int bare_cx_form(const QGate &g) {
     }
   return is_lo ? kSlotCxLo : is_hi ? kSlotCxHi : 0;
 }
-// kind of a dense-queue 1-qubit gate (column-major 2x2): diagonal, real, or neither
-static int one_qubit_kind(const QGate &g) {
-  const double *u = g.mat;
-  if (u[2] == 0.0 && u[3] == 0.0 && u[4] == 0.0 && u[5] == 0.0) return K1_DIAG;
-  if (u[1] == 0.0 && u[3] == 0.0 && u[5] == 0.0 && u[7] == 0.0) return K1_REAL;
-  return K1_DENSE;
-}
 static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates, const std::vector<int> &sel,
                               const std::vector<int> &tile_bits, std::vector<int> &leftover) {
   constexpr int kTB = 12;
@@ -1191,25 +1135,6 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
         any_pauli = true;
       }
       for (int k = 0; k < sr.kind; k++) {
-        const std::vector<int> &sl1 = sr.slot[k];
-        if (allow_cx && gates[sl1[0]].nq == 1) {  // 1-qubit gates by kind, unless both are dense
-          int kinds[2] = {K1_NONE, K1_NONE};
-          for (size_t w = 0; w < sl1.size(); w++) kinds[w] = one_qubit_kind(gates[sl1[w]]);
-          if (kinds[0] != K1_DENSE || kinds[1] != K1_DENSE) {
-            if (nm >= kMaxTileGates) throw Error("tile pass: matrix slots exhausted");
-            double2 *M = p.mats[nm];
-            for (int i = 0; i < 16; i++) M[i] = mk<double>(0, 0);
-            for (size_t w = 0; w < sl1.size(); w++) {
-              const double *u = gates[sl1[w]].mat;  // column-major 2x2 -> row-major entries 4w .. 4w+3
-              for (int r = 0; r < 2; r++)
-                for (int c = 0; c < 2; c++) M[4 * w + 2 * r + c] = mk<double>(u[2 * (r + 2 * c)], u[2 * (r + 2 * c) + 1]);
-            }
-            R.form[k] = (uint8_t)(kSlotPair + kinds[0] + 4 * kinds[1]);
-            R.gate[k] = (uint16_t)nm++;
-            any_cx = true;
-            continue;
-          }
-        }
         if (const int cxf = slot_form(sr.slot[k])) {  // no matrix, no arithmetic: output e = input e ^ (ctl(e) << tgt)
           R.form[k] = (uint8_t)cxf;
           R.gate[k] = 0;

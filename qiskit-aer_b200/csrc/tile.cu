@@ -231,6 +231,22 @@ __device__ __forceinline__ void apply_pre_paulis(double2 *__restrict__ tile, con
   }
 }
 
+// Pauli codes of one tile's state -> shared memory, by ONE warp with one (two) parallel loads: lane i fetches the code
+// of the pass's i-th (and i+32-th) Pauli op.  The slot numbers come out of the parameter block with a UNIFORM index (a
+// thread-indexed parameter read makes the compiler copy the block to local memory and takes the gate matrices off the
+// uniform datapath), each lane keeping its own.  (The first version fetched the codes one after the other: ~40 dependent
+// L2 round trips per tile, which the rest of the group sat out at the barrier -- half of a noisy pass's time.)
+__device__ __forceinline__ void stage_pauli_codes(uint8_t *sc, const TilePassParams &p, const uint64_t state, const int lane) {
+  uint32_t s0 = 0, s1 = 0;
+  for (int i = 0; i < p.npauli; i++) {
+    const uint32_t sl = p.pauli_slot[i];
+    if ((i & 31) == lane) { if (i < 32) s0 = sl; else s1 = sl; }
+  }
+  if (lane < p.npauli) sc[lane] = p.codes[(size_t)s0 * p.nstates + state];
+  if (lane + 32 < p.npauli) sc[lane + 32] = p.codes[(size_t)s1 * p.nstates + state];
+  if (lane == 0) sc[kMaxRounds] = 0;  // "no Pauli"
+}
+
 // all rounds of one tile, in place in shared memory.  GROUPED = 0: the CTA is one 2^(TB-4)-thread group
 // (__syncthreads); GROUPED = 1: 256-thread groups of a bigger CTA, named barrier 1 + grp.
 // MODE 0: fast and generic rounds; 1: every round of the pass is fast; 2: generic code only (fast rounds carry
@@ -482,13 +498,8 @@ tile_pipe_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
     if (MODE == 4) {  // this tile's state: one code per Pauli op of the pass, fetched once (not once per round)
       // the group's first warp fetches them (uniform branch, uniform parameter index: anything thread-indexed here makes
       // the compiler move the parameter block to local memory and the gate matrices off the uniform datapath)
-      if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0) {
-        for (int i = 0; i < p.npauli; i++) {  // every lane reads (uniform address), lane 0 writes
-          const uint8_t v = p.codes[(size_t)p.pauli_slot[i] * p.nstates + (t >> p.state_shift)];
-          if ((tid & 31) == 0) scodes[grp * (kMaxRounds + 16) + i] = v;
-        }
-        if ((tid & 31) == 0) scodes[grp * (kMaxRounds + 16) + kMaxRounds] = 0;  // "no Pauli"
-      }
+      if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0)
+        stage_pauli_codes(scodes + grp * (kMaxRounds + 16), p, valid ? (t >> p.state_shift) : 0, tid & 31);
       if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
       else asm volatile("bar.sync 1, 256;" ::: "memory");
     }
@@ -663,13 +674,7 @@ __global__ void __maxnreg__(96) tile_pipe2_kernel(double2 *__restrict__ psi, con
     // the group's next tile while the others still read this one's codes (the barrier below bounds the lead to one tile).
     uint8_t *sc = scodes + (grp * 2 + (kk & 1)) * (kMaxRounds + 16);
     if (MODE == 4) {
-      if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0) {
-        for (int i = 0; i < p.npauli; i++) {  // every lane reads (uniform address), lane 0 writes
-          const uint8_t v = p.codes[(size_t)p.pauli_slot[i] * p.nstates + (t >> p.state_shift)];
-          if ((tid & 31) == 0) sc[i] = v;
-        }
-        if ((tid & 31) == 0) sc[kMaxRounds] = 0;
-      }
+      if (__shfl_sync(0xffffffffu, tid >> 5, 0) == 0) stage_pauli_codes(sc, p, valid ? (t >> p.state_shift) : 0, tid & 31);
       if (grp) asm volatile("bar.sync 2, 256;" ::: "memory");
       else asm volatile("bar.sync 1, 256;" ::: "memory");
     }
@@ -1372,6 +1377,22 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
       }
     }
     r0 = r1;
+  }
+  static const int env_trace_rounds = [] { const char *e = getenv("B200SV_TILE_TRACE"); return e ? atoi(e) : 0; }();
+  if (env_trace_rounds >= 2) {  // round census: dense slots / bare-cx slots / stand-alone Pauli rounds / folded Paulis / barriers
+    int dense = 0, cx = 0, prounds = 0, pre = 0, syncs = 0, cxonly = 0;
+    for (int r = 0; r < p.nrounds; r++) {
+      const TileRound &R = p.rounds[r];
+      syncs += R.sync;
+      pre += R.npre;
+      if (R.fast == 5) { prounds++; continue; }
+      int d = 0, c = 0;
+      for (int k = 0; k < R.ngates; k++) (R.fast && slot_pauli && R.form[k] >= kSlotCxLo ? c : d)++;
+      dense += d; cx += c;
+      cxonly += (d == 0 && c > 0);
+    }
+    fprintf(stderr, "b200sv   rounds %d: dense slots %d, cx slots %d (%d cx-only rounds), Pauli rounds %d, folded Paulis %d, CTA barriers %d\n",
+            p.nrounds, dense, cx, cxonly, prounds, pre, syncs);
   }
   if (s.selftest_host) {  // scheduler self-test: interpret the parameter block on the host array
     if (!s.plan_only) emulate_tile_pass<double>(p, s.selftest_host, s.selftest_codes, false);

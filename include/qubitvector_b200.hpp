@@ -598,7 +598,13 @@ public:
       }
       Q.nslots++;
     }
-    if (!queue_enabled() || Q.kind.size() >= 2048) Q.flush(batch_->h);
+    if (!queue_enabled() || Q.kind.size() >= batch_queue_limit()) Q.flush(batch_->h);
+  }
+  // ops queued before a batched container flushes on its own: the flush is asynchronous, so the executor's host work
+  // for the following ops (noise sampling for every shot) runs while the GPU works through the passes of this part
+  static size_t batch_queue_limit() {
+    static const size_t n = [] { const char *e = getenv("B200SV_BATCH_QUEUE_OPS"); return e && atoi(e) > 0 ? (size_t)atoi(e) : (size_t)512; }();
+    return n;
   }
   // apply_batched_measure (qubitvector_thrust.hpp:2251-2330): r = rng[s].rand(); outcome = first i with
   // r < cumulative probability; collapse + renormalise; store bits.
@@ -766,7 +772,7 @@ protected:
     if (batch_) {
       if (!batch_->on || batch_->cond_reg >= 0) return false;
       batch_->queue.push_dense(qubits.data(), (int)qubits.size(), mat);
-      if (batch_->queue.kind.size() >= 2048) batch_->queue.flush(batch_->h);
+      if (batch_->queue.kind.size() >= batch_queue_limit()) batch_->queue.flush(batch_->h);
       return true;
     }
     queue_.push_dense(qubits.data(), (int)qubits.size(), mat);

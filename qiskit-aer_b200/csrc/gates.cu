@@ -656,11 +656,17 @@ collapse_kernel(cx<T> *__restrict__ psi, const __grid_constant__ CollapseParams 
   const T sc = (T)scale[s];
   cx<T> *st = psi + (s << p.nq);
   const uint64_t n = 1ull << p.nq, stride = (uint64_t)gridDim.x * blockDim.x;
+  // the outcome deposited at the measured positions: one mask compare per amplitude; amplitudes that do not survive
+  // are only written (a full-register measurement is a write-only pass)
+  uint64_t qmask = 0, wbits = 0;
+  for (int j = 0; j < p.k; j++) {
+    qmask |= 1ull << p.q[j];
+    wbits |= ((want >> j) & 1ull) << p.q[j];
+  }
+#pragma unroll 4
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint64_t m = 0;
-    for (int j = 0; j < p.k; j++) m |= ((i >> p.q[j]) & 1ull) << j;
-    cx<T> v = st[i];
-    if (m != want) { st[i] = mk<T>(0, 0); continue; }
+    if ((i & qmask) != wbits) { st[i] = mk<T>(0, 0); continue; }
+    const cx<T> v = st[i];
     if (sc > (T)0) { st[i] = mk<T>(v.x * sc, v.y * sc); continue; }
     // scale <= 0: every qubit was measured, the single survivor is normalised by its own modulus
     const T r = (T)1 / sqrt(v.x * v.x + v.y * v.y);

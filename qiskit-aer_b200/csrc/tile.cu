@@ -68,6 +68,9 @@ struct TileRound {
   uint8_t npre;                 // number of valid entries in pre[]
   uint8_t pre[4];               // slot rounds: staged-code index of a per-state Pauli applied to round bit i BEFORE the
                                 // round's gates (sampled noise folded into the next gate round on that qubit), or kMaxRounds = none
+  uint8_t npre2;                // number of valid entries in pre2[]
+  uint8_t pre2[4];              // like pre[], but applied AFTER the round's folded cx gates (through eoff_ld): the noise
+                                // that sits between a folded cx and the 1-qubit gates of its slot
   uint8_t sync;                 // 1: CTA barrier after this round; 0: the next round stays inside each warp's sub-tile
   uint8_t fast;                 // 2 / 1: exactly two / one dense 4x4 block(s), on round bits (0,1) [and (2,3)]:
                                 // straight-line code (LDS, DFMA and STS interleave, no form dispatch); 5: one per-state
@@ -204,12 +207,12 @@ __device__ __forceinline__ void slot_gate(double2 (&a)[16], const int form, cons
 // the round's gates on its four bits.  Identity draws (99 %) cost four shared-memory bytes and a vote; a hit takes the
 // block through registers once more (same thread, same slots: no synchronisation) before the straight-line gate code,
 // which stays untouched.  pre index kMaxRounds ("none") reads a constant 0.
-__device__ __forceinline__ void apply_pre_paulis(double2 *__restrict__ tile, const uint32_t base, const TileRound &R,
-                                                 const uint8_t *scodes, const bool valid) {
-  const int c0 = __shfl_sync(0xffffffffu, (int)scodes[R.pre[0]], 0);
-  const int c1 = __shfl_sync(0xffffffffu, (int)scodes[R.pre[1]], 0);
-  const int c2 = __shfl_sync(0xffffffffu, (int)scodes[R.pre[2]], 0);
-  const int c3 = __shfl_sync(0xffffffffu, (int)scodes[R.pre[3]], 0);
+__device__ __forceinline__ void apply_pre_paulis(double2 *__restrict__ tile, const uint32_t base, const uint16_t (&eoff)[16],
+                                                 const uint8_t (&pre)[4], const uint8_t *scodes, const bool valid) {
+  const int c0 = __shfl_sync(0xffffffffu, (int)scodes[pre[0]], 0);
+  const int c1 = __shfl_sync(0xffffffffu, (int)scodes[pre[1]], 0);
+  const int c2 = __shfl_sync(0xffffffffu, (int)scodes[pre[2]], 0);
+  const int c3 = __shfl_sync(0xffffffffu, (int)scodes[pre[3]], 0);
   if (c0 | c1 | c2 | c3) {
     // rare path (a few per cent of the rounds): pair by pair in shared memory, runtime bit and code, so that it adds
     // almost no registers or code next to the straight-line gate blocks
@@ -220,7 +223,7 @@ __device__ __forceinline__ void apply_pre_paulis(double2 *__restrict__ tile, con
 #pragma unroll 1
       for (int j = 0; j < 8; j++) {
         const int i0 = ((j >> b) << (b + 1)) | (j & ((1 << b) - 1)), i1 = i0 | (1 << b);
-        double2 *s0 = &tile[base ^ R.eoff[i0]], *s1 = &tile[base ^ R.eoff[i1]];
+        double2 *s0 = &tile[base ^ eoff[i0]], *s1 = &tile[base ^ eoff[i1]];
         const double2 x0 = *s0, x1 = *s1;
         if (!valid) continue;
         if (code == 1) { *s0 = x1; *s1 = x0; }
@@ -266,7 +269,8 @@ __device__ __forceinline__ void run_rounds(double2 *__restrict__ tile, const int
 #pragma unroll
       for (int i = 0; i < kLoBits; i++)
         if ((g >> i) & 1) base ^= R.gbit[i];
-      if (MODE == 4 && R.npre) apply_pre_paulis(tile, base, R, scodes, valid);
+      if (MODE == 4 && R.npre) apply_pre_paulis(tile, base, R.eoff, R.pre, scodes, valid);
+      if (MODE == 4 && R.npre2) apply_pre_paulis(tile, base, R.eoff_ld, R.pre2, scodes, valid);  // after the folded cx gates
       const int fast = MODE == 2 ? 0 : R.fast;  // MODE 4 = MODE 1 + Pauli rounds
       if (fast == 2) {
         double2 a[16];
@@ -811,6 +815,18 @@ static void emulate_tile_pass(const TilePassParams &p, void *host, const uint8_t
               b[e] = a[src];
             }
             std::copy(b, b + 16, a);
+            for (int P = 0; P < 4; P++) {  // noise between a folded cx and the gates of its slot
+              if (R.pre2[P] == kMaxRounds) continue;
+              const int code = codes[(size_t)p.pauli_slot[R.pre2[P]] * p.nstates + (t >> p.state_shift)];
+              for (int i = 0; i < na && code; i++) {
+                if (i & (1 << P)) continue;
+                const int j = i | (1 << P);
+                const C x0 = a[i], x1 = a[j];
+                if (code == 1) { a[i] = x1; a[j] = x0; }
+                else if (code == 2) { a[i] = C(x1.imag(), -x1.real()); a[j] = C(-x0.imag(), x0.real()); }
+                else a[j] = -x1;
+              }
+            }
           }
           if (R.fast == 5) {
             const int code = codes[(size_t)p.pauli_slot[R.gate[0]] * p.nstates + (t >> p.state_shift)];
@@ -907,7 +923,8 @@ static std::vector<int> build_round(TileRound &R, const std::vector<int> &round_
   R.sync = 1;
   R.fast = 0;
   R.pre[0] = R.pre[1] = R.pre[2] = R.pre[3] = (uint8_t)kMaxRounds;
-  R.npre = 0;
+  R.pre2[0] = R.pre2[1] = R.pre2[2] = R.pre2[3] = (uint8_t)kMaxRounds;
+  R.npre = R.npre2 = 0;
   return pos;
 }
 
@@ -992,15 +1009,71 @@ static int bare_cx_form(const QGate &g) {
     }
   return is_lo ? kSlotCxLo : is_hi ? kSlotCxHi : 0;
 }
-static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates, const std::vector<int> &sel,
+static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates_in, const std::vector<int> &sel_in,
                               const std::vector<int> &tile_bits, std::vector<int> &leftover) {
   constexpr int kTB = 12;
   // bare cx gates as register renamings: only in passes that carry sampled noise (they run the MODE 4 kernels, the
   // only ones that read the slot forms)
-  static const int env_cx = [] { const char *e = getenv("B200SV_TILE_CX_SLOTS"); return e ? atoi(e) : 1; }();
+  static const int env_cx = [] { const char *e = getenv("B200SV_TILE_CX_SLOTS"); return e ? atoi(e) : 2; }();
   bool allow_cx = false, any_cx = false;
-  for (int gi : sel) allow_cx = allow_cx || !gates[gi].mat;
+  for (int gi : sel_in) allow_cx = allow_cx || !gates_in[gi].mat;
   allow_cx = allow_cx && env_cx;
+  // Folded cx (B200SV_TILE_CX_SLOTS >= 2, default): a bare cx(a, b) whose next gates on a and on b are 1-qubit gates of
+  // this pass -- with at most one sampled Pauli per qubit in between, the noise of the cx -- becomes ONE slot: the cx as
+  // the slot's load permutation, the Paulis in between applied through the permuted offsets (TileRound::pre2), then
+  // u_b x u_a as the slot's 4x4.  The layer pattern of a noisy circuit (cx layer, 1-qubit layer) then costs one
+  // shared-memory round trip per two cx + four 1-qubit gates instead of two.  The macro op takes the cx's place in the
+  // order; its constituents only share qubits with each other and with ops that stay behind them.
+  struct Macro { int cx, u[2], inner[2], form; };
+  std::vector<QGate> gates(gates_in);
+  std::vector<int> sel(sel_in);
+  std::vector<Macro> macros;
+  std::vector<std::array<double, 32>> macro_mats;
+  const int first_macro = (int)gates_in.size();
+  if (allow_cx && env_cx >= 2) {
+    macro_mats.reserve(sel_in.size());
+    std::vector<char> gone(sel_in.size(), 0);
+    std::vector<int> out;
+    for (size_t i = 0; i < sel_in.size(); i++) {
+      if (gone[i]) continue;
+      const QGate &g = gates_in[sel_in[i]];
+      const int form = bare_cx_form(g);
+      Macro m{sel_in[i], {-1, -1}, {-1, -1}, form};
+      size_t at_u[2] = {0, 0}, at_in[2] = {0, 0};
+      bool ok = form != 0;
+      for (int x = 0; x < 2 && ok; x++) {  // next ops on q[x]: [one Pauli] then a 1-qubit gate
+        ok = false;
+        for (size_t j = i + 1; j < sel_in.size(); j++) {
+          const QGate &h = gates_in[sel_in[j]];
+          if (gone[j] || !((qmask(h) >> g.q[x]) & 1)) continue;
+          if (!h.mat && m.inner[x] < 0) { m.inner[x] = sel_in[j]; at_in[x] = j; continue; }
+          if (h.mat && h.nq == 1) { m.u[x] = sel_in[j]; at_u[x] = j; ok = true; }
+          break;
+        }
+      }
+      if (!ok) { out.push_back(sel_in[i]); continue; }
+      macro_mats.emplace_back();
+      double *M = macro_mats.back().data();  // column-major 4x4, index = bit(q[0]) + 2 bit(q[1]): u1 x u0
+      const cd_t *u0 = reinterpret_cast<const cd_t *>(gates_in[m.u[0]].mat), *u1 = reinterpret_cast<const cd_t *>(gates_in[m.u[1]].mat);
+      for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++) {
+          const cd_t v = u0[(r & 1) + 2 * (c & 1)] * u1[(r >> 1) + 2 * (c >> 1)];
+          M[2 * (r + 4 * c)] = v.real();
+          M[2 * (r + 4 * c) + 1] = v.imag();
+        }
+      QGate mg;
+      mg.nq = 2; mg.q[0] = g.q[0]; mg.q[1] = g.q[1]; mg.mat = M; mg.slot = 0;
+      gates.push_back(mg);
+      out.push_back(first_macro + (int)macros.size());
+      macros.push_back(m);
+      for (int x = 0; x < 2; x++) {
+        gone[at_u[x]] = 1;
+        if (m.inner[x] >= 0) gone[at_in[x]] = 1;
+      }
+    }
+    sel.swap(out);
+  }
+  auto macro_of = [&](int gi) -> const Macro * { return gi >= first_macro ? &macros[gi - first_macro] : nullptr; };
   auto slot_form = [&](const std::vector<int> &sl) { return allow_cx && !sl.empty() ? bare_cx_form(gates[sl[0]]) : 0; };
   auto tile_pos = [&](int q) {
     for (int u = 0; u < kTB; u++)
@@ -1026,7 +1099,18 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
   }
   int nmat = 0, npaul = 0;
   while (!rem.empty()) {
-    if ((int)rounds.size() >= kMaxRounds || nmat + 2 > kMaxTileGates || npaul + 5 > kMaxRounds) { leftover = rem; break; }
+    if ((int)rounds.size() >= kMaxRounds || nmat + 2 > kMaxTileGates || npaul + 7 > kMaxRounds) {
+      for (int gi : rem) {  // macro ops go back as their constituents
+        const Macro *mc = macro_of(gi);
+        if (!mc) { leftover.push_back(gi); continue; }
+        leftover.push_back(mc->cx);
+        for (int x = 0; x < 2; x++) {
+          if (mc->inner[x] >= 0) leftover.push_back(mc->inner[x]);
+          leftover.push_back(mc->u[x]);
+        }
+      }
+      break;
+    }
     SRound sr;
     uint64_t rq = 0, blocked = 0;
     std::vector<std::pair<int, int>> rest;  // (scan position, op): held Paulis that stay unattached re-enter in order
@@ -1077,6 +1161,9 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
     if (sr.kind != 5)
       for (int k = 0; k < sr.kind; k++) nmat += slot_form(sr.slot[k]) ? 0 : 1;
     npaul += sr.kind == 5 ? 1 : (int)sr.pre.size();
+    if (sr.kind != 5)
+      for (int k = 0; k < sr.kind; k++)
+        if (const Macro *mc = macro_of(sr.slot[k][0])) npaul += (mc->inner[0] >= 0) + (mc->inner[1] >= 0);
     rounds.push_back(sr);
     round_pos.push_back(rp);
     rem.clear();
@@ -1156,6 +1243,20 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
           for (int j = 0; j < 4; j++) M[i * 4 + j] = mk<double>(M4[k][i + 4 * j].real(), M4[k][i + 4 * j].imag());
         R.form[k] = (uint8_t)(k == 0 ? 0 : 5);
         R.gate[k] = (uint16_t)nm++;
+        if (const Macro *mc = macro_of(sr.slot[k][0])) {  // folded cx: load permutation, then the noise in between
+          const int ctl = 2 * k + (mc->form == kSlotCxLo ? 0 : 1), tgt = 2 * k + (mc->form == kSlotCxLo ? 1 : 0);
+          uint16_t ld[16];
+          for (int e = 0; e < 16; e++) ld[e] = R.eoff_ld[e ^ (((e >> ctl) & 1) << tgt)];
+          std::copy(ld, ld + 16, R.eoff_ld);
+          for (int x = 0; x < 2; x++) {
+            if (mc->inner[x] < 0) continue;
+            p.pauli_slot[p.npauli] = (uint16_t)gates[mc->inner[x]].slot;
+            R.pre2[2 * k + x] = (uint8_t)p.npauli++;
+            R.npre2++;
+            any_pauli = true;
+          }
+          any_cx = true;
+        }
       }
     }
     R.sync = (r == seg_end[r] - 1);
@@ -1384,7 +1485,7 @@ static std::vector<int> run_tile_pass(State &s, const std::vector<QGate> &gates,
     for (int r = 0; r < p.nrounds; r++) {
       const TileRound &R = p.rounds[r];
       syncs += R.sync;
-      pre += R.npre;
+      pre += R.npre + R.npre2;
       if (R.fast == 5) { prounds++; continue; }
       int d = 0, c = 0;
       for (int k = 0; k < R.ngates; k++) (R.fast && slot_pauli && R.form[k] >= kSlotCxLo ? c : d)++;
@@ -1454,9 +1555,39 @@ struct PassPacker {
   bool finished() const { return ndone == (int)gates.size(); }
   // selects ops for one pass; Q (in/out) = tile qubit mask, cap = tile bits
   std::vector<int> select(uint64_t &Q, int cap, int max_dense, int max_ops) {
+    // Noisy sequences: a sampled Pauli whose next op on its qubit does not make it into this pass would get a round of
+    // its own at the end of the pass; left for the next pass it is folded into that op's round.  Such Paulis are banned
+    // and the selection is redone, so that the op slots they held go to gates (a ban never unblocks anything: the ops
+    // behind a banned Pauli were not selectable in the first place).
+    std::vector<char> banned(gates.size(), 0);
+    const uint64_t Q0 = Q;
+    std::vector<int> sel;
+    for (int attempt = 0; attempt < 6; attempt++) {
+      Q = Q0;
+      sel = select_once(Q, cap, max_dense, max_ops, banned);
+      static const int env_defer = [] { const char *e = getenv("B200SV_TILE_DEFER_PAULI"); return e ? atoi(e) : 1; }();
+      if (!noisy || !env_defer) break;
+      std::vector<char> in(gates.size(), 0);
+      for (int i : sel) in[i] = 1;
+      int ndrop = 0, ngate = 0;
+      std::vector<int> drop;
+      for (int k = (int)sel.size() - 1; k >= 0; k--) {  // reverse: a dropped Pauli exposes the Pauli before it
+        const int i = sel[k];
+        bool d = false;
+        if (!gates[i].mat)
+          for (int sx : succ[i]) d = d || !in[sx];
+        if (d) { in[i] = 0; drop.push_back(i); ndrop++; }
+        else ngate += gates[i].mat != nullptr;
+      }
+      if (!ndrop || !ngate) break;  // nothing to defer, or a pass of Paulis only: run it as selected
+      for (int i : drop) banned[i] = 1;
+    }
+    return sel;
+  }
+  std::vector<int> select_once(uint64_t &Q, int cap, int max_dense, int max_ops, const std::vector<char> &banned) {
     std::vector<int> pp(pending), cand, sel;
     for (int i = 0; i < (int)gates.size(); i++)
-      if (!done[i] && pp[i] == 0) cand.push_back(i);
+      if (!done[i] && pp[i] == 0 && !banned[i]) cand.push_back(i);
     int ndense = 0;
     while ((int)sel.size() < max_ops) {
       int best = -1, best_new = 99, best_sc = -1;
@@ -1480,7 +1611,7 @@ struct PassPacker {
       Q |= qmask(gates[best]);
       ndense += half_slots(gates[best]);
       for (int sx : succ[best])
-        if (--pp[sx] == 0) cand.push_back(sx);
+        if (--pp[sx] == 0 && !banned[sx]) cand.push_back(sx);
     }
     return sel;
   }

@@ -39,10 +39,10 @@ def _mats(op):
     return list(op[2]), executor.colmajor(fusion.gate_matrix(op[1], op[3]))
 
 
-@pytest.mark.parametrize("n,shots,batch", [(12, 24, 8), (13, 10, 16), (6, 12, 5)])
+@pytest.mark.parametrize("n,shots,batch", [(12, 24, 8), (13, 10, 16), (6, 12, 5), (20, 5, 4)])  # 20: the config-5 width
 def test_shared_noise_realisation_matches_per_shot_oracle(n, shots, batch):
     from qiskit_aer_b200 import batched, circuits
-    ops = circuits.random_noisy_circuit(n, 3, seed=n)
+    ops = circuits.random_noisy_circuit(n, 3 if n < 20 else 6, seed=n)
     rng = np.random.default_rng(4)
     nslots = sum(len(op[2]) for op in ops)
     codes = (rng.random((nslots, shots)) < 0.15) * rng.integers(1, 4, size=(nslots, shots))

@@ -525,9 +525,25 @@ tile_pipe_kernel(double2 *__restrict__ psi, const __grid_constant__ TilePassPara
 // elements (tile = 2^12 slots = 2^13 amplitudes).  A thread's 16 slots are a 5-bit block: bit 0 = global qubit 0,
 // bits 1..4 = the round's slot positions.  Rounds are straight-line only: gate A on bits (1,2) -- or (0,1) when it
 // involves qubit 0 -- and optionally gate B on bits (3,4); the host promotes 1-qubit gates to 4x4.
+// Blackwell packed FP32 (`fma.rn.f32x2`, SASS FFMA2): one instruction does the two FMAs of a complex-times-real step,
+//   acc(re, im) += (m.re, m.re) * (x.re, x.im);   acc(re, im) += (-m.im, m.im) * (x.im, x.re)
+// -- the same four roundings in the same order as cfma().  The host stores every matrix entry of a float pass as the two
+// pairs {m.re, m.re, -m.im, m.im} (16 bytes, the room a double-precision entry takes), so that both multipliers are
+// 64-bit uniform-register operands straight from LDCU; the swap of x is an operand modifier (R.F32x2.LO_HI).  A 4x4
+// complex mat-vec is 32 FFMA2 instead of 64 FFMA.  The float rounds were issue bound (ncu: 87 % of the issue slots
+// busy, 75 % of them FFMA): halving the FMA instructions is what moves them.
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void cfma_f32x2(unsigned long long &acc, const ulonglong2 m, const float2 x) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(m.x), "l"(pack_f32x2(x.x, x.y)));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(m.y), "l"(pack_f32x2(x.y, x.x)));
+}
 template <int P0, int P1>
-__device__ __forceinline__ void apply2f(float2 (&a)[32], const float2 *__restrict__ m) {
-  float2 mm[16];
+__device__ __forceinline__ void apply2f(float2 (&a)[32], const ulonglong2 *__restrict__ m) {
+  ulonglong2 mm[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) mm[i] = m[i];
 #pragma unroll
@@ -543,11 +559,13 @@ __device__ __forceinline__ void apply2f(float2 (&a)[32], const float2 *__restric
     const float2 x0 = a[i0], x1 = a[i1], x2 = a[i2], x3 = a[i3];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-      float2 acc = mk<float>(0, 0);
-      cfma(acc, mm[r * 4 + 0], x0);
-      cfma(acc, mm[r * 4 + 1], x1);
-      cfma(acc, mm[r * 4 + 2], x2);
-      cfma(acc, mm[r * 4 + 3], x3);
+      unsigned long long acc2 = 0ull;
+      cfma_f32x2(acc2, mm[r * 4 + 0], x0);
+      cfma_f32x2(acc2, mm[r * 4 + 1], x1);
+      cfma_f32x2(acc2, mm[r * 4 + 2], x2);
+      cfma_f32x2(acc2, mm[r * 4 + 3], x3);
+      float2 acc;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(acc2));
       a[r == 0 ? i0 : r == 1 ? i1 : r == 2 ? i2 : i3] = acc;
     }
   }
@@ -562,8 +580,8 @@ __device__ __forceinline__ void run_rounds_f32(double2 *__restrict__ tile, const
 #pragma unroll
     for (int i = 0; i < 8; i++)
       if ((tid >> i) & 1) base ^= R.gbit[i];
-    const float2 *mA = reinterpret_cast<const float2 *>(p.mats[R.gate[0]]);
-    const float2 *mB = reinterpret_cast<const float2 *>(p.mats[R.gate[1]]);
+    const ulonglong2 *mA = reinterpret_cast<const ulonglong2 *>(p.mats[R.gate[0]]);  // {re, re, -im, im} per entry
+    const ulonglong2 *mB = reinterpret_cast<const ulonglong2 *>(p.mats[R.gate[1]]);
     const int kind = R.fast;
     float2 a[32];
 #define B200_F32_LOAD                                                                  \
@@ -781,9 +799,14 @@ static void emulate_tile_pass(const TilePassParams &p, void *host, const uint8_t
         };
         if (f32_layout) {
           std::complex<float> MA[16], MB[16];
-          const float2 *mA = reinterpret_cast<const float2 *>(p.mats[R.gate[0]]);
-          const float2 *mB = reinterpret_cast<const float2 *>(p.mats[R.gate[1]]);
-          for (int i = 0; i < 16; i++) { MA[i] = {mA[i].x, mA[i].y}; MB[i] = {mB[i].x, mB[i].y}; }
+          const float4 *mA = reinterpret_cast<const float4 *>(p.mats[R.gate[0]]);  // {re, re, -im, im} per entry
+          const float4 *mB = reinterpret_cast<const float4 *>(p.mats[R.gate[1]]);
+          for (int i = 0; i < 16; i++) {
+            if (mA[i].x != mA[i].y || mA[i].z != -mA[i].w || mB[i].x != mB[i].y || mB[i].z != -mB[i].w)
+              throw Error("selftest: float matrix entry is not stored as {re, re, -im, im}");
+            MA[i] = {mA[i].x, mA[i].w};
+            MB[i] = {mB[i].x, mB[i].w};
+          }
           const C *A = reinterpret_cast<const C *>(MA), *B = reinterpret_cast<const C *>(MB);
           if (R.fast == 1 || R.fast == 2) dense2(1, 2, A); else dense2(0, 1, A);
           if (R.fast == 2 || R.fast == 4) dense2(3, 4, B);
@@ -1685,8 +1708,9 @@ static std::vector<int> run_tile_pass_f32(State &s, const std::vector<QGate> &ga
   plan_segments(round_pos, kSB, round_w, seg_end);
   int nm = 0;
   auto put_matrix = [&](const QGate &g, bool q0_is_low_round_bit) {
-    // 4x4 row-major float2, matrix bit 0 <-> lower round bit; 1-qubit gates become (identity on the pad bit) x U
-    float2 *M = reinterpret_cast<float2 *>(p.mats[nm]);
+    // 4x4 row-major, matrix bit 0 <-> lower round bit; 1-qubit gates become (identity on the pad bit) x U; every entry
+    // as the two FFMA2 multiplier pairs {re, re, -im, im} (apply2f)
+    float4 *M = reinterpret_cast<float4 *>(p.mats[nm]);
     for (int i = 0; i < 4; i++)
       for (int j = 0; j < 4; j++) {
         double re, im;
@@ -1700,7 +1724,7 @@ static std::vector<int> run_tile_pass_f32(State &s, const std::vector<QGate> &ga
           re = g.mat[2 * (si + 4 * sj)];
           im = g.mat[2 * (si + 4 * sj) + 1];
         }
-        M[i * 4 + j] = make_float2((float)re, (float)im);
+        M[i * 4 + j] = make_float4((float)re, (float)re, -(float)im, (float)im);
       }
     return nm++;
   };

@@ -35,8 +35,10 @@ def test_tile_kernels_take_their_matrices_from_uniform_registers():
     tile = {k: v for k, v in kernels.items() if "tile_p" in k}
     assert len(tile) >= 6, sorted(tile)
     for name, lines in tile.items():
-        fma = [l for l in lines if re.search(r"\b(DFMA|FFMA)\b", l)]
+        fma = [l for l in lines if re.search(r"\b(DFMA|FFMA|FFMA2)\b", l)]
         assert len(fma) >= 256, (name, len(fma))
+        if "tile_pipe2_kernelILi3E" in name:  # single-precision rounds: packed FP32 FMAs (Blackwell), no scalar FFMA left
+            assert sum("FFMA2" in l for l in fma) >= 1024 and not any(re.search(r"\bFFMA\b", l) for l in fma), name
         vec = [l for l in fma if "UR" not in l]
         assert not vec, "%s: %d of %d FMAs lost their uniform-register operand" % (name, len(vec), len(fma))
         assert not any(re.search(r"\b(STL|LDL)\b", l) for l in lines if "DFMA" in l)

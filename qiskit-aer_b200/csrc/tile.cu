@@ -1122,7 +1122,7 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
   }
   int nmat = 0, npaul = 0;
   while (!rem.empty()) {
-    if ((int)rounds.size() >= kMaxRounds || nmat + 2 > kMaxTileGates || npaul + 7 > kMaxRounds) {
+    if ((int)rounds.size() >= kMaxRounds || nmat + 2 > kMaxTileGates || npaul + 8 > kMaxRounds) {
       for (int gi : rem) {  // macro ops go back as their constituents
         const Macro *mc = macro_of(gi);
         if (!mc) { leftover.push_back(gi); continue; }
@@ -1215,6 +1215,7 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
       while (ordered.size() < 4) ordered.push_back(pads[np++]);
       build_round(R, ordered, round_w[r], kTB, true);
       R.fast = 5;
+      if (p.npauli >= kMaxRounds) throw Error("tile pass: Pauli table overflow");
       p.pauli_slot[p.npauli] = (uint16_t)gates[sr.pauli].slot;
       R.gate[0] = (uint16_t)p.npauli++;
       R.ngates = 0;
@@ -1244,6 +1245,7 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
       R.ngates = (uint8_t)sr.kind;
       for (const auto &pr : sr.pre) {  // (qubit, Pauli op): applied to that qubit's round bit before the gates
         const int bit = (int)(std::find(ordered.begin(), ordered.end(), tile_pos(pr.first)) - ordered.begin());
+        if (p.npauli >= kMaxRounds) throw Error("tile pass: Pauli table overflow");
         p.pauli_slot[p.npauli] = (uint16_t)gates[pr.second].slot;
         R.pre[bit] = (uint8_t)p.npauli++;
         R.npre++;
@@ -1273,6 +1275,7 @@ static bool build_slot_rounds(TilePassParams &p, const std::vector<QGate> &gates
           std::copy(ld, ld + 16, R.eoff_ld);
           for (int x = 0; x < 2; x++) {
             if (mc->inner[x] < 0) continue;
+            if (p.npauli >= kMaxRounds) throw Error("tile pass: Pauli table overflow");
             p.pauli_slot[p.npauli] = (uint16_t)gates[mc->inner[x]].slot;
             R.pre2[2 * k + x] = (uint8_t)p.npauli++;
             R.npre2++;

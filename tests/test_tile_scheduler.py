@@ -200,6 +200,37 @@ _CX_FIRST_CONTROLS = np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 1, 
 _CX_SECOND_CONTROLS = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0]], dtype=np.complex128)
 
 
+def test_noisy_layers_against_the_per_pass_budgets():
+    """Twelve qubits = one tile: everything could ride on one pass, so the per-pass budgets (matrix slots, ops, Pauli
+    table entries -- a round with two folded cx gates adds up to eight) are what cuts the circuit into passes.  Every
+    gate is followed by Paulis with a high hit rate; must equal the oracle."""
+    n, S = 12, 2
+    rng = np.random.default_rng(4242)
+    states = [opgen.random_state(rng, n) for _ in range(S)]
+    ops, nslots = [], 0
+    for layer in range(14):
+        for q in range(n):
+            ops.append((1, [q], opgen.colmajor(opgen.haar_unitary(rng, 2))))
+            ops.append((3, [q], nslots)); nslots += 1
+        perm = rng.permutation(n)
+        for i in range(n // 2):
+            a, b = int(perm[2 * i]), int(perm[2 * i + 1])
+            ops.append((2, [a, b], opgen.colmajor(_CX_FIRST_CONTROLS if (layer + i) % 2 else _CX_SECOND_CONTROLS)))
+            for q in (a, b):
+                ops.append((3, [q], nslots)); nslots += 1
+    codes = rng.choice(4, size=(nslots, S), p=[0.4, 0.2, 0.2, 0.2]).astype(np.uint8)
+    state = np.concatenate(states).astype(np.complex128)
+    passes = selftest(n, state, ops, num_states=S, codes=codes)
+    assert passes >= 8  # 14 layers x (12 + 12 + 6 + 12) ops against 64 ops per pass
+    got = state.reshape(S, -1)
+    for s_i, st in enumerate(states):
+        o = OracleQV(n)
+        o.set_state(st)
+        for k, qs, m in ops:
+            o.apply_matrix(qs, opgen.colmajor(_PAULI[int(codes[m, s_i])].astype(np.complex128)) if k == 3 else m)
+        assert np.max(np.abs(got[s_i] - o.vector())) < 1e-12
+
+
 @pytest.mark.parametrize("seed", [0, 1, 2])
 def test_bare_cx_gates_of_noisy_passes_become_load_permutations(seed):
     """The config-5 pattern: layers of 1-qubit gates and cx gates (either qubit as the control), a sampled Pauli after

@@ -439,7 +439,7 @@ def b200_arm(args):
         from qiskit_aer_b200 import capi
         capi.lib().b200sv_trim()   # the child processes of the head-to-head need the memory the library keeps for reuse
         for key, fn in (("qft30", lambda: extra_qft30(local_rank)), ("noisy20_10k", extra_noisy20),
-                        ("vs_reference_gpu", extra_vs_reference_gpu)):
+                        ("qv33_single_precision", extra_qv33_single), ("vs_reference_gpu", extra_vs_reference_gpu)):
             t0 = time.perf_counter()
             try:
                 extras[key] = fn()
@@ -650,6 +650,23 @@ def extra_noisy20():
             "expval_gpu": [float(x) for x in ev_gpu], "expval_cpu": [float(x) for x in ev_cpu],
             "expval_sigma": [float(x) for x in sigma],
             "expval_max_deviation_sigma": dev_sigma, "expval_within_5_sigma": bool(dev_sigma < 5.0)}
+
+
+def extra_qv33_single():
+    """The headline circuit in single precision (complex64, 64 GiB): the float tile passes, whose rounds run on packed
+    FP32 FMAs (FFMA2).  The same bench in a child process (`--precision single`), two timed steps."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--precision", "single", "--steps", "2", "--warmup", "3",
+           "--no-cpu-baseline", "--no-aer-e2e", "--no-extras"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    if r.returncode != 0 or not line:
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    d = json.loads(line[-1])
+    rf = d.get("roofline", {})
+    return {"workload": d["config"]["workload"], "dtype": d["dtype"], "ms_per_step": d["ms_per_step"],
+            "amp_updates_per_s": d["value"], "hbm_passes": d["config"].get("hbm_passes"),
+            "tile_pass_avg_ms": rf.get("avg_ms"), "hbm_frac": rf.get("frac"), "e2e_ms_per_step": d.get("e2e", {}).get("ms_per_step"),
+            "clocks": d.get("clocks")}
 
 
 def extra_vs_reference_gpu():
